@@ -1,0 +1,643 @@
+// kaarme_gpu.cu -- implementation of the C ABI in include/kaarme_gpu.h (libkaarme_gpu.so, sm_100a only).
+// Host-side orchestration: pinned double-buffered H2D on a copy stream, parse + count kernels on a compute
+// stream, device-resident stream state (no host round trip per batch), chunked export.
+// There is no CPU fallback anywhere in this file: every data-path step is a kernel launch.
+#include "../../include/kaarme_gpu.h"
+
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "kg_count.cuh"
+#include "kg_device.cuh"
+#include "kg_parse.cuh"
+
+#define KG_MAX_W 8
+#define KG_DEFAULT_BATCH (128ull << 20)
+#define KG_MAX_BATCH (1ull << 30)
+
+struct kg_ctx {
+    kg_config cfg;
+    int W = 0;
+    cudaStream_t s_compute = nullptr, s_copy = nullptr;
+    size_t batch_bytes = 0;
+    uint32_t max_tiles = 0;
+    // raw input double buffer
+    uint8_t* d_raw[2] = {nullptr, nullptr};
+    cudaEvent_t ev_raw_free[2] = {nullptr, nullptr};
+    cudaEvent_t ev_copy_done[2] = {nullptr, nullptr};
+    uint8_t* h_stage[2] = {nullptr, nullptr};
+    cudaEvent_t ev_stage_free[2] = {nullptr, nullptr};
+    int raw_idx = 0;
+    // parse scratch
+    u32 *d_tile_hdr_eff = nullptr, *d_tile_hdr_in = nullptr, *d_tile_nbases = nullptr, *d_tile_pend_eff = nullptr,
+        *d_tile_pend_in = nullptr, *d_tile_off = nullptr;
+    u64* d_words = nullptr;
+    u32* d_brk = nullptr;
+    size_t words_cap = 0;  // in words
+    u64* d_carry_words = nullptr;
+    u32* d_carry_brk = nullptr;
+    u32 carry_max_words = 0;
+    KgStream* d_stream = nullptr;
+    KgStats* d_stats = nullptr;
+    KgTable table{nullptr, 0, 0, 0};
+    size_t table_bytes = 0;
+    KgBloom bloom{nullptr, 0, 0};
+    size_t bloom_bytes = 0;
+    uint64_t bloom_m = 0;
+    int pass = 0;
+    bool stream_open = false;
+    bool bloom_done = false;
+    uint64_t new_in_second = 0;
+    // timing
+    cudaEvent_t ev_pass_begin = nullptr, ev_pass_end = nullptr;
+    std::vector<cudaEvent_t> ev_pool;   // [parse_begin, parse_end(=count_begin), count_end] per batch
+    size_t ev_used = 0;
+    uint64_t raw_bytes_pass = 0, bases_pass = 0;
+    uint64_t launches = 0;
+    // export staging
+    u64* d_out_keys[2] = {nullptr, nullptr};
+    u32* d_out_counts[2] = {nullptr, nullptr};
+    u32* d_out_n[2] = {nullptr, nullptr};
+    u64* h_out_keys[2] = {nullptr, nullptr};
+    u32* h_out_counts[2] = {nullptr, nullptr};
+    u32* h_out_n = nullptr;
+    size_t out_chunk = 0;
+    cudaEvent_t ev_out[2] = {nullptr, nullptr};
+    std::string err;
+};
+
+static thread_local std::string g_err;
+
+#define KG_CUDA(ctx, call)                                                                            \
+    do {                                                                                              \
+        cudaError_t e_ = (call);                                                                      \
+        if (e_ != cudaSuccess) {                                                                      \
+            char buf_[512];                                                                           \
+            snprintf(buf_, sizeof(buf_), "%s:%d %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(e_)); \
+            if (ctx) (ctx)->err = buf_;                                                               \
+            g_err = buf_;                                                                             \
+            return e_ == cudaErrorMemoryAllocation ? KG_ENOMEM : KG_ECUDA;                           \
+        }                                                                                             \
+    } while (0)
+
+// ---- host math: functions_math.cpp:53-96 (table sizing is part of the drop-in contract) --------------------
+static uint64_t next_prime3mod4(uint64_t at_least) {
+    uint64_t c = at_least;
+    if (c <= 2) return 2;
+    if ((c & 1) == 0) c += 1;
+    for (;;) {
+        bool prime = true;
+        for (uint64_t d = 3; d * d <= c; d += 2)
+            if (c % d == 0) { prime = false; break; }
+        if (prime && (c % 4 == 3)) return c;
+        c += 2;
+    }
+}
+
+// main.cpp:401-418
+static void bloom_params(uint64_t U, double fpr, uint64_t* m, uint32_t* nh) {
+    double bits_min = (-(double)U * std::log(fpr)) / std::pow(std::log(2.0), 2.0);
+    double h = (bits_min / (double)U) * std::log(2.0);
+    uint64_t p2 = 2;
+    while (p2 < (uint64_t)bits_min) p2 *= 2;
+    *m = p2;
+    *nh = (uint32_t)std::ceil(h);
+}
+
+extern "C" int kg_abi_version(void) { return KG_ABI_VERSION; }
+
+extern "C" const char* kg_strerror(int s) {
+    switch (s) {
+        case KG_OK: return "ok";
+        case KG_EBADARG: return "bad argument or call order";
+        case KG_ECUDA: return "CUDA error / no usable sm_100 device";
+        case KG_ETABLE_FULL: return "hash table is full";
+        case KG_ENCCL: return "NCCL error";
+        case KG_ENOMEM: return "out of device or pinned memory";
+        case KG_ESINK: return "export sink aborted";
+        default: return "unknown status";
+    }
+}
+
+extern "C" const char* kg_last_error(const kg_ctx* ctx) { return ctx ? ctx->err.c_str() : g_err.c_str(); }
+
+extern "C" int kg_device_count(int* count) {
+    if (!count) return KG_EBADARG;
+    *count = 0;
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess) { g_err = cudaGetErrorString(e); cudaGetLastError(); return KG_ECUDA; }
+    for (int i = 0; i < n; i++) {
+        cudaDeviceProp p;
+        if (cudaGetDeviceProperties(&p, i) == cudaSuccess && p.major == 10) (*count)++;
+    }
+    return KG_OK;
+}
+
+extern "C" int kg_host_alloc(size_t bytes, void** out) {
+    if (!out) return KG_EBADARG;
+    cudaError_t e = cudaHostAlloc(out, bytes ? bytes : 1, cudaHostAllocDefault);
+    if (e != cudaSuccess) { g_err = cudaGetErrorString(e); cudaGetLastError(); return KG_ENOMEM; }
+    return KG_OK;
+}
+extern "C" int kg_host_free(void* p) {
+    if (p && cudaFreeHost(p) != cudaSuccess) { cudaGetLastError(); return KG_ECUDA; }
+    return KG_OK;
+}
+
+// -----------------------------------------------------------------------------------------------------------
+static void free_all(kg_ctx* c) {
+    cudaSetDevice(c->cfg.device);
+    if (c->s_compute) cudaStreamSynchronize(c->s_compute);
+    if (c->s_copy) cudaStreamSynchronize(c->s_copy);
+    for (int i = 0; i < 2; i++) {
+        cudaFree(c->d_raw[i]);
+        if (c->h_stage[i]) cudaFreeHost(c->h_stage[i]);
+        if (c->ev_raw_free[i]) cudaEventDestroy(c->ev_raw_free[i]);
+        if (c->ev_copy_done[i]) cudaEventDestroy(c->ev_copy_done[i]);
+        if (c->ev_stage_free[i]) cudaEventDestroy(c->ev_stage_free[i]);
+        cudaFree(c->d_out_keys[i]); cudaFree(c->d_out_counts[i]); cudaFree(c->d_out_n[i]);
+        if (c->h_out_keys[i]) cudaFreeHost(c->h_out_keys[i]);
+        if (c->h_out_counts[i]) cudaFreeHost(c->h_out_counts[i]);
+        if (c->ev_out[i]) cudaEventDestroy(c->ev_out[i]);
+    }
+    if (c->h_out_n) cudaFreeHost(c->h_out_n);
+    cudaFree(c->d_tile_hdr_eff); cudaFree(c->d_tile_hdr_in); cudaFree(c->d_tile_nbases);
+    cudaFree(c->d_tile_pend_eff); cudaFree(c->d_tile_pend_in); cudaFree(c->d_tile_off);
+    cudaFree(c->d_words); cudaFree(c->d_brk); cudaFree(c->d_carry_words); cudaFree(c->d_carry_brk);
+    cudaFree(c->d_stream); cudaFree(c->d_stats); cudaFree(c->table.slots); cudaFree(c->bloom.bits);
+    for (auto e : c->ev_pool) cudaEventDestroy(e);
+    if (c->ev_pass_begin) cudaEventDestroy(c->ev_pass_begin);
+    if (c->ev_pass_end) cudaEventDestroy(c->ev_pass_end);
+    if (c->s_compute) cudaStreamDestroy(c->s_compute);
+    if (c->s_copy) cudaStreamDestroy(c->s_copy);
+    cudaGetLastError();
+}
+
+extern "C" int kg_create(const kg_config* cfg, kg_ctx** out) {
+    if (!cfg || !out) return KG_EBADARG;
+    *out = nullptr;
+    if (cfg->abi_version != KG_ABI_VERSION) { g_err = "abi_version mismatch"; return KG_EBADARG; }
+    if (cfg->k < 1 || (cfg->k + 31) / 32 > KG_MAX_W) { g_err = "k must be in [1, 256]"; return KG_EBADARG; }
+    if (cfg->table_mode != KG_TABLE_PLAIN && cfg->table_mode != KG_TABLE_KAARME) { g_err = "table_mode must be 0 or 2"; return KG_EBADARG; }
+    if (cfg->input_mode != KG_INPUT_FASTA && cfg->input_mode != KG_INPUT_PLAIN) { g_err = "input_mode must be 0 or 2"; return KG_EBADARG; }
+    if (cfg->use_bloom) {
+        if (cfg->expected_unique == 0 || !(cfg->fpr > 0.0 && cfg->fpr < 1.0)) { g_err = "bloom needs expected_unique > 0 and 0 < fpr < 1"; return KG_EBADARG; }
+    } else if (cfg->min_slots == 0) { g_err = "min_slots must be > 0"; return KG_EBADARG; }
+    if (cfg->world < 1 || cfg->rank < 0 || cfg->rank >= cfg->world) { g_err = "bad rank/world"; return KG_EBADARG; }
+
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || cfg->device < 0 || cfg->device >= ndev) {
+        g_err = e != cudaSuccess ? cudaGetErrorString(e) : "device ordinal out of range";
+        cudaGetLastError();
+        return KG_ECUDA;
+    }
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, cfg->device) != cudaSuccess || prop.major != 10) {
+        g_err = "device is not compute capability 10.x (this library ships sm_100a code only; there is no fallback)";
+        cudaGetLastError();
+        return KG_ECUDA;
+    }
+    kg_ctx* c = new kg_ctx();
+    c->cfg = *cfg;
+    c->W = (int)((cfg->k + 31) / 32);
+    c->batch_bytes = cfg->batch_bytes ? cfg->batch_bytes : KG_DEFAULT_BATCH;
+    if (c->batch_bytes > KG_MAX_BATCH) c->batch_bytes = KG_MAX_BATCH;
+    c->batch_bytes = (c->batch_bytes + KG_TILE - 1) / KG_TILE * KG_TILE;
+    c->max_tiles = (uint32_t)(c->batch_bytes / KG_TILE);
+    c->carry_max_words = (u32)c->W + 2;
+    c->words_cap = c->batch_bytes / 32 + c->carry_max_words + 8;
+
+#define KG_TRY(call)                              \
+    do {                                          \
+        int s_ = [&]() -> int { KG_CUDA(c, call); return KG_OK; }(); \
+        if (s_ != KG_OK) { g_err = c->err; free_all(c); delete c; return s_; } \
+    } while (0)
+
+    KG_TRY(cudaSetDevice(cfg->device));
+    KG_TRY(cudaStreamCreateWithFlags(&c->s_compute, cudaStreamNonBlocking));
+    KG_TRY(cudaStreamCreateWithFlags(&c->s_copy, cudaStreamNonBlocking));
+    for (int i = 0; i < 2; i++) {
+        KG_TRY(cudaMalloc(&c->d_raw[i], c->batch_bytes));
+        KG_TRY(cudaEventCreateWithFlags(&c->ev_raw_free[i], cudaEventDisableTiming));
+        KG_TRY(cudaEventCreateWithFlags(&c->ev_copy_done[i], cudaEventDisableTiming));
+        KG_TRY(cudaEventCreateWithFlags(&c->ev_stage_free[i], cudaEventDisableTiming));
+        KG_TRY(cudaEventCreateWithFlags(&c->ev_out[i], cudaEventDisableTiming));
+    }
+    KG_TRY(cudaMalloc(&c->d_tile_hdr_eff, sizeof(u32) * c->max_tiles));
+    KG_TRY(cudaMalloc(&c->d_tile_hdr_in, sizeof(u32) * c->max_tiles));
+    KG_TRY(cudaMalloc(&c->d_tile_nbases, sizeof(u32) * c->max_tiles));
+    KG_TRY(cudaMalloc(&c->d_tile_pend_eff, sizeof(u32) * c->max_tiles));
+    KG_TRY(cudaMalloc(&c->d_tile_pend_in, sizeof(u32) * c->max_tiles));
+    KG_TRY(cudaMalloc(&c->d_tile_off, sizeof(u32) * c->max_tiles));
+    KG_TRY(cudaMalloc(&c->d_words, sizeof(u64) * c->words_cap));
+    KG_TRY(cudaMalloc(&c->d_brk, sizeof(u32) * c->words_cap));
+    KG_TRY(cudaMalloc(&c->d_carry_words, sizeof(u64) * c->carry_max_words));
+    KG_TRY(cudaMalloc(&c->d_carry_brk, sizeof(u32) * c->carry_max_words));
+    KG_TRY(cudaMalloc(&c->d_stream, sizeof(KgStream)));
+    KG_TRY(cudaMalloc(&c->d_stats, sizeof(KgStats)));
+    KG_TRY(cudaMemset(c->d_stream, 0, sizeof(KgStream)));
+    KG_TRY(cudaMemset(c->d_stats, 0, sizeof(KgStats)));
+    KG_TRY(cudaEventCreate(&c->ev_pass_begin));
+    KG_TRY(cudaEventCreate(&c->ev_pass_end));
+    if (cfg->use_bloom) {
+        uint64_t m; uint32_t nh;
+        bloom_params(cfg->expected_unique, cfg->fpr, &m, &nh);
+        if (nh < 1) nh = 1;
+        if (nh > 16) nh = 16;
+        // every shard holds m/world bits per filter (rounded up to whole 256-bit blocks, at least one)
+        uint64_t m_local = (m + (uint64_t)cfg->world - 1) / (uint64_t)cfg->world;
+        uint64_t nblocks = (m_local + 255) / 256;
+        if (nblocks == 0) nblocks = 1;
+        c->bloom_m = m;
+        c->bloom.nblocks = nblocks;
+        c->bloom.nh = nh;
+        c->bloom_bytes = nblocks * 64;
+        KG_TRY(cudaMalloc(&c->bloom.bits, c->bloom_bytes));
+    }
+#undef KG_TRY
+    *out = c;
+    return KG_OK;
+}
+
+extern "C" int kg_destroy(kg_ctx* c) {
+    if (!c) return KG_OK;
+    free_all(c);
+    delete c;
+    return KG_OK;
+}
+
+extern "C" int kg_comm_unique_id(void* id_out) {
+    (void)id_out;
+    g_err = "multi-GPU exchange not built into this library yet";
+    return KG_ENCCL;
+}
+extern "C" int kg_comm_init(kg_ctx* ctx, const void* id, int rank, int world) {
+    (void)id; (void)rank; (void)world;
+    if (ctx) ctx->err = "multi-GPU exchange not built into this library yet";
+    return KG_ENCCL;
+}
+
+// -----------------------------------------------------------------------------------------------------------
+extern "C" int kg_pass_begin(kg_ctx* c, int pass) {
+    if (!c || (pass != KG_PASS_BLOOM && pass != KG_PASS_COUNT)) return KG_EBADARG;
+    if (pass == KG_PASS_BLOOM && !c->cfg.use_bloom) { c->err = "Bloom pass without use_bloom"; return KG_EBADARG; }
+    if (pass == KG_PASS_COUNT && c->cfg.use_bloom && !c->bloom_done) { c->err = "count pass before Bloom pass"; return KG_EBADARG; }
+    KG_CUDA(c, cudaSetDevice(c->cfg.device));
+    c->pass = pass;
+    c->stream_open = false;
+    c->ev_used = 0;
+    c->raw_bytes_pass = 0;
+    KG_CUDA(c, cudaEventRecord(c->ev_pass_begin, c->s_compute));
+    KG_CUDA(c, cudaMemsetAsync(c->d_stats, 0, sizeof(KgStats), c->s_compute));
+    if (pass == KG_PASS_BLOOM) {
+        KG_CUDA(c, cudaMemsetAsync(c->bloom.bits, 0, c->bloom_bytes, c->s_compute));
+        c->bloom_done = false;
+    } else {
+        uint64_t want;
+        if (c->cfg.use_bloom) want = 2 * c->new_in_second;                      // main.cpp:454
+        else want = (c->cfg.min_slots + (uint64_t)c->cfg.world - 1) / (uint64_t)c->cfg.world;
+        uint64_t nslots = next_prime3mod4(want);                                 // parallel_parser.hpp:236
+        u32 stride = kg_slot_stride_words((u32)c->W, c->cfg.table_mode == KG_TABLE_KAARME);
+        size_t bytes = (size_t)nslots * stride * sizeof(u64);
+        if (!c->table.slots || bytes != c->table_bytes) {
+            if (c->table.slots) { KG_CUDA(c, cudaFree(c->table.slots)); c->table.slots = nullptr; }
+            KG_CUDA(c, cudaMalloc(&c->table.slots, bytes ? bytes : 16));
+            c->table_bytes = bytes;
+        }
+        c->table.nslots = nslots;
+        c->table.stride = stride;
+        c->table.kaarme = c->cfg.table_mode == KG_TABLE_KAARME;
+        KG_CUDA(c, cudaMemsetAsync(c->table.slots, 0, bytes, c->s_compute));
+    }
+    return KG_OK;
+}
+
+extern "C" int kg_stream_begin(kg_ctx* c, int starts_in_header) {
+    if (!c || !c->pass) return KG_EBADARG;
+    KG_CUDA(c, cudaSetDevice(c->cfg.device));
+    KgStream s;
+    memset(&s, 0, sizeof(s));
+    s.in_header = starts_in_header ? 1u : 0u;
+    s.pending_break = 1u;  // the first base of a stream starts a run
+    // pageable -> async copy is staged by the runtime before returning, so a stack source is fine
+    KG_CUDA(c, cudaMemcpyAsync(c->d_stream, &s, sizeof(s), cudaMemcpyHostToDevice, c->s_compute));
+    KG_CUDA(c, cudaStreamSynchronize(c->s_compute));
+    c->stream_open = true;
+    return KG_OK;
+}
+
+static cudaEvent_t next_event(kg_ctx* c) {
+    if (c->ev_used == c->ev_pool.size()) {
+        cudaEvent_t e;
+        if (cudaEventCreate(&e) != cudaSuccess) return nullptr;
+        c->ev_pool.push_back(e);
+    }
+    return c->ev_pool[c->ev_used++];
+}
+
+template <int W>
+static void launch_count(kg_ctx* c, const KgCountArgs& a, u32 nthreads_words, int sink) {
+    const u32 block = 256;
+    const u32 grid = (nthreads_words + block - 1) / block;
+    if (grid == 0) return;
+    switch (sink) {
+        case KG_SINK_TABLE: kg_count_kernel<W, KG_SINK_TABLE><<<grid, block, 0, c->s_compute>>>(a); break;
+        case KG_SINK_BLOOM1: kg_count_kernel<W, KG_SINK_BLOOM1><<<grid, block, 0, c->s_compute>>>(a); break;
+        case KG_SINK_BLOOM2: kg_count_kernel<W, KG_SINK_BLOOM2><<<grid, block, 0, c->s_compute>>>(a); break;
+        default: break;
+    }
+    c->launches++;
+}
+
+// parse + count one device-resident batch (n <= batch_bytes, 16-byte aligned) on the compute stream
+static int process_batch(kg_ctx* c, const uint8_t* d_in, size_t n, uint32_t flags) {
+    if (n == 0) return KG_OK;
+    cudaStream_t s = c->s_compute;
+    const u32 ntiles = (u32)((n + KG_TILE - 1) / KG_TILE);
+    const bool fasta = c->cfg.input_mode == KG_INPUT_FASTA;
+    const size_t nwords = n / 32 + c->carry_max_words + 4;
+    cudaEvent_t e0 = next_event(c), e1 = next_event(c), e2 = next_event(c);
+    if (e0) cudaEventRecord(e0, s);
+    KG_CUDA(c, cudaMemsetAsync(c->d_words, 0, sizeof(u64) * nwords, s));
+    KG_CUDA(c, cudaMemsetAsync(c->d_brk, 0, sizeof(u32) * nwords, s));
+    kg_carry_restore<<<1, 32, 0, s>>>(c->d_words, c->d_brk, c->d_stream, c->d_carry_words, c->d_carry_brk, c->carry_max_words);
+    if (fasta) {
+        kg_hdr_summary<<<ntiles, KG_PT, 0, s>>>(d_in, n, c->d_tile_hdr_eff);
+        kg_lww_scan<<<1, 1024, 0, s>>>(c->d_tile_hdr_eff, c->d_tile_hdr_in, ntiles, &c->d_stream->in_header);
+        kg_tile_count<true><<<ntiles, KG_PT, 0, s>>>(d_in, n, c->d_tile_hdr_in, c->d_tile_nbases, c->d_tile_pend_eff);
+        c->launches += 3;
+    } else {
+        kg_tile_count<false><<<ntiles, KG_PT, 0, s>>>(d_in, n, c->d_tile_hdr_in, c->d_tile_nbases, c->d_tile_pend_eff);
+        c->launches += 1;
+    }
+    kg_tile_scan<<<1, 1024, 0, s>>>(c->d_tile_nbases, c->d_tile_off, ntiles, c->d_stream);
+    kg_lww_scan<<<1, 1024, 0, s>>>(c->d_tile_pend_eff, c->d_tile_pend_in, ntiles, &c->d_stream->pending_break);
+    if (fasta)
+        kg_tile_pack<true><<<ntiles, KG_PT, 0, s>>>(d_in, n, c->d_tile_hdr_in, c->d_tile_off, c->d_tile_pend_in, c->d_words, c->d_brk);
+    else
+        kg_tile_pack<false><<<ntiles, KG_PT, 0, s>>>(d_in, n, c->d_tile_hdr_in, c->d_tile_off, c->d_tile_pend_in, c->d_words, c->d_brk);
+    c->launches += 4;
+    if (e1) cudaEventRecord(e1, s);
+    if (!(flags & KG_FEED_CONTEXT)) {
+        KgCountArgs a;
+        a.words = c->d_words; a.brk = c->d_brk; a.st = c->d_stream;
+        a.table = c->table; a.bloom = c->bloom;
+        memset(&a.buckets, 0, sizeof(a.buckets));
+        a.stats = c->d_stats; a.k = c->cfg.k; a.rank = (u32)c->cfg.rank; a.world = (u32)c->cfg.world;
+        int sink = c->pass == KG_PASS_BLOOM ? KG_SINK_BLOOM1 : (c->cfg.use_bloom ? KG_SINK_BLOOM2 : KG_SINK_TABLE);
+        const u32 nthreads = (u32)(n / 32 + c->carry_max_words + 2);   // upper bound on packed words
+        switch (c->W) {
+            case 1: launch_count<1>(c, a, nthreads, sink); break;
+            case 2: launch_count<2>(c, a, nthreads, sink); break;
+            case 3: launch_count<3>(c, a, nthreads, sink); break;
+            case 4: launch_count<4>(c, a, nthreads, sink); break;
+            case 5: launch_count<5>(c, a, nthreads, sink); break;
+            case 6: launch_count<6>(c, a, nthreads, sink); break;
+            case 7: launch_count<7>(c, a, nthreads, sink); break;
+            case 8: launch_count<8>(c, a, nthreads, sink); break;
+        }
+    }
+    kg_carry_save<<<1, 32, 0, s>>>(c->d_words, c->d_brk, c->d_stream, c->d_carry_words, c->d_carry_brk, c->cfg.k, c->carry_max_words);
+    c->launches += 1;
+    if (e2) cudaEventRecord(e2, s);
+    KG_CUDA(c, cudaGetLastError());
+    c->raw_bytes_pass += n;
+    return KG_OK;
+}
+
+static int check_feed(kg_ctx* c) {
+    if (!c || !c->pass) return KG_EBADARG;
+    if (c->pass == KG_PASS_COUNT && !c->table.slots) return KG_EBADARG;
+    if (!c->stream_open) { c->err = "kg_feed before kg_stream_begin"; return KG_EBADARG; }
+    return KG_OK;
+}
+
+extern "C" int kg_feed_device(kg_ctx* c, const void* device_bytes, size_t n, uint32_t flags) {
+    int rc = check_feed(c);
+    if (rc) return rc;
+    if (n == 0) return KG_OK;
+    if (!device_bytes) return KG_EBADARG;
+    KG_CUDA(c, cudaSetDevice(c->cfg.device));
+    const uint8_t* p = (const uint8_t*)device_bytes;
+    const bool aligned = ((uintptr_t)p & 15u) == 0;
+    for (size_t off = 0; off < n; off += c->batch_bytes) {
+        size_t len = n - off < c->batch_bytes ? n - off : c->batch_bytes;
+        if (aligned) {
+            rc = process_batch(c, p + off, len, flags);
+        } else {
+            int idx = c->raw_idx; c->raw_idx ^= 1;
+            KG_CUDA(c, cudaMemcpyAsync(c->d_raw[idx], p + off, len, cudaMemcpyDeviceToDevice, c->s_compute));
+            rc = process_batch(c, c->d_raw[idx], len, flags);
+        }
+        if (rc) return rc;
+    }
+    return KG_OK;
+}
+
+extern "C" int kg_feed(kg_ctx* c, const uint8_t* bytes, size_t n, uint32_t flags) {
+    int rc = check_feed(c);
+    if (rc) return rc;
+    if (n == 0) return KG_OK;
+    if (!bytes) return KG_EBADARG;
+    KG_CUDA(c, cudaSetDevice(c->cfg.device));
+    cudaPointerAttributes attr;
+    bool pinned = false;
+    if (cudaPointerGetAttributes(&attr, bytes) == cudaSuccess) {
+        if (attr.type == cudaMemoryTypeDevice) return kg_feed_device(c, bytes, n, flags);
+        pinned = attr.type == cudaMemoryTypeHost;
+    } else {
+        cudaGetLastError();
+    }
+    for (size_t off = 0; off < n; off += c->batch_bytes) {
+        size_t len = n - off < c->batch_bytes ? n - off : c->batch_bytes;
+        const int idx = c->raw_idx; c->raw_idx ^= 1;
+        // the compute stream must be done with this raw buffer (two batches ago)
+        KG_CUDA(c, cudaEventSynchronize(c->ev_raw_free[idx]));
+        const uint8_t* src = bytes + off;
+        if (!pinned) {
+            if (!c->h_stage[idx]) KG_CUDA(c, cudaHostAlloc((void**)&c->h_stage[idx], c->batch_bytes, cudaHostAllocDefault));
+            KG_CUDA(c, cudaEventSynchronize(c->ev_stage_free[idx]));
+            memcpy(c->h_stage[idx], src, len);
+            src = c->h_stage[idx];
+        }
+        KG_CUDA(c, cudaMemcpyAsync(c->d_raw[idx], src, len, cudaMemcpyHostToDevice, c->s_copy));
+        KG_CUDA(c, cudaEventRecord(c->ev_copy_done[idx], c->s_copy));
+        if (!pinned) KG_CUDA(c, cudaEventRecord(c->ev_stage_free[idx], c->s_copy));
+        KG_CUDA(c, cudaStreamWaitEvent(c->s_compute, c->ev_copy_done[idx], 0));
+        rc = process_batch(c, c->d_raw[idx], len, flags);
+        if (rc) return rc;
+        KG_CUDA(c, cudaEventRecord(c->ev_raw_free[idx], c->s_compute));
+        // the caller owns `bytes` again when we return: wait for the H2D copy (compute keeps running)
+        if (pinned) KG_CUDA(c, cudaEventSynchronize(c->ev_copy_done[idx]));
+    }
+    return KG_OK;
+}
+
+extern "C" int kg_pass_end(kg_ctx* c, kg_pass_stats* out) {
+    if (!c || !c->pass) return KG_EBADARG;
+    KG_CUDA(c, cudaSetDevice(c->cfg.device));
+    KG_CUDA(c, cudaEventRecord(c->ev_pass_end, c->s_compute));
+    KG_CUDA(c, cudaStreamSynchronize(c->s_compute));
+    KgStats st;
+    KG_CUDA(c, cudaMemcpy(&st, c->d_stats, sizeof(st), cudaMemcpyDeviceToHost));
+    if (c->pass == KG_PASS_BLOOM) {
+        c->new_in_second = st.new_in_second;
+        c->bloom_done = true;
+    }
+    if (out) {
+        memset(out, 0, sizeof(*out));
+        out->input_kmers = st.input_kmers;
+        out->inserted_kmers = st.inserted;
+        out->distinct = st.distinct;
+        out->table_slots = c->pass == KG_PASS_COUNT ? c->table.nslots : 0;
+        out->new_in_first = st.new_in_first;
+        out->new_in_second = st.new_in_second;
+        out->bloom_bits = c->bloom_m;
+        out->bloom_hashes = c->bloom.nh;
+        out->raw_bytes = c->raw_bytes_pass;
+        float ms = 0;
+        cudaEventElapsedTime(&ms, c->ev_pass_begin, c->ev_pass_end);
+        out->device_ms = ms;
+        for (size_t i = 0; i + 3 <= c->ev_used; i += 3) {
+            float a = 0, b = 0;
+            if (cudaEventElapsedTime(&a, c->ev_pool[i], c->ev_pool[i + 1]) == cudaSuccess) out->parse_ms += a;
+            if (cudaEventElapsedTime(&b, c->ev_pool[i + 1], c->ev_pool[i + 2]) == cudaSuccess) out->count_ms += b;
+        }
+        cudaGetLastError();
+    }
+    const int pass = c->pass;
+    c->pass = 0;
+    c->stream_open = false;
+    if (pass == KG_PASS_COUNT && st.table_full) { c->err = "Hash table is full"; c->pass = 0; return KG_ETABLE_FULL; }
+    return KG_OK;
+}
+
+extern "C" int kg_compact(kg_ctx* c, kg_compact_stats* stats) {
+    (void)stats;
+    if (!c) return KG_EBADARG;
+    c->err = "kg_compact: not built yet";
+    return KG_EBADARG;
+}
+
+// -----------------------------------------------------------------------------------------------------------
+template <int W>
+static void launch_export(kg_ctx* c, u64 b, u64 e, uint64_t min_ab, int count_mode, int buf) {
+    const u32 block = 256;
+    const u32 grid = (u32)((e - b + block - 1) / block);
+    kg_export_kernel<W><<<grid, block, 0, c->s_compute>>>(c->table, b, e, min_ab, count_mode, c->cfg.table_mode,
+                                                        c->d_out_keys[buf], c->d_out_counts[buf], c->d_out_n[buf]);
+    c->launches++;
+}
+
+extern "C" int kg_export(kg_ctx* c, uint64_t min_abundance, int count_mode, kg_sink_fn sink, void* user) {
+    if (!c || !sink || !c->table.slots) return KG_EBADARG;
+    if (min_abundance == 0) return KG_OK;  // parallel_parser.hpp:860-861
+    KG_CUDA(c, cudaSetDevice(c->cfg.device));
+    const int W = c->W;
+    if (!c->out_chunk) {
+        c->out_chunk = (16u << 20) / (size_t)W;
+        for (int i = 0; i < 2; i++) {
+            KG_CUDA(c, cudaMalloc(&c->d_out_keys[i], c->out_chunk * W * sizeof(u64)));
+            KG_CUDA(c, cudaMalloc(&c->d_out_counts[i], c->out_chunk * sizeof(u32)));
+            KG_CUDA(c, cudaMalloc(&c->d_out_n[i], sizeof(u32)));
+            KG_CUDA(c, cudaHostAlloc((void**)&c->h_out_keys[i], c->out_chunk * W * sizeof(u64), cudaHostAllocDefault));
+            KG_CUDA(c, cudaHostAlloc((void**)&c->h_out_counts[i], c->out_chunk * sizeof(u32), cudaHostAllocDefault));
+        }
+        KG_CUDA(c, cudaHostAlloc((void**)&c->h_out_n, 2 * sizeof(u32), cudaHostAllocDefault));
+    }
+    const u64 nslots = c->table.nslots;
+    const u64 nchunks = (nslots + c->out_chunk - 1) / c->out_chunk;
+    auto finish = [&](u64 i) -> int {
+        const int b = (int)(i & 1);
+        KG_CUDA(c, cudaEventSynchronize(c->ev_out[b]));
+        const u32 n = c->h_out_n[b];
+        if (n) {
+            KG_CUDA(c, cudaMemcpyAsync(c->h_out_keys[b], c->d_out_keys[b], (size_t)n * W * sizeof(u64), cudaMemcpyDeviceToHost, c->s_copy));
+            KG_CUDA(c, cudaMemcpyAsync(c->h_out_counts[b], c->d_out_counts[b], (size_t)n * sizeof(u32), cudaMemcpyDeviceToHost, c->s_copy));
+            KG_CUDA(c, cudaStreamSynchronize(c->s_copy));
+            if (sink(user, (const uint64_t*)c->h_out_keys[b], (const uint32_t*)c->h_out_counts[b], n) != 0) return KG_ESINK;
+        }
+        return KG_OK;
+    };
+    for (u64 i = 0; i < nchunks; i++) {
+        const int b = (int)(i & 1);
+        const u64 sb = i * c->out_chunk, se = sb + c->out_chunk < nslots ? sb + c->out_chunk : nslots;
+        KG_CUDA(c, cudaMemsetAsync(c->d_out_n[b], 0, sizeof(u32), c->s_compute));
+        switch (W) {
+            case 1: launch_export<1>(c, sb, se, min_abundance, count_mode, b); break;
+            case 2: launch_export<2>(c, sb, se, min_abundance, count_mode, b); break;
+            case 3: launch_export<3>(c, sb, se, min_abundance, count_mode, b); break;
+            case 4: launch_export<4>(c, sb, se, min_abundance, count_mode, b); break;
+            case 5: launch_export<5>(c, sb, se, min_abundance, count_mode, b); break;
+            case 6: launch_export<6>(c, sb, se, min_abundance, count_mode, b); break;
+            case 7: launch_export<7>(c, sb, se, min_abundance, count_mode, b); break;
+            case 8: launch_export<8>(c, sb, se, min_abundance, count_mode, b); break;
+        }
+        KG_CUDA(c, cudaMemcpyAsync(&c->h_out_n[b], c->d_out_n[b], sizeof(u32), cudaMemcpyDeviceToHost, c->s_compute));
+        KG_CUDA(c, cudaEventRecord(c->ev_out[b], c->s_compute));
+        if (i > 0) { int rc = finish(i - 1); if (rc) { cudaStreamSynchronize(c->s_compute); return rc; } }
+    }
+    if (nchunks > 0) { int rc = finish(nchunks - 1); if (rc) return rc; }
+    KG_CUDA(c, cudaGetLastError());
+    return KG_OK;
+}
+
+extern "C" int kg_table_info(const kg_ctx* c, uint64_t* slots, uint32_t* slot_bytes, uint32_t* key_words) {
+    if (!c) return KG_EBADARG;
+    if (slots) *slots = c->table.nslots;
+    if (slot_bytes) *slot_bytes = c->table.stride * 8;
+    if (key_words) *key_words = (uint32_t)c->W;
+    return KG_OK;
+}
+
+extern "C" int kg_launch_count(const kg_ctx* c, uint64_t* launches) {
+    if (!c || !launches) return KG_EBADARG;
+    *launches = c->launches;
+    return KG_OK;
+}
+
+// ---- random 32-byte-sector atomic ceiling (roofline denominator for the insert kernel) ---------------------
+__global__ void kg_atomic_ceiling_kernel(u32* region, u64 nsectors, u64 n_ops, u64 seed) {
+    const u64 tid = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    const u64 stride = (u64)gridDim.x * blockDim.x;
+    for (u64 i = tid; i < n_ops; i += stride) {
+        u64 h = kg_fmix64(i * 0x9E3779B97F4A7C15ULL + seed);
+        u64 sector = __umul64hi(h, nsectors);
+        atomicAdd(region + sector * 8, 1u);   // one RED per random 32-byte sector
+    }
+}
+
+extern "C" int kg_atomic_ceiling(int device, uint64_t region_bytes, uint64_t n_ops, int reps, double* sectors_per_s) {
+    if (!sectors_per_s || region_bytes < 32 || n_ops == 0) return KG_EBADARG;
+    kg_ctx* c = nullptr;
+    KG_CUDA(c, cudaSetDevice(device));
+    u32* region = nullptr;
+    KG_CUDA(c, cudaMalloc(&region, region_bytes));
+    KG_CUDA(c, cudaMemset(region, 0, region_bytes));
+    cudaEvent_t a, b;
+    KG_CUDA(c, cudaEventCreate(&a));
+    KG_CUDA(c, cudaEventCreate(&b));
+    cudaDeviceProp prop;
+    KG_CUDA(c, cudaGetDeviceProperties(&prop, device));
+    const u32 grid = prop.multiProcessorCount * 8;
+    double best = 0;
+    for (int r = 0; r < (reps < 1 ? 1 : reps) + 1; r++) {
+        KG_CUDA(c, cudaEventRecord(a));
+        kg_atomic_ceiling_kernel<<<grid, 256>>>(region, region_bytes / 32, n_ops, (u64)r * 7919u);
+        KG_CUDA(c, cudaEventRecord(b));
+        KG_CUDA(c, cudaEventSynchronize(b));
+        float ms = 0;
+        KG_CUDA(c, cudaEventElapsedTime(&ms, a, b));
+        if (r > 0 && ms > 0) { double v = (double)n_ops / (ms * 1e-3); if (v > best) best = v; }
+    }
+    cudaEventDestroy(a); cudaEventDestroy(b);
+    cudaFree(region);
+    *sectors_per_s = best;
+    return KG_OK;
+}

@@ -1,0 +1,307 @@
+// kg_count.cuh -- K1b/K3 "window + insert": rolling forward / reverse-complement window over the packed
+// base stream, canonical selection, hash, and find-or-insert into the count table.
+//
+// Replaces, per base of input:
+//   window shift + reverse complement + lexicographic min   parallel_parser.hpp:643-702 (-m 0),
+//                                                           kmer_factory.cpp:172-239 (-m 2 / Bloom)
+//   rolling hash                                            hash_functions.cpp:102-232
+//   find-or-insert + count                                  parallel_parser.hpp:711-789,
+//                                                           kmer_hash_table.cpp:2207-2567 (process_kmer_MT)
+// Mapping: one thread per packed word (32 consecutive k-mer END positions).  The thread rebuilds the
+// window of the k-1 preceding bases straight from the packed words (O(W) funnel shifts + one bit-reversal
+// for the reverse complement) instead of warming up base by base, then rolls 32 steps.
+#pragma once
+#include "kg_device.cuh"
+
+enum KgSink : int {
+    KG_SINK_TABLE = 0,   // insert into the local table
+    KG_SINK_BLOOM1 = 1,  // Bloom pass 1: test-and-set F1/F2
+    KG_SINK_BLOOM2 = 2,  // Bloom pass 2: insert only if F2 admits
+    KG_SINK_BUCKET = 3,  // multi-GPU: append (key) to the owner's send bucket
+    KG_SINK_BUCKET_BLOOM = 4
+};
+
+// blocked double Bloom filter: block = 64 B = [F1: 256 bits][F2: 256 bits]; all nh bits of a k-mer fall in
+// one block, so a test touches one 32-byte sector per filter (double_bloomfilter.hpp:303-413 touches nh
+// random bytes per filter).  m = bits per filter (main.cpp:404-410), nblocks = m / 256.
+struct KgBloom {
+    u32* bits;     // nblocks * 16 words
+    u64 nblocks;
+    u32 nh;        // ceil(h) (main.cpp:417)
+};
+
+struct KgBuckets {
+    u64* keys;        // world * capacity * W words
+    u32* fill;        // world counters
+    u32 capacity;     // keys per destination
+    u32 world;
+    u32 overflow;     // unused (kernel reports through KgStats.table_full)
+};
+
+// the nh bit positions of a k-mer inside its 256-bit block, as 8 x 32-bit masks
+__device__ __forceinline__ void kg_bloom_masks(u64 h, u32 nh, u32 (&mask)[8]) {
+#pragma unroll
+    for (int i = 0; i < 8; i++) mask[i] = 0;
+    u64 g = kg_fmix64(h ^ 0xA24BAED4963EE407ULL);
+    for (u32 i = 0; i < nh; i++) {
+        if ((i & 7u) == 7u) g = kg_fmix64(g + 0x9FB21C651E98DF25ULL);
+        u32 b = (u32)(g >> (8 * (i & 7u))) & 255u;
+        // (i&7)==7 consumed the refreshed g's low byte; fine: all bytes of g are well mixed
+#pragma unroll
+        for (int w = 0; w < 8; w++) if ((b >> 5) == (u32)w) mask[w] |= 1u << (b & 31u);
+    }
+}
+__device__ __forceinline__ u64 kg_bloom_block(u64 h, u64 nblocks) {
+    return __umul64hi(kg_fmix64(h + 0x632BE59BD9B4E019ULL), nblocks);
+}
+
+// pass 1 (insertion_process, double_bloomfilter.hpp:371-413) on the blocked layout.
+__device__ __forceinline__ void kg_bloom_insert(const KgBloom& bf, u64 h, u32& new1, u32& new2) {
+    u32 mask[8];
+    kg_bloom_masks(h, bf.nh, mask);
+    u32* blk = bf.bits + kg_bloom_block(h, bf.nblocks) * 16;
+    // F2 first: "in second? done"
+    bool in2 = true;
+    u32 miss2[8];
+    {
+        uint4 a = __ldcg(reinterpret_cast<const uint4*>(blk + 8));
+        uint4 b = __ldcg(reinterpret_cast<const uint4*>(blk + 12));
+        u32 cur[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+#pragma unroll
+        for (int w = 0; w < 8; w++) { miss2[w] = mask[w] & ~cur[w]; in2 = in2 && (miss2[w] == 0); }
+    }
+    if (in2) return;
+    bool in1 = true;
+    u32 miss1[8];
+    {
+        uint4 a = __ldcg(reinterpret_cast<const uint4*>(blk));
+        uint4 b = __ldcg(reinterpret_cast<const uint4*>(blk + 4));
+        u32 cur[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+#pragma unroll
+        for (int w = 0; w < 8; w++) { miss1[w] = mask[w] & ~cur[w]; in1 = in1 && (miss1[w] == 0); }
+    }
+    bool to_second = in1;
+    if (!in1) {
+        // set F1; "mine" = I flipped every bit that was missing when I looked
+        bool mine = true;
+#pragma unroll
+        for (int w = 0; w < 8; w++)
+            if (miss1[w]) { u32 old = atomicOr(blk + w, miss1[w]); mine = mine && ((old & miss1[w]) == 0); }
+        if (mine) new1++;
+        else to_second = true;  // somebody raced me on a bit: the k-mer was seen twice concurrently (:401-411)
+    }
+    if (to_second) {
+        bool mine = true;
+#pragma unroll
+        for (int w = 0; w < 8; w++)
+            if (miss2[w]) { u32 old = atomicOr(blk + 8 + w, miss2[w]); mine = mine && ((old & miss2[w]) == 0); }
+        if (mine) new2++;
+    }
+}
+
+// pass 2 admission (second_contains, double_bloomfilter.hpp:319-337; parallel_parser.hpp:2021-2026)
+__device__ __forceinline__ bool kg_bloom_admits(const KgBloom& bf, u64 h) {
+    u32 mask[8];
+    kg_bloom_masks(h, bf.nh, mask);
+    const u32* blk = bf.bits + kg_bloom_block(h, bf.nblocks) * 16 + 8;
+    uint4 a = __ldg(reinterpret_cast<const uint4*>(blk));
+    uint4 b = __ldg(reinterpret_cast<const uint4*>(blk + 4));
+    u32 cur[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+    bool ok = true;
+#pragma unroll
+    for (int w = 0; w < 8; w++) ok = ok && ((mask[w] & ~cur[w]) == 0);
+    return ok;
+}
+
+struct KgCountArgs {
+    const u64* words;
+    const u32* brk;
+    const KgStream* st;
+    KgTable table;
+    KgBloom bloom;
+    KgBuckets buckets;
+    KgStats* stats;
+    u32 k;
+    u32 rank, world;
+};
+
+template <int W>
+__device__ __forceinline__ void kg_bucket_append(const KgBuckets& b, u32 owner, const u64 (&key)[W], KgStats* stats) {
+    u32 pos = atomicAdd(b.fill + owner, 1u);
+    if (pos >= b.capacity) { stats->table_full = 2; return; }
+    u64* dst = b.keys + ((u64)owner * b.capacity + pos) * W;
+#pragma unroll
+    for (int i = 0; i < W; i++) dst[i] = key[i];
+}
+
+template <int W, int SINK>
+__global__ void __launch_bounds__(256) kg_count_kernel(KgCountArgs a) {
+    const u32 T = a.st->total_bases;
+    const u32 C = a.st->carry_bases;
+    const u32 t = blockIdx.x * blockDim.x + threadIdx.x;
+    u32 n_windows = 0, n_new = 0, n_ins = 0, n_b1 = 0, n_b2 = 0, n_rej = 0;
+    bool full = false;
+    if ((u64)t * 32u < T) {
+        const KgKGeom g = kg_geom(a.k);
+        const u32 k = a.k;
+        const u64 myword = a.words[t];
+        const u32 mybrk = a.brk[t];
+        const u32 nvalid = min(32u, T - t * 32u);
+        // Quick reject: can any window end inside this word?  Needs run >= k at some position.
+        // run before this word
+        u32 run = 0;
+        {
+            bool found = false;
+#pragma unroll 1
+            for (int i = 1; i <= W + 1 && !found; i++) {
+                if ((int)t - i < 0) { found = true; break; }   // position 0 carries a break bit, handled below
+                u32 b = a.brk[t - i];
+                if (b) { run += __ffs(b) - 1 + 1; found = true; }   // lowest set bit = most recent base
+                else run += 32;
+            }
+            // when the scan ran off the start of the stream, `run` already equals 32*t (position 0 has its bit)
+        }
+        KgKmerWindow<W> w;
+        // forward window = the k-1 bases before this word, right-aligned
+#pragma unroll
+        for (int i = 0; i < W; i++) {
+            int src = (int)t - 1 - i;
+            w.f[W - 1 - i] = src >= 0 ? a.words[src] : 0ULL;
+        }
+        {
+            // keep only 2(k-1) bits
+            const u32 keep = 2 * (k - 1);             // bits
+            const u32 topkeep = keep > 64u * (W - 1) ? keep - 64u * (W - 1) : 0u;   // bits kept in word 0
+            w.f[0] = topkeep == 0 ? 0ULL : (topkeep >= 64 ? w.f[0] : (w.f[0] & ((1ULL << topkeep) - 1)));
+        }
+        kg_revcomp<W>(w.f, w.r, g);
+        const u32 base_pos = t * 32u;
+#pragma unroll 1
+        for (u32 j = 0; j < nvalid; j++) {
+            const u32 c = (u32)(myword >> (62 - 2 * j)) & 3u;
+            kg_push<W>(w, g, c);
+            run = ((mybrk >> (31 - j)) & 1u) ? 1u : run + 1u;
+            if (run >= k && base_pos + j >= C) {
+                n_windows++;
+                u64 key[W];
+                const bool fwd = kg_forward_is_canonical<W>(w);
+#pragma unroll
+                for (int i = 0; i < W; i++) key[i] = fwd ? w.f[i] : w.r[i];
+                const u64 h = kg_hash_key<W>(key);
+                if (SINK == KG_SINK_BLOOM1) {
+                    if (a.world > 1) {
+                        // (multi-GPU Bloom pass goes through buckets; not this sink)
+                    }
+                    kg_bloom_insert(a.bloom, h, n_b1, n_b2);
+                } else if (SINK == KG_SINK_BUCKET) {
+                    kg_bucket_append<W>(a.buckets, kg_owner(h, a.world), key, a.stats);
+                } else {
+                    if (SINK == KG_SINK_BLOOM2) {
+                        if (!kg_bloom_admits(a.bloom, h)) { n_rej++; continue; }
+                    }
+                    bool is_new;
+                    u64 slot = kg_table_add<W>(a.table, key, h, is_new);
+                    if (slot == ~0ULL) full = true;
+                    else { n_ins++; n_new += is_new ? 1u : 0u; }
+                }
+            }
+        }
+    }
+    // statistics: warp-reduce, one atomic per warp and counter
+    const u32 lane = threadIdx.x & 31u;
+#define KG_WARP_ADD(var, field)                                                   \
+    {                                                                             \
+        u32 v_ = var;                                                             \
+        for (int d = 16; d; d >>= 1) v_ += __shfl_xor_sync(0xffffffffu, v_, d);   \
+        if (lane == 0 && v_) atomicAdd(&a.stats->field, (u64)v_);                 \
+    }
+    KG_WARP_ADD(n_windows, input_kmers)
+    if (SINK == KG_SINK_TABLE || SINK == KG_SINK_BLOOM2) {
+        KG_WARP_ADD(n_ins, inserted)
+        KG_WARP_ADD(n_new, distinct)
+    }
+    if (SINK == KG_SINK_BLOOM1) {
+        KG_WARP_ADD(n_b1, new_in_first)
+        KG_WARP_ADD(n_b2, new_in_second)
+    }
+    if (SINK == KG_SINK_BLOOM2) { KG_WARP_ADD(n_rej, bloom_rejected) }
+    if (full) a.stats->table_full = 1;
+}
+
+// insert keys that arrived from other shards (multi-GPU), one thread per key
+template <int W, int SINK>
+__global__ void __launch_bounds__(256) kg_insert_keys_kernel(const u64* __restrict__ keys, u64 n, KgTable table,
+                                                             KgBloom bloom, KgStats* stats) {
+    const u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    u32 n_new = 0, n_ins = 0, n_b1 = 0, n_b2 = 0, n_rej = 0;
+    bool full = false;
+    if (i < n) {
+        u64 key[W];
+#pragma unroll
+        for (int j = 0; j < W; j++) key[j] = keys[i * W + j];
+        const u64 h = kg_hash_key<W>(key);
+        if (SINK == KG_SINK_BLOOM1) {
+            kg_bloom_insert(bloom, h, n_b1, n_b2);
+        } else {
+            bool admit = true;
+            if (SINK == KG_SINK_BLOOM2) admit = kg_bloom_admits(bloom, h);
+            if (admit) {
+                bool is_new;
+                u64 slot = kg_table_add<W>(table, key, h, is_new);
+                if (slot == ~0ULL) full = true;
+                else { n_ins++; n_new += is_new ? 1u : 0u; }
+            } else n_rej++;
+        }
+    }
+    const u32 lane = threadIdx.x & 31u;
+#define KG_WARP_ADD2(var, field)                                                  \
+    {                                                                             \
+        u32 v_ = var;                                                             \
+        for (int d = 16; d; d >>= 1) v_ += __shfl_xor_sync(0xffffffffu, v_, d);   \
+        if (lane == 0 && v_) atomicAdd(&stats->field, (u64)v_);                   \
+    }
+    KG_WARP_ADD2(n_ins, inserted)
+    KG_WARP_ADD2(n_new, distinct)
+    KG_WARP_ADD2(n_b1, new_in_first)
+    KG_WARP_ADD2(n_b2, new_in_second)
+    KG_WARP_ADD2(n_rej, bloom_rejected)
+    if (full) stats->table_full = 1;
+}
+
+// ---- K5 export: stream-compact slots whose reported count >= min_abundance -------------------------------
+// (replaces the table scan of write_kmers, kmer_hash_table.cpp:2013-2050)
+__device__ __forceinline__ u32 kg_reported_count(u32 n, int count_mode, int table_mode) {
+    if (count_mode == 0) return n;
+    if (table_mode == 0) return n & 0xFFFFu;          // uint16 wrap, parallel_parser.hpp:720-734
+    return n > 16383u ? 16383u : n;                   // 14-bit saturation, kmer.cpp:699-714
+}
+
+template <int W>
+__global__ void __launch_bounds__(256) kg_export_kernel(KgTable table, u64 slot_begin, u64 slot_end, u64 min_abundance,
+                                                        int count_mode, int table_mode, u64* __restrict__ out_keys,
+                                                        u32* __restrict__ out_counts, u32* out_n) {
+    const u64 s = slot_begin + (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    bool emit = false;
+    u32 rep = 0;
+    const u64* p = nullptr;
+    if (s < slot_end) {
+        p = table.slots + s * table.stride;
+        u32 n = (u32)p[0];
+        if (n != 0 && n != KG_LOCKED) {
+            rep = kg_reported_count(n, count_mode, table_mode);
+            emit = min_abundance > 0 && (u64)rep >= min_abundance;
+        }
+    }
+    const u32 ballot = __ballot_sync(0xffffffffu, emit);
+    if (ballot == 0) return;
+    const u32 lane = threadIdx.x & 31u;
+    u32 base = 0;
+    if (lane == 0) base = atomicAdd(out_n, (u32)__popc(ballot));
+    base = __shfl_sync(0xffffffffu, base, 0);
+    if (emit) {
+        const u32 idx = base + __popc(ballot & ((1u << lane) - 1u));
+#pragma unroll
+        for (int i = 0; i < W; i++) out_keys[(u64)idx * W + i] = p[1 + i];
+        out_counts[idx] = rep;
+    }
+}

@@ -1,0 +1,230 @@
+// kg_device.cuh -- device-side building blocks shared by the kernels of libkaarme_gpu.so (sm_100a).
+//
+// Data layout in HBM:
+//   packed base stream   u64 words, 32 bases per word, first base in bits 63:62 (so numeric order ==
+//                        lexicographic order, as in KMerFactoryCanonical2BC, kmer_factory.cpp:172-205)
+//   break mask           u32 words, bit (31 - i%32) of word i/32 set <=> base i starts a new run
+//                        (after a header, a non-ACGT byte, or the start of a stream)
+//   count table          open addressing, linear probing (+1 slot, what parallel_parser.hpp:711-789
+//                        effectively does), slot = [meta u64][key words W][first-pos u64 if Kaarme],
+//                        stride padded to 16 B (W=1) or a multiple of 32 B so a probe touches whole sectors
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+typedef unsigned long long u64;
+typedef unsigned int u32;
+
+#define KG_LOCKED 0xFFFFFFFFu
+
+// ---- statistics / error word written by the kernels -------------------------------------------------
+struct KgStats {
+    u64 input_kmers;     // complete windows seen
+    u64 inserted;        // occurrences inserted into the local table
+    u64 distinct;        // slots claimed
+    u64 new_in_first;    // Bloom counters (double_bloomfilter.hpp:389-396)
+    u64 new_in_second;
+    u64 bloom_rejected;  // pass 2: windows not admitted
+    u32 table_full;      // an insert exhausted the probe budget
+    u32 pad;
+};
+
+// ---- stream state carried from batch to batch (lives in device memory; no host round trip) ----------
+struct KgStream {
+    u32 in_header;     // header state at the first byte of the next batch (text_chunk::broken_header)
+    u32 pending_break; // a break event happened after the last packed base
+    u32 carry_bases;   // bases at the head of the packed stream that belong to the previous batch (C)
+    u32 total_bases;   // bases in the packed stream of the current batch, carry included (T)
+    u64 bases_seen;    // bases packed so far in this stream, before the current batch (global ordinal base)
+};
+
+// ---- 64-bit mixers ---------------------------------------------------------------------------------
+__device__ __forceinline__ u64 kg_fmix64(u64 x) {
+    x ^= x >> 33; x *= 0xff51afd7ed558ccdULL;
+    x ^= x >> 33; x *= 0xc4ceb9fe1a85ec53ULL;
+    x ^= x >> 33;
+    return x;
+}
+
+// hash of a canonical key (replaces RollingHasherDual, hash_functions.cpp:102-232: the parity contract
+// is the k-mer multiset, not the slot order, so any well-mixed function of the canonical key serves)
+template <int W>
+__device__ __forceinline__ u64 kg_hash_key(const u64 (&key)[W]) {
+    u64 h = 0x9E3779B97F4A7C15ULL;
+#pragma unroll
+    for (int i = 0; i < W; i++) h = kg_fmix64(h ^ key[i]) + 0x9E3779B97F4A7C15ULL * (u64)(i + 1);
+    return h;
+}
+
+// owner shard of a hash (multi-GPU) and slot within the shard use decorrelated bits
+__device__ __forceinline__ u32 kg_owner(u64 h, u32 world) { return (u32)__umul64hi(h, (u64)world); }
+__device__ __forceinline__ u64 kg_slot(u64 h, u64 nslots) {
+    return __umul64hi(h * 0xD6E8FEB86659FD93ULL + 0x2545F4914F6CDD1DULL, nslots);
+}
+
+// ---- strong (L2-coherent, L1-bypassing) accesses used on the table -----------------------------------
+__device__ __forceinline__ u32 kg_ld_u32(const void* p) {
+    u32 v;
+    asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ u64 kg_ld_u64(const void* p) {
+    u64 v;
+    asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void kg_ld_v2(const void* p, u64& a, u64& b) {
+    asm volatile("ld.relaxed.gpu.global.v2.u64 {%0, %1}, [%2];" : "=l"(a), "=l"(b) : "l"(p) : "memory");
+}
+__device__ __forceinline__ void kg_st_u64(void* p, u64 v) {
+    asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ void kg_st_release_u32(void* p, u32 v) {
+    asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
+// ---- table geometry ----------------------------------------------------------------------------------
+struct KgTable {
+    u64* slots;      // nslots * stride words
+    u64 nslots;      // next_prime3mod4(...)
+    u32 stride;      // u64 words per slot
+    u32 kaarme;      // slot carries a first-occurrence word at [1+W]
+};
+
+__host__ __device__ inline u32 kg_slot_stride_words(u32 W, bool kaarme) {
+    u32 need = 1 + W + (kaarme ? 1u : 0u);
+    if (need <= 2) return 2;           // 16 B: two slots per 32-byte sector
+    return (need + 3u) & ~3u;          // multiple of 32 B
+}
+
+// find-or-insert `key`, count += 1.  Returns slot index, or ~0 when the probe budget is exhausted.
+//   meta low 32 bits: 0 = empty, KG_LOCKED = being written, otherwise the occurrence count.
+//   Writer: CAS 0->LOCKED, store key words, release-store count=1.  Reader: meta first, then (program- and
+//   data-dependent) the key words, all as L2-coherent accesses; key words never change once published.
+template <int W>
+__device__ __forceinline__ u64 kg_table_add(const KgTable& t, const u64 (&key)[W], u64 h, bool& is_new) {
+    u64 slot = kg_slot(h, t.nslots);
+    is_new = false;
+    const u64 max_probe = t.nslots < 4096 ? t.nslots : 4096;
+    for (u64 probe = 0; probe < max_probe; probe++) {
+        u64* p = t.slots + slot * t.stride;
+        u64 meta, k0;
+        kg_ld_v2(p, meta, k0);                 // one 16-byte access: meta and key word 0 together
+        u32 m = (u32)meta;
+        bool k0_valid = true;                  // k0 was read in the same access that saw a published meta
+        if (m == 0) {
+            u32 old = atomicCAS((u32*)p, 0u, KG_LOCKED);
+            if (old == 0) {
+#pragma unroll
+                for (int i = 0; i < W; i++) kg_st_u64(p + 1 + i, key[i]);
+                kg_st_release_u32(p, 1u);
+                is_new = true;
+                return slot;
+            }
+            m = old;
+            k0_valid = false;
+        }
+        if (m == KG_LOCKED) {
+            do { m = kg_ld_u32(p); } while (m == KG_LOCKED);
+            k0_valid = false;
+        }
+        // slot is published: compare
+        if (!k0_valid) k0 = kg_ld_u64(p + 1);
+        bool same = (k0 == key[0]);
+        if (same) {
+#pragma unroll
+            for (int i = 1; i < W; i++) same = same && (kg_ld_u64(p + 1 + i) == key[i]);
+        }
+        if (same) {
+            atomicAdd((u32*)p, 1u);
+            return slot;
+        }
+        slot = slot + 1 == t.nslots ? 0 : slot + 1;
+    }
+    return ~0ULL;
+}
+
+// read-only lookup (compaction / decode); returns slot or ~0
+template <int W>
+__device__ __forceinline__ u64 kg_table_find(const KgTable& t, const u64 (&key)[W], u64 h) {
+    u64 slot = kg_slot(h, t.nslots);
+    const u64 max_probe = t.nslots < 4096 ? t.nslots : 4096;
+    for (u64 probe = 0; probe < max_probe; probe++) {
+        const u64* p = t.slots + slot * t.stride;
+        if ((u32)p[0] == 0) return ~0ULL;
+        bool same = true;
+#pragma unroll
+        for (int i = 0; i < W; i++) same = same && (p[1 + i] == key[i]);
+        if (same) return slot;
+        slot = slot + 1 == t.nslots ? 0 : slot + 1;
+    }
+    return ~0ULL;
+}
+
+// ---- 2-bit helpers -----------------------------------------------------------------------------------
+// reverse the order of the 32 2-bit characters of a word
+__device__ __forceinline__ u64 kg_rev2(u64 x) {
+    x = __brevll(x);
+    return ((x >> 1) & 0x5555555555555555ULL) | ((x & 0x5555555555555555ULL) << 1);
+}
+
+template <int W>
+struct KgKmerWindow {
+    u64 f[W];  // forward window, right-aligned, word 0 most significant
+    u64 r[W];  // reverse complement
+};
+
+// masks for a k-mer of W words
+struct KgKGeom {
+    u32 k;
+    u32 topbits;  // bits of word 0 in use: 2k - 64(W-1), in (0,64]
+    u64 topmask;
+};
+__host__ __device__ inline KgKGeom kg_geom(u32 k) {
+    KgKGeom g;
+    u32 W = (k + 31) / 32;
+    g.k = k;
+    g.topbits = 2 * k - 64 * (W - 1);
+    g.topmask = g.topbits == 64 ? ~0ULL : ((1ULL << g.topbits) - 1);
+    return g;
+}
+
+template <int W>
+__device__ __forceinline__ void kg_push(KgKmerWindow<W>& w, const KgKGeom& g, u32 c) {
+#pragma unroll
+    for (int i = 0; i < W - 1; i++) w.f[i] = (w.f[i] << 2) | (w.f[i + 1] >> 62);
+    w.f[W - 1] = (w.f[W - 1] << 2) | (u64)c;
+    w.f[0] &= g.topmask;
+#pragma unroll
+    for (int i = W - 1; i > 0; i--) w.r[i] = (w.r[i] >> 2) | (w.r[i - 1] << 62);
+    w.r[0] = (w.r[0] >> 2) | ((u64)(3u - c) << (g.topbits - 2));
+}
+
+// reverse complement of a right-aligned 2k-bit value
+template <int W>
+__device__ __forceinline__ void kg_revcomp(const u64 (&f)[W], u64 (&r)[W], const KgKGeom& g) {
+    // reverse all 32*W characters, complement, then shift right by (64W - 2k) bits
+    u64 t[W];
+#pragma unroll
+    for (int i = 0; i < W; i++) t[i] = ~kg_rev2(f[W - 1 - i]);
+    const u32 sh = 64 - g.topbits;  // 0..62, even
+    if (sh == 0) {
+#pragma unroll
+        for (int i = 0; i < W; i++) r[i] = t[i];
+    } else {
+#pragma unroll
+        for (int i = W - 1; i > 0; i--) r[i] = (t[i] >> sh) | (t[i - 1] << (64 - sh));
+        r[0] = t[0] >> sh;
+    }
+}
+
+// forward is canonical when it is <= reverse complement (ties keep forward: parallel_parser.hpp:686-702)
+template <int W>
+__device__ __forceinline__ bool kg_forward_is_canonical(const KgKmerWindow<W>& w) {
+    bool fwd = true;  // equal => forward
+#pragma unroll
+    for (int i = W - 1; i >= 0; i--) {
+        if (w.f[i] != w.r[i]) fwd = w.f[i] < w.r[i];
+    }
+    return fwd;
+}

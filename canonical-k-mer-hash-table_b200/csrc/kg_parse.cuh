@@ -1,0 +1,341 @@
+// kg_parse.cuh -- K1 "parse": raw FASTA / one-string-per-line bytes -> packed 2-bit base stream + break
+// mask.  Replaces the per-byte scanner of the reference functors (parallel_parser.hpp:597-638 FASTA,
+// :391-400 PLAIN; char codec functions_strings.cpp:56-70) and the chunk-overlap logic of
+// text_reader.h:91-226 (here: device-resident carry of the last k-1 bases).
+//
+// Semantics restated:
+//   FASTA  '>' anywhere starts a header that runs through the next '\n'; a header resets the window;
+//          '\n' outside a header is skipped (multi-line records are one sequence)
+//   PLAIN  '\n' is just an invalid byte (each line its own sequence)
+//   both   AaCcGgTt -> 0,1,2,3; any other byte resets the window
+// Both "am I inside a header" and "did a reset happen since the previous base" are last-writer-wins
+// scans, so the batch is processed in 4 KiB tiles with two tiny single-block scans in between:
+//   kg_hdr_summary -> kg_hdr_scan -> kg_tile_count -> kg_tile_scan -> kg_tile_pack
+// All kernels are HBM-streaming: 3 reads of the raw bytes + 0.375 B/base written.
+#pragma once
+#include "kg_device.cuh"
+
+#define KG_PT 256                    // threads per tile block
+#define KG_BPT 16                    // bytes per thread (one 128-bit load)
+#define KG_TILE (KG_PT * KG_BPT)     // 4096 bytes per tile
+
+// last-writer-wins effects
+#define KG_EFF_NONE 0u
+#define KG_EFF_SET 1u    // header: enter header   | pending: a break happened after the last base
+#define KG_EFF_CLEAR 2u  // header: leave header   | pending: a base was emitted after the last break
+
+// byte classes
+#define KG_C_NL 4u
+#define KG_C_GT 5u
+#define KG_C_INV 6u
+
+__device__ __forceinline__ u32 kg_classify(u32 b) {
+    u32 u = b & 0xDFu;  // fold case
+    if (u == 0x41u || u == 0x43u || u == 0x47u || u == 0x54u) {
+        u32 c = (u >> 1) & 3u;  // A0 C1 G3 T2
+        return c ^ (c >> 1);    // A0 C1 G2 T3
+    }
+    if (b == '\n') return KG_C_NL;
+    if (b == '>') return KG_C_GT;
+    return KG_C_INV;
+}
+
+__device__ __forceinline__ uint4 kg_load_tile16(const uint8_t* in, size_t n, size_t off) {
+    // 16 bytes at `off` (16-byte aligned base pointer + multiple-of-16 offset); bytes past n read as '\n'
+    // in the sense of "no effect": callers mask by position.
+    uint4 v = make_uint4(0, 0, 0, 0);
+    if (off + 16 <= n) {
+        v = *reinterpret_cast<const uint4*>(in + off);
+    } else if (off < n) {
+        uint8_t tmp[16];
+#pragma unroll
+        for (int i = 0; i < 16; i++) tmp[i] = (off + i < n) ? in[off + i] : 0;
+        v = *reinterpret_cast<uint4*>(tmp);
+    }
+    return v;
+}
+__device__ __forceinline__ u32 kg_byte_of(const uint4& v, int i) {
+    u32 w = i < 4 ? v.x : i < 8 ? v.y : i < 12 ? v.z : v.w;
+    return (w >> (8 * (i & 3))) & 0xFFu;
+}
+
+// combine for last-writer-wins: later non-NONE effect overrides
+__device__ __forceinline__ u32 kg_lww(u32 earlier, u32 later) { return later != KG_EFF_NONE ? later : earlier; }
+
+// inclusive last-writer-wins scan over the block's threads; returns the EXCLUSIVE value for this thread
+// (effect of all earlier threads) and the block total in *block_total.
+__device__ __forceinline__ u32 kg_block_lww_exclusive(u32 mine, u32* smem /*>= 8 words*/, u32* block_total) {
+    const u32 lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    u32 incl = mine;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        u32 o = __shfl_up_sync(0xffffffffu, incl, d);
+        if (lane >= (u32)d) incl = kg_lww(o, incl);
+    }
+    u32 excl = __shfl_up_sync(0xffffffffu, incl, 1);
+    if (lane == 0) excl = KG_EFF_NONE;
+    if (lane == 31) smem[warp] = incl;
+    __syncthreads();
+    u32 pre = KG_EFF_NONE, tot = KG_EFF_NONE;
+    for (u32 w = 0; w < KG_PT / 32; w++) {
+        u32 e = smem[w];
+        if (w < warp) pre = kg_lww(pre, e);
+        tot = kg_lww(tot, e);
+    }
+    __syncthreads();
+    *block_total = tot;
+    return kg_lww(pre, excl);
+}
+
+__device__ __forceinline__ u32 kg_block_sum_exclusive(u32 mine, u32* smem, u32* block_total) {
+    const u32 lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    u32 incl = mine;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        u32 o = __shfl_up_sync(0xffffffffu, incl, d);
+        if (lane >= (u32)d) incl += o;
+    }
+    if (lane == 31) smem[warp] = incl;
+    __syncthreads();
+    u32 pre = 0, tot = 0;
+    for (u32 w = 0; w < KG_PT / 32; w++) {
+        u32 e = smem[w];
+        if (w < warp) pre += e;
+        tot += e;
+    }
+    __syncthreads();
+    *block_total = tot;
+    return pre + incl - mine;
+}
+
+// header effect of 16 bytes: '>' => SET (from this byte on), '\n' => CLEAR (from the next byte on)
+__device__ __forceinline__ u32 kg_hdr_effect16(const uint4& v, int nvalid) {
+    u32 eff = KG_EFF_NONE;
+#pragma unroll
+    for (int i = 0; i < 16; i++) {
+        if (i < nvalid) {
+            u32 b = kg_byte_of(v, i);
+            if (b == '>') eff = KG_EFF_SET;
+            else if (b == '\n') eff = KG_EFF_CLEAR;
+        }
+    }
+    return eff;
+}
+
+// ---- pass A (FASTA only): per-tile header effect ------------------------------------------------------
+__global__ void __launch_bounds__(KG_PT) kg_hdr_summary(const uint8_t* __restrict__ in, size_t n,
+                                                        u32* __restrict__ tile_hdr_eff) {
+    __shared__ u32 sm[8];
+    const size_t off = (size_t)blockIdx.x * KG_TILE + (size_t)threadIdx.x * KG_BPT;
+    int nvalid = off >= n ? 0 : (n - off >= 16 ? 16 : (int)(n - off));
+    uint4 v = kg_load_tile16(in, n, off);
+    u32 tot;
+    kg_block_lww_exclusive(kg_hdr_effect16(v, nvalid), sm, &tot);
+    if (threadIdx.x == 0) tile_hdr_eff[blockIdx.x] = tot;
+}
+
+// ---- single-block exclusive last-writer-wins scan over tiles ------------------------------------------
+// in_eff[t] -> out_state[t] = state (0/1) at the start of tile t; *state_io: initial state in, final out.
+__global__ void __launch_bounds__(1024) kg_lww_scan(const u32* __restrict__ in_eff, u32* __restrict__ out_state,
+                                                    u32 ntiles, u32* state_io) {
+    __shared__ u32 sm[1024];
+    const u32 per = (ntiles + 1023) / 1024;
+    const u32 b = threadIdx.x * per, e = min(b + per, ntiles);
+    u32 mine = KG_EFF_NONE;
+    for (u32 t = b; t < e; t++) mine = kg_lww(mine, in_eff[t]);
+    sm[threadIdx.x] = mine;
+    __syncthreads();
+    u32 init = *state_io ? KG_EFF_SET : KG_EFF_CLEAR;
+    u32 pre = init;
+    for (u32 i = 0; i < threadIdx.x; i++) pre = kg_lww(pre, sm[i]);
+    u32 cur = pre;
+    for (u32 t = b; t < e; t++) {
+        out_state[t] = cur == KG_EFF_SET ? 1u : 0u;
+        cur = kg_lww(cur, in_eff[t]);
+    }
+    __syncthreads();
+    if (threadIdx.x == 1023) *state_io = (kg_lww(pre, mine) == KG_EFF_SET) ? 1u : 0u;
+}
+
+// ---- classification of one thread's 16 bytes given its incoming header state ---------------------------
+struct KgThreadParse {
+    u32 nbases;     // bases emitted
+    u32 bits;       // 2-bit codes, first base in the TOP bits of a 32-bit word
+    u32 brk;        // break flag per emitted base, first base in bit 15 (of 16), *excluding* incoming pending
+    u32 first_needs_pending;  // 1 if the first base's break flag is (still) decided by the incoming pending
+    u32 pend_eff;   // effect on "pending break" after these bytes
+};
+
+template <bool FASTA>
+__device__ __forceinline__ KgThreadParse kg_parse16(const uint4& v, int nvalid, u32 in_header) {
+    KgThreadParse r;
+    r.nbases = 0; r.bits = 0; r.brk = 0; r.first_needs_pending = 1; r.pend_eff = KG_EFF_NONE;
+    u32 hdr = in_header;
+    u32 pend = 0;  // break seen since the last base inside this thread
+#pragma unroll
+    for (int i = 0; i < 16; i++) {
+        if (i < nvalid) {
+            u32 b = kg_byte_of(v, i);
+            u32 c = kg_classify(b);
+            if (FASTA) {
+                if (c == KG_C_GT) hdr = 1;
+                if (hdr) {
+                    pend = 1;                       // header bytes reset the window
+                    if (c == KG_C_NL) hdr = 0;      // the newline ends the header
+                    continue;
+                }
+                if (c == KG_C_NL) continue;         // newline inside a record is skipped
+            }
+            if (c > 3u) { pend = 1; continue; }     // non-ACGT (PLAIN: newline too) resets the window
+            // a base
+            if (r.nbases == 0) { if (pend) { r.brk |= 1u << 15; r.first_needs_pending = 0; } }
+            else if (pend) r.brk |= 1u << (15 - r.nbases);
+            r.bits |= c << (30 - 2 * r.nbases);
+            r.nbases++;
+            pend = 0;
+        }
+    }
+    if (r.nbases > 0) r.pend_eff = pend ? KG_EFF_SET : KG_EFF_CLEAR;
+    else r.pend_eff = pend ? KG_EFF_SET : KG_EFF_NONE;
+    return r;
+}
+
+// ---- pass B: per-tile base count and pending-break effect -----------------------------------------------
+template <bool FASTA>
+__global__ void __launch_bounds__(KG_PT) kg_tile_count(const uint8_t* __restrict__ in, size_t n,
+                                                       const u32* __restrict__ tile_hdr_in,
+                                                       u32* __restrict__ tile_nbases, u32* __restrict__ tile_pend_eff) {
+    __shared__ u32 sm[8];
+    const size_t off = (size_t)blockIdx.x * KG_TILE + (size_t)threadIdx.x * KG_BPT;
+    int nvalid = off >= n ? 0 : (n - off >= 16 ? 16 : (int)(n - off));
+    uint4 v = kg_load_tile16(in, n, off);
+    u32 hdr_in = 0, tot;
+    if (FASTA) {
+        u32 pre = kg_block_lww_exclusive(kg_hdr_effect16(v, nvalid), sm, &tot);
+        u32 tile_in = tile_hdr_in[blockIdx.x] ? KG_EFF_SET : KG_EFF_CLEAR;
+        hdr_in = kg_lww(tile_in, pre) == KG_EFF_SET;
+    }
+    KgThreadParse p = kg_parse16<FASTA>(v, nvalid, hdr_in);
+    u32 total_bases, pend_tot;
+    kg_block_sum_exclusive(p.nbases, sm, &total_bases);
+    kg_block_lww_exclusive(p.pend_eff, sm, &pend_tot);
+    if (threadIdx.x == 0) { tile_nbases[blockIdx.x] = total_bases; tile_pend_eff[blockIdx.x] = pend_tot; }
+}
+
+// ---- single-block exclusive sum over tiles; also finalises the stream state ------------------------------
+__global__ void __launch_bounds__(1024) kg_tile_scan(const u32* __restrict__ tile_nbases, u32* __restrict__ tile_off,
+                                                     u32 ntiles, KgStream* st) {
+    __shared__ u32 sm[1024];
+    const u32 per = (ntiles + 1023) / 1024;
+    const u32 b = threadIdx.x * per, e = min(b + per, ntiles);
+    u32 mine = 0;
+    for (u32 t = b; t < e; t++) mine += tile_nbases[t];
+    sm[threadIdx.x] = mine;
+    __syncthreads();
+    u32 pre = st->carry_bases;
+    for (u32 i = 0; i < threadIdx.x; i++) pre += sm[i];
+    u32 cur = pre;
+    for (u32 t = b; t < e; t++) { tile_off[t] = cur; cur += tile_nbases[t]; }
+    __syncthreads();
+    if (threadIdx.x == 1023) st->total_bases = pre + mine;
+}
+
+// ---- pass C: pack bases and break bits ---------------------------------------------------------------------
+// words/brk must be zero beyond the carried head; tile boundary words are merged with atomicOr.
+template <bool FASTA>
+__global__ void __launch_bounds__(KG_PT) kg_tile_pack(const uint8_t* __restrict__ in, size_t n,
+                                                      const u32* __restrict__ tile_hdr_in,
+                                                      const u32* __restrict__ tile_off,
+                                                      const u32* __restrict__ tile_pend_in,
+                                                      u64* __restrict__ words, u32* __restrict__ brk) {
+    __shared__ u32 sm[8];
+    __shared__ u64 sw[KG_TILE / 32 + 2];
+    __shared__ u32 sb[KG_TILE / 32 + 2];
+    const size_t off = (size_t)blockIdx.x * KG_TILE + (size_t)threadIdx.x * KG_BPT;
+    int nvalid = off >= n ? 0 : (n - off >= 16 ? 16 : (int)(n - off));
+    uint4 v = kg_load_tile16(in, n, off);
+    for (u32 i = threadIdx.x; i < KG_TILE / 32 + 2; i += KG_PT) { sw[i] = 0; sb[i] = 0; }
+    u32 hdr_in = 0, tot;
+    if (FASTA) {
+        u32 pre = kg_block_lww_exclusive(kg_hdr_effect16(v, nvalid), sm, &tot);
+        u32 tile_in = tile_hdr_in[blockIdx.x] ? KG_EFF_SET : KG_EFF_CLEAR;
+        hdr_in = kg_lww(tile_in, pre) == KG_EFF_SET;
+    } else {
+        __syncthreads();
+    }
+    KgThreadParse p = kg_parse16<FASTA>(v, nvalid, hdr_in);
+    u32 total_bases, pend_tot;
+    u32 base_pre = kg_block_sum_exclusive(p.nbases, sm, &total_bases);
+    u32 pend_pre = kg_block_lww_exclusive(p.pend_eff, sm, &pend_tot);
+    const u32 t_off = tile_off[blockIdx.x];
+    if (p.nbases) {
+        u32 tile_pend = tile_pend_in[blockIdx.x] ? KG_EFF_SET : KG_EFF_CLEAR;
+        u32 pend_in = kg_lww(tile_pend, pend_pre) == KG_EFF_SET;
+        u32 bmask = p.brk;
+        if (p.first_needs_pending && pend_in) bmask |= 1u << 15;
+        // local ordinal relative to the first word this tile touches
+        u32 lo = (t_off & 31u) + base_pre;
+        u32 wi = lo >> 5, bo = lo & 31u;                // word index, base offset inside the word
+        // bits: p.nbases characters in the top of a 32-bit value -> place at base offset bo of a 64-bit word
+        u64 chunk = (u64)p.bits << 32;                  // first base at bits 63:62
+        u32 bchunk = bmask << 16;                       // first base at bit 31
+        atomicOr(&sw[wi], chunk >> (2 * bo));
+        atomicOr(&sb[wi], bchunk >> bo);
+        if (bo + p.nbases > 32) {                       // spills into the next word
+            u32 used = 32 - bo;                         // bases that fitted
+            atomicOr(&sw[wi + 1], chunk << (2 * used));
+            atomicOr(&sb[wi + 1], bchunk << used);
+        }
+    }
+    __syncthreads();
+    const u32 nwords = total_bases ? (((t_off & 31u) + total_bases + 31u) >> 5) : 0;
+    const u32 gw0 = t_off >> 5;
+    for (u32 i = threadIdx.x; i < nwords; i += KG_PT) {
+        if (i == 0 || i + 1 == nwords) {
+            if (sw[i]) atomicOr(&words[gw0 + i], sw[i]);
+            if (sb[i]) atomicOr(&brk[gw0 + i], sb[i]);
+        } else {
+            words[gw0 + i] = sw[i];
+            brk[gw0 + i] = sb[i];
+        }
+    }
+}
+
+// ---- carry: move the tail of the finished batch to the head of the next one -------------------------------
+// Keeps whole words: the carried region starts at word floor((T-(k-1))/32), so C = T - 32*that >= k-1
+// (or everything when T < k-1).  Runs AFTER the count kernel of the batch, single block.
+__global__ void kg_carry_save(const u64* __restrict__ words, const u32* __restrict__ brk, KgStream* st,
+                              u64* __restrict__ carry_words, u32* __restrict__ carry_brk, u32 k, u32 max_words) {
+    const u32 T = st->total_bases;
+    u32 w0 = T >= (k - 1) ? (T - (k - 1)) >> 5 : 0;
+    u32 nw = ((T + 31) >> 5) - w0;
+    if (nw > max_words) nw = max_words;  // cannot happen (max_words = W+2)
+    for (u32 i = threadIdx.x; i < max_words; i += blockDim.x) {
+        carry_words[i] = i < nw ? words[w0 + i] : 0;
+        carry_brk[i] = i < nw ? brk[w0 + i] : 0;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        st->bases_seen += (u64)(w0) * 32u;   // global ordinal of the first carried base
+        st->carry_bases = T - w0 * 32u;
+    }
+}
+
+// Runs BEFORE packing a batch: zero-initialised words/brk get the carried head; position 0 is a run start.
+__global__ void kg_carry_restore(u64* __restrict__ words, u32* __restrict__ brk, const KgStream* st,
+                                 const u64* __restrict__ carry_words, const u32* __restrict__ carry_brk,
+                                 u32 max_words) {
+    const u32 C = st->carry_bases;
+    const u32 nw = (C + 31) >> 5;
+    for (u32 i = threadIdx.x; i < max_words; i += blockDim.x) {
+        if (i < nw) {
+            words[i] = carry_words[i];
+            u32 b = carry_brk[i];
+            if (i == 0) b |= 0x80000000u;
+            brk[i] = b;
+        }
+    }
+}
+
+// pending-break input for every tile: exclusive last-writer-wins scan seeded by the stream state
+// (reuses kg_lww_scan with state_io = &st->pending_break)

@@ -1,0 +1,430 @@
+// kaarme_main.cpp -- the drop-in `kaarme` executable: the reference's command line (main.cpp:134-151,
+// README.md:31-52), file-format sniffing (main.cpp:27-68), log lines and output format, driving the sm_100a
+// kernels of libkaarme_gpu.so through the C ABI (include/kaarme_gpu.h).  No CPU counting path exists here:
+// the host only reads bytes, feeds them, and formats what the GPU exports.
+//
+//   kaarme [OPTIONS] INPUT KLEN
+//     -m,--hash-table-type {0,2}   -a,--min-k-abu N   -t,--threads N   -o,--output-file PATH
+//     -b,--use-bfilter  -f,--bfilter-fpr F   exactly one of  -s,--hash-tab-size N | -u,--unq-kmers N
+//   GPU-side extras (do not collide with the reference's flags):
+//     --device N   --batch-mb N   --exact-counts   --stats-json PATH
+//
+// Exit codes follow the reference: 0 ok; CLI11's 105 (validation), 106 (required), 107 (requires),
+// 109 (unexpected argument); 1 for an ill-formed input file (main.cpp:168-171) or a full table
+// (kmer_hash_table.cpp:2552-2556; the plain table's silent truncation, parallel_parser.hpp:742-746, is
+// deliberately NOT reproduced).
+#include <algorithm>
+#include <chrono>
+#include <cmath>
+#include <cstdint>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <fcntl.h>
+#include <filesystem>
+#include <fstream>
+#include <iostream>
+#include <string>
+#include <sys/stat.h>
+#include <thread>
+#include <unistd.h>
+#include <vector>
+
+#include "kaarme_gpu.h"
+
+namespace {
+
+struct Args {
+    std::string input, output, stats_json;
+    long long k = 0;
+    int mode = 2;                 // main.cpp:137
+    uint64_t min_abundance = 2;   // main.cpp:138
+    int threads = 0;              // main.cpp:139 has no usable default; 0 = pick hardware_concurrency
+    bool bloom = false;
+    double fpr = 0.01;            // main.cpp:142
+    bool has_s = false, has_u = false, has_f = false, has_t = false;
+    uint64_t slots = 0, unique = 0;
+    int device = 0;
+    uint64_t batch_mb = 0;
+    bool exact_counts = false;
+};
+
+[[noreturn]] void cli_fail(int code, const std::string& msg) {
+    std::cerr << msg << "\nRun with --help for more information.\n";
+    std::exit(code);
+}
+
+void print_help(const char* argv0) {
+    std::cout << "Space-efficient k-mer counter (B200 GPU build)\n"
+                 "Usage: " << argv0 << " [OPTIONS] INPUT KLEN\n\n"
+                 "Positionals:\n"
+                 "  INPUT TEXT REQUIRED        Input file (automatic format detection)\n"
+                 "  KLEN INT REQUIRED          k-mer length\n\n"
+                 "Options:\n"
+                 "  -h,--help                  Print this help message and exit\n"
+                 "  -m,--hash-table-type INT   Hash table type: 0 for plain and 2 for kaarme (def. 2)\n"
+                 "  -a,--min-k-abu UINT        Minimum abundance threshold for the output k-mers (def. 2)\n"
+                 "  -t,--threads UINT          Number of host threads formatting the output (def. all cores)\n"
+                 "  -o,--output-file TEXT      Output file where the k-mer counts will be stored\n"
+                 "  -b,--use-bfilter           Use bloom filters to discard unique k-mers\n"
+                 "  -f,--bfilter-fpr FLOAT     Bloom filter false positive rate (def. 0.01)\n"
+                 "  --device INT               CUDA device ordinal (def. 0)\n"
+                 "  --batch-mb UINT            Raw bytes per device batch in MiB (def. 128)\n"
+                 "  --exact-counts             Report true 32-bit counts instead of emulating the reference's\n"
+                 "                             16-bit wrap (-m 0) / 14-bit saturation (-m 2)\n"
+                 "  --stats-json TEXT          Write pass statistics and device timings as JSON\n\n"
+                 "[Exactly 1 of the following options is required]\n"
+                 "Mandatory params:\n"
+                 "  -s,--hash-tab-size UINT    Hash table size\n"
+                 "  -u,--unq-kmers UINT        Estimated number of unique k-mers\n";
+}
+
+bool parse_u64(const std::string& s, uint64_t& v) {
+    if (s.empty() || s[0] == '-') return false;
+    char* end = nullptr;
+    errno = 0;
+    unsigned long long x = strtoull(s.c_str(), &end, 10);
+    if (errno || *end) return false;
+    v = x;
+    return true;
+}
+bool parse_i64(const std::string& s, long long& v) {
+    if (s.empty()) return false;
+    char* end = nullptr;
+    errno = 0;
+    long long x = strtoll(s.c_str(), &end, 10);
+    if (errno || *end) return false;
+    v = x;
+    return true;
+}
+bool parse_f64(const std::string& s, double& v) {
+    if (s.empty()) return false;
+    char* end = nullptr;
+    errno = 0;
+    double x = strtod(s.c_str(), &end);
+    if (errno || *end) return false;
+    v = x;
+    return true;
+}
+
+Args parse_args(int argc, char** argv) {
+    Args a;
+    std::vector<std::string> pos;
+    auto need_value = [&](int& i, const std::string& name) -> std::string {
+        if (i + 1 >= argc) cli_fail(114, name + ": 1 required");
+        return argv[++i];
+    };
+    for (int i = 1; i < argc; i++) {
+        std::string s = argv[i];
+        std::string val;
+        bool has_eq = false;
+        if (s.rfind("--", 0) == 0) {
+            size_t eq = s.find('=');
+            if (eq != std::string::npos) { val = s.substr(eq + 1); s = s.substr(0, eq); has_eq = true; }
+        }
+        auto value = [&](const std::string& name) { return has_eq ? val : need_value(i, name); };
+        if (s == "-h" || s == "--help") { print_help(argv[0]); std::exit(0); }
+        else if (s == "-m" || s == "--hash-table-type") {
+            long long v;
+            std::string t = value("--hash-table-type");
+            if (!parse_i64(t, v) || v < 0 || v > 2) cli_fail(105, "--hash-table-type: Value " + t + " not in range 0 to 2");
+            a.mode = (int)v;
+        } else if (s == "-a" || s == "--min-k-abu") {
+            std::string t = value("--min-k-abu");
+            if (!parse_u64(t, a.min_abundance)) cli_fail(104, "Could not convert: --min-k-abu = " + t);
+        } else if (s == "-t" || s == "--threads") {
+            long long v;
+            std::string t = value("--threads");
+            if (!parse_i64(t, v) || v < 3 || v > 64) cli_fail(105, "--threads: Value " + t + " not in range 3 to 64");
+            a.threads = (int)v; a.has_t = true;
+        } else if (s == "-o" || s == "--output-file") a.output = value("--output-file");
+        else if (s == "-b" || s == "--use-bfilter") a.bloom = true;
+        else if (s == "-f" || s == "--bfilter-fpr") {
+            std::string t = value("--bfilter-fpr");
+            if (!parse_f64(t, a.fpr) || a.fpr < 0.001 || a.fpr > 0.999)
+                cli_fail(105, "--bfilter-fpr: Value " + t + " not in range 0.001000 to 0.999000");
+            a.has_f = true;
+        } else if (s == "-s" || s == "--hash-tab-size") {
+            std::string t = value("--hash-tab-size");
+            if (!parse_u64(t, a.slots)) cli_fail(104, "Could not convert: --hash-tab-size = " + t);
+            a.has_s = true;
+        } else if (s == "-u" || s == "--unq-kmers") {
+            std::string t = value("--unq-kmers");
+            if (!parse_u64(t, a.unique)) cli_fail(104, "Could not convert: --unq-kmers = " + t);
+            a.has_u = true;
+        } else if (s == "--device") {
+            long long v; std::string t = value("--device");
+            if (!parse_i64(t, v) || v < 0) cli_fail(105, "--device: Value " + t + " not a device ordinal");
+            a.device = (int)v;
+        } else if (s == "--batch-mb") {
+            std::string t = value("--batch-mb");
+            if (!parse_u64(t, a.batch_mb) || a.batch_mb == 0 || a.batch_mb > 1024) cli_fail(105, "--batch-mb: Value " + t + " not in range 1 to 1024");
+        } else if (s == "--exact-counts") a.exact_counts = true;
+        else if (s == "--stats-json") a.stats_json = value("--stats-json");
+        else if (s.size() > 1 && s[0] == '-' && !(s[1] >= '0' && s[1] <= '9')) cli_fail(109, "The following argument was not expected: " + s);
+        else pos.push_back(s);
+    }
+    if (pos.size() > 2) cli_fail(109, "The following argument was not expected: " + pos[2]);
+    if (pos.empty()) cli_fail(106, "INPUT is required");
+    a.input = pos[0];
+    {
+        struct stat st{};
+        if (stat(a.input.c_str(), &st) != 0) cli_fail(105, "INPUT: File does not exist: " + a.input);
+        if (S_ISDIR(st.st_mode)) cli_fail(105, "INPUT: File is actually a directory: " + a.input);
+    }
+    if (pos.size() < 2) cli_fail(106, "KLEN is required");
+    if (!parse_i64(pos[1], a.k) || a.k <= 0) cli_fail(105, "KLEN: Value " + pos[1] + " not in range 0 to inf (positive number required)");
+    int given = (a.has_s ? 1 : 0) + (a.has_u ? 1 : 0);
+    if (given == 0) cli_fail(106, "Exactly 1 option from [-s,--hash-tab-size,-u,--unq-kmers] is required");
+    if (given == 2) cli_fail(106, "Exactly 1 option from [-s,--hash-tab-size,-u,--unq-kmers] is required and 2 were given");
+    if (a.has_u && !a.bloom) cli_fail(107, "--unq-kmers requires --use-bfilter");
+    if (a.bloom && !a.has_u) cli_fail(107, "--use-bfilter requires --unq-kmers");
+    if (a.has_f && !a.bloom) cli_fail(107, "--bfilter-fpr requires --use-bfilter");
+    return a;
+}
+
+// main.cpp:19-68 (is_gz, file_format): format by extension + first byte
+struct Format { char header_symbol; bool ill_formed; bool gz; };
+Format file_format(const std::string& path) {
+    Format f{0, false, false};
+    unsigned char b[2] = {0, 0};
+    {
+        std::ifstream ifs(path, std::ios::binary);
+        ifs.read((char*)b, 2);
+        f.gz = ifs.gcount() == 2 && b[0] == 0x1f && b[1] == 0x8b;
+    }
+    std::string ext = std::filesystem::path(path).extension().string();
+    char sym = (char)b[0];
+    if (ext == ".fasta" || ext == ".fa") { f.header_symbol = '>'; f.ill_formed = sym != '>'; }
+    else if (ext == ".fastq" || ext == ".fq") { f.header_symbol = '@'; f.ill_formed = sym != '@'; }
+    else { f.header_symbol = 0; f.ill_formed = std::string("actgACGT").find(sym) == std::string::npos || sym == 0; }
+    return f;
+}
+
+#define KG_CHECK(call)                                                                              \
+    do {                                                                                            \
+        int rc_ = (call);                                                                           \
+        if (rc_ == KG_ETABLE_FULL) { std::cout << "Hash table is full... Cannot handle this yet\n"; std::exit(1); } \
+        if (rc_ != KG_OK) {                                                                         \
+            std::cerr << "kaarme: " #call " failed: " << kg_strerror(rc_) << " (" << kg_last_error(ctx) << ")\n"; \
+            std::exit(2);                                                                           \
+        }                                                                                           \
+    } while (0)
+
+// one pass over the file: read(2) into two pinned buffers, feed the GPU while the next read proceeds
+void feed_file(kg_ctx* ctx, const std::string& path, uint8_t* buf[2], size_t buf_bytes) {
+    int fd = open(path.c_str(), O_RDONLY);
+    if (fd < 0) { std::cerr << "kaarme: cannot open " << path << "\n"; std::exit(1); }
+#ifdef __linux__
+    posix_fadvise(fd, 0, 0, POSIX_FADV_SEQUENTIAL);  // parallel_parser.hpp:280
+#endif
+    KG_CHECK(kg_stream_begin(ctx, 0));
+    int which = 0;
+    for (;;) {
+        size_t got = 0;
+        while (got < buf_bytes) {
+            ssize_t r = read(fd, buf[which] + got, buf_bytes - got);
+            if (r < 0) { std::cerr << "kaarme: read error on " << path << "\n"; std::exit(1); }
+            if (r == 0) break;
+            got += (size_t)r;
+        }
+        if (got == 0) break;
+        KG_CHECK(kg_feed(ctx, buf[which], got, 0));   // returns once the H2D copy is done; kernels keep running
+        which ^= 1;
+        if (got < buf_bytes) break;
+    }
+    close(fd);
+}
+
+struct Writer {
+    FILE* f = nullptr;
+    uint32_t k = 0, W = 0;
+    int threads = 1;
+    uint64_t written = 0;
+    std::vector<std::vector<char>> bufs;
+};
+
+// kmer_hash_table.cpp:2022-2043: k characters, a space, the decimal count, newline
+size_t format_range(const Writer& w, const uint64_t* keys, const uint32_t* counts, size_t b, size_t e, std::vector<char>& out) {
+    const uint32_t k = w.k, W = w.W;
+    out.resize((e - b) * (k + 12));
+    char* p = out.data();
+    for (size_t i = b; i < e; i++) {
+        const uint64_t* key = keys + i * W;
+        for (uint32_t j = 0; j < k; j++) {
+            uint32_t pos = k - 1 - j;
+            *p++ = "ACGT"[(key[W - 1 - pos / 32] >> (2 * (pos % 32))) & 3];
+        }
+        *p++ = ' ';
+        char num[12];
+        int nd = 0;
+        uint32_t v = counts[i];
+        do { num[nd++] = (char)('0' + v % 10); v /= 10; } while (v);
+        while (nd) *p++ = num[--nd];
+        *p++ = '\n';
+    }
+    return (size_t)(p - out.data());
+}
+
+int sink(void* user, const uint64_t* keys, const uint32_t* counts, size_t n) {
+    Writer& w = *(Writer*)user;
+    const int T = (int)std::min<size_t>((size_t)w.threads, std::max<size_t>(1, n / 65536));
+    w.bufs.resize(T);
+    std::vector<size_t> lens(T);
+    std::vector<std::thread> th;
+    for (int t = 0; t < T; t++) {
+        size_t b = n * t / T, e = n * (t + 1) / T;
+        th.emplace_back([&, t, b, e]() { lens[t] = format_range(w, keys, counts, b, e, w.bufs[t]); });
+    }
+    for (auto& x : th) x.join();
+    for (int t = 0; t < T; t++)
+        if (lens[t] && fwrite(w.bufs[t].data(), 1, lens[t], w.f) != lens[t]) return 1;
+    w.written += n;
+    return 0;
+}
+
+void json_pass(std::ostream& o, const char* name, const kg_pass_stats& s) {
+    o << "\"" << name << "\": {\"input_kmers\": " << s.input_kmers << ", \"inserted_kmers\": " << s.inserted_kmers
+      << ", \"distinct\": " << s.distinct << ", \"table_slots\": " << s.table_slots << ", \"new_in_first\": " << s.new_in_first
+      << ", \"new_in_second\": " << s.new_in_second << ", \"bloom_bits\": " << s.bloom_bits << ", \"bloom_hashes\": " << s.bloom_hashes
+      << ", \"raw_bytes\": " << s.raw_bytes << ", \"device_ms\": " << s.device_ms << ", \"parse_ms\": " << s.parse_ms
+      << ", \"count_ms\": " << s.count_ms << "}";
+}
+
+}  // namespace
+
+int main(int argc, char** argv) {
+    Args args = parse_args(argc, argv);
+    Format fmt = file_format(args.input);
+    if (fmt.ill_formed) {
+        std::cerr << "Input file " << args.input << " is ill-formed" << std::endl;
+        return 1;  // main.cpp:168-171
+    }
+    std::string fmt_name;
+    int input_mode;
+    if (fmt.header_symbol == '>') { fmt_name = "FASTA"; input_mode = KG_INPUT_FASTA; }
+    else if (fmt.header_symbol == '@') { fmt_name = "FASTQ"; input_mode = 1; }
+    else { fmt_name = "ONE-STR-PER-LINE"; input_mode = KG_INPUT_PLAIN; }
+    if (args.output.empty())
+        args.output = std::filesystem::path(args.input).replace_extension().filename().string() + ".kaarme_counts";  // main.cpp:189-191
+    if (!args.has_t) {
+        unsigned hc = std::thread::hardware_concurrency();
+        args.threads = (int)std::max(3u, std::min(64u, hc ? hc : 3u));
+    }
+    // main.cpp:193-208
+    std::cout << "Running settings: " << std::endl;
+    std::cout << "  input file:               " << std::filesystem::path(args.input).filename().string() << std::endl;
+    std::cout << "  input format:             " << fmt_name << std::endl;
+    std::cout << "  gzip compressed:          " << (fmt.gz ? "yes" : "no") << std::endl;
+    std::cout << "  k-mer length:             " << args.k << std::endl;
+    std::cout << "  min. abundance threshold: " << args.min_abundance << std::endl;
+    std::cout << "  hash table type:          " << (args.mode == 0 ? "plain" : "kaarme") << std::endl;
+    std::cout << "  using bloom filers:       " << (args.bloom ? "yes" : "no") << std::endl;
+    if (args.bloom) {
+        std::cout << "    est. unique k-mers:     " << args.unique << std::endl;
+        std::cout << "    false positive rate:    " << args.fpr << std::endl;
+    } else {
+        std::cout << "    est. hash table size:   " << args.slots << std::endl;
+    }
+    std::cout << "  working threads:          " << args.threads << std::endl;
+    std::cout << "  output file:              " << args.output << std::endl;
+
+    if (fmt.gz) { std::cout << "gzip input is not supported by the GPU build (the reference's gz path is broken, SURVEY.md section 2)\n"; return 1; }
+    if (input_mode == 1) { std::cout << "Not implemented yet" << std::endl; return 0; }  // parallel_parser.hpp:797-800
+    if (args.mode == 1) { std::cout << "Chosen mode not recognized\n"; return 0; }       // -m 1 (superseded variant) is out of scope
+    if (args.k > 256) { std::cerr << "kaarme: k > 256 is not supported by the GPU build\n"; return 1; }
+
+    kg_ctx* ctx = nullptr;
+    kg_config cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.abi_version = KG_ABI_VERSION;
+    cfg.k = (uint32_t)args.k;
+    cfg.table_mode = args.mode;
+    cfg.input_mode = input_mode;
+    cfg.min_slots = args.slots;
+    cfg.use_bloom = args.bloom ? 1 : 0;
+    cfg.device = args.device;
+    cfg.fpr = args.fpr;
+    cfg.expected_unique = args.unique;
+    cfg.batch_bytes = args.batch_mb << 20;
+    cfg.rank = 0;
+    cfg.world = 1;
+    {
+        int rc = kg_create(&cfg, &ctx);
+        if (rc != KG_OK) {
+            std::cerr << "kaarme: cannot initialise the GPU path: " << kg_strerror(rc) << " (" << kg_last_error(nullptr)
+                      << "). This build has no CPU fallback.\n";
+            return 2;
+        }
+    }
+    const size_t buf_bytes = (args.batch_mb ? args.batch_mb : 128) << 20;
+    uint8_t* bufs[2] = {nullptr, nullptr};
+    for (int i = 0; i < 2; i++) KG_CHECK(kg_host_alloc(buf_bytes, (void**)&bufs[i]));
+
+    kg_pass_stats bloom_stats, count_stats;
+    memset(&bloom_stats, 0, sizeof(bloom_stats));
+    memset(&count_stats, 0, sizeof(count_stats));
+    kg_compact_stats compact_stats;
+    memset(&compact_stats, 0, sizeof(compact_stats));
+
+    if (args.bloom) {
+        std::cout << "Starting parallel bloom filtering\n";  // parallel_parser.hpp:2689
+        auto t0 = std::chrono::high_resolution_clock::now();
+        KG_CHECK(kg_pass_begin(ctx, KG_PASS_BLOOM));
+        feed_file(ctx, args.input, bufs, buf_bytes);
+        KG_CHECK(kg_pass_end(ctx, &bloom_stats));
+        auto t1 = std::chrono::high_resolution_clock::now();
+        std::cout << "New k-mers in first bloom filter " << bloom_stats.new_in_first << "\n";   // parallel_parser.hpp:2900-2901
+        std::cout << "New k-mers in second bloom filter " << bloom_stats.new_in_second << "\n";
+        std::cout << "Time used to bloom filter k-mers: " << std::chrono::duration_cast<std::chrono::microseconds>(t1 - t0).count() << " microseconds\n";
+    }
+    std::cout << (args.mode == 0 ? "Starting atomic flag basic hash table\n" : "Starting atomic variable pointer hash table\n");
+    auto t_build0 = std::chrono::high_resolution_clock::now();
+    KG_CHECK(kg_pass_begin(ctx, KG_PASS_COUNT));
+    {
+        uint64_t slots = 0;
+        kg_table_info(ctx, &slots, nullptr, nullptr);
+        std::cout << "Hash table size is: " << slots << "\n";  // functions_math.cpp:90
+    }
+    feed_file(ctx, args.input, bufs, buf_bytes);
+    KG_CHECK(kg_pass_end(ctx, &count_stats));
+    if (args.mode == KG_TABLE_KAARME) KG_CHECK(kg_compact(ctx, &compact_stats));
+    auto t_build1 = std::chrono::high_resolution_clock::now();
+
+    Writer w;
+    w.k = cfg.k; w.W = (cfg.k + 31) / 32; w.threads = std::max(1, args.threads - 2);
+    if (args.min_abundance > 0) {
+        w.f = fopen(args.output.c_str(), "wb");
+        if (!w.f) { std::cerr << "kaarme: cannot open output file " << args.output << "\n"; return 1; }
+        setvbuf(w.f, nullptr, _IOFBF, 8 << 20);
+        KG_CHECK(kg_export(ctx, args.min_abundance, args.exact_counts ? KG_COUNT_EXACT : KG_COUNT_REFERENCE, sink, &w));
+        fclose(w.f);
+    }
+    auto t_write1 = std::chrono::high_resolution_clock::now();
+    std::cout << "Time used to build hash table: " << std::chrono::duration_cast<std::chrono::microseconds>(t_build1 - t_build0).count() << " microseconds\n";
+    std::cout << "Time used to write k-mers in a file: " << std::chrono::duration_cast<std::chrono::microseconds>(t_write1 - t_build1).count() << " microseconds\n";
+    if (args.mode == KG_TABLE_KAARME) {
+        std::cout << "Written k-mers: " << w.written << "\n";                         // kmer_hash_table.cpp:4522-4523
+        std::cout << "Skipped k-mers: " << (count_stats.distinct - w.written) << "\n";
+        std::cout << "Main array slots used " << count_stats.distinct << " / " << count_stats.table_slots << "\n";  // parallel_parser.hpp:1560-1561
+        std::cout << "Max secondary array slots used " << compact_stats.roots << "\n";
+        std::cout << "Kaarme bytes: " << compact_stats.bytes << " (" << (compact_stats.kmers ? (double)compact_stats.bytes / compact_stats.kmers : 0.0)
+                  << " B/k-mer; reference layout would hold " << compact_stats.reference_bytes << " B)\n";
+    }
+    std::cout << "GPU: input k-mers " << count_stats.input_kmers << ", distinct " << count_stats.distinct << ", device time "
+              << count_stats.device_ms + bloom_stats.device_ms << " ms ("
+              << (count_stats.device_ms + bloom_stats.device_ms > 0 ? count_stats.input_kmers / ((count_stats.device_ms + bloom_stats.device_ms) * 1e3) : 0.0)
+              << " M k-mers/s)\n";
+    if (!args.stats_json.empty()) {
+        std::ofstream o(args.stats_json);
+        o << "{";
+        if (args.bloom) { json_pass(o, "bloom", bloom_stats); o << ", "; }
+        json_pass(o, "count", count_stats);
+        o << ", \"written\": " << w.written << ", \"kaarme\": {\"kmers\": " << compact_stats.kmers << ", \"roots\": " << compact_stats.roots
+          << ", \"bytes\": " << compact_stats.bytes << ", \"reference_bytes\": " << compact_stats.reference_bytes << ", \"max_chain\": "
+          << compact_stats.max_chain << "}}\n";
+    }
+    for (int i = 0; i < 2; i++) kg_host_free(bufs[i]);
+    kg_destroy(ctx);
+    return 0;
+}

@@ -1,0 +1,230 @@
+"""GPU parity tests (run with -m gpu on a B200): the CUDA path through the C ABI vs the oracle / golden vectors.
+Bit-exact: same canonical k-mers, same counts, same -a threshold (integer work, no tolerance)."""
+import hashlib
+import importlib
+import json
+import os
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN
+
+pytestmark = pytest.mark.gpu
+
+kg = importlib.import_module("canonical-k-mer-hash-table_b200")
+K = kg.kaarme_gpu
+
+CASES = json.load(open(os.path.join(GOLDEN, "golden.json")))
+COMP = str.maketrans("ACGT", "TGCA")
+
+
+def _read(name):
+    with open(os.path.join(GOLDEN, name), "rb") as f:
+        return f.read()
+
+
+def _imode(name):
+    return K.INPUT_PLAIN if name.endswith(".txt") else K.INPUT_FASTA
+
+
+def gpu_count(data, k, input_mode=K.INPUT_FASTA, table_mode=K.TABLE_PLAIN, slots=400000, a=1,
+              count_mode=K.COUNT_EXACT, batch_bytes=0, feeder=None, starts_in_header=False):
+    with kg.Counter(k=k, table_mode=table_mode, input_mode=input_mode, min_slots=slots, batch_bytes=batch_bytes) as c:
+        c.pass_begin(K.PASS_COUNT)
+        c.stream_begin(starts_in_header)
+        if feeder:
+            feeder(c, data)
+        else:
+            c.feed(data)
+        st = c.pass_end()
+        keys, counts = c.export(a, count_mode)
+    return keys, counts, st
+
+
+def assert_same(keys, counts, want):
+    assert keys.shape == want.keys.shape, (keys.shape, want.keys.shape)
+    assert (keys == want.keys).all()
+    assert (counts.astype(np.uint64) == want.counts).all()
+
+
+def make_fasta(rng, genome_len, nreads, read_len, wrap=0, err=0.0, n_rate=0.0):
+    g = rng.integers(0, 4, genome_len).astype(np.uint8)
+    out = []
+    for i in range(nreads):
+        p = int(rng.integers(0, genome_len - read_len + 1))
+        r = g[p:p + read_len].copy()
+        if err:
+            e = rng.random(read_len) < err
+            r[e] = (r[e] + rng.integers(1, 4, int(e.sum()))) & 3
+        s = np.frombuffer(b"ACGT", np.uint8)[r].tobytes().decode()
+        if rng.random() < 0.5:
+            s = s[::-1].translate(COMP)
+        if n_rate:
+            s = "".join("N" if rng.random() < n_rate else ch for ch in s)
+        if rng.random() < 0.3:
+            s = s.lower()
+        body = "\n".join(s[j:j + wrap] for j in range(0, len(s), wrap)) if wrap else s
+        out.append(f">read{i} len={read_len}\n{body}\n")
+    return "".join(out).encode()
+
+
+@pytest.mark.parametrize("case", [c for c in CASES if c["unique"] is None and c["mode"] == 0],
+                         ids=lambda c: f"{c['input']}-k{c['k']}-a{c['a']}")
+def test_golden_plain(case):
+    """-m 0 against the reference binary's sorted output (tests/golden/golden.json)."""
+    data = _read(case["input"])
+    keys, counts, st = gpu_count(data, case["k"], _imode(case["input"]), K.TABLE_PLAIN, case["slots"], case["a"],
+                                 K.COUNT_REFERENCE)
+    txt = kg.keys_to_text(keys, counts, case["k"])
+    assert txt.count(b"\n") == case["n_lines"]
+    assert hashlib.sha256(txt).hexdigest() == case["sha256"]
+    assert st["table_slots"] == case["table_slots"]
+
+
+@pytest.mark.parametrize("k", [1, 5, 21, 31, 32, 33, 51, 63, 64, 65, 96, 97, 127, 128, 129, 160, 200, 255, 256])
+def test_k_sweep_vs_oracle(oracle, k):
+    rng = np.random.default_rng(1000 + k)
+    data = make_fasta(rng, 20000, 60, 900, wrap=70, err=0.01, n_rate=0.001)
+    want = oracle.count(data, k)
+    keys, counts, st = gpu_count(data, k)
+    assert st["input_kmers"] == want.total_windows
+    assert st["distinct"] == want.n
+    assert_same(keys, counts, want)
+
+
+@pytest.mark.parametrize("batch", [4096, 8192, 65536])
+@pytest.mark.parametrize("k", [31, 51, 127])
+def test_batch_boundaries_invisible(oracle, k, batch):
+    """windows, headers and multi-line records crossing device batch boundaries (carry of k-1 bases)"""
+    rng = np.random.default_rng(k + batch)
+    data = make_fasta(rng, 50000, 120, 1500, wrap=80, err=0.005, n_rate=0.0005)
+    want = oracle.count(data, k)
+    keys, counts, st = gpu_count(data, k, batch_bytes=batch)
+    assert st["input_kmers"] == want.total_windows
+    assert_same(keys, counts, want)
+
+
+def test_ragged_feeds(oracle):
+    """the byte stream may be cut anywhere: 1-byte feeds, cuts inside headers, inside windows"""
+    rng = np.random.default_rng(77)
+    data = make_fasta(rng, 5000, 30, 400, wrap=60, n_rate=0.002)
+    want = oracle.count(data, 31)
+
+    def feeder(c, d):
+        pos = 0
+        while pos < len(d):
+            n = int(rng.integers(1, 700))
+            c.feed(d[pos:pos + n])
+            pos += n
+
+    keys, counts, st = gpu_count(data, 31, feeder=feeder, batch_bytes=4096)
+    assert st["input_kmers"] == want.total_windows
+    assert_same(keys, counts, want)
+
+
+def test_context_feed(oracle):
+    """KG_FEED_CONTEXT bytes warm the window but their k-mers are not counted (slice overlap of text_reader.h)"""
+    rng = np.random.default_rng(5)
+    data = make_fasta(rng, 8000, 1, 6000, wrap=70)           # one multi-line record
+    cut = 3001
+    k = 51
+    whole = oracle.count(data, k)
+    first = oracle.count(data[:cut], k)
+
+    def feeder(c, d):
+        c.feed(d[:cut], K.FEED_CONTEXT)
+        c.feed(d[cut:])
+
+    keys, counts, st = gpu_count(data, k, feeder=feeder)
+    assert st["input_kmers"] == whole.total_windows - first.total_windows
+    # second-half counts = whole - first
+    tot = dict(zip(map(bytes, whole.keys.view(np.uint8).reshape(whole.n, -1)), whole.counts))
+    for kk, cc in zip(map(bytes, first.keys.view(np.uint8).reshape(first.n, -1)), first.counts):
+        tot[kk] -= cc
+    want = {kk: cc for kk, cc in tot.items() if cc}
+    got = dict(zip(map(bytes, keys.view(np.uint8).reshape(len(counts), -1)), counts.astype(np.uint64)))
+    assert got == want
+
+
+def test_starts_in_header(oracle):
+    data = b"tail of a broken header ACGTACGTACGTACGTACGTACGTACGT\nACGTTGCAAGGCTTAACCGGTACGT\n>r2\nGGGGGCCCCCAAAAATTTTTACGTAC\n"
+    want = oracle.count(data, 21, oracle.FASTA, starts_in_header=True)
+    keys, counts, st = gpu_count(data, 21, starts_in_header=True)
+    assert st["input_kmers"] == want.total_windows
+    assert_same(keys, counts, want)
+
+
+def test_plain_mode(oracle):
+    rng = np.random.default_rng(9)
+    g = "".join("ACGT"[x] for x in rng.integers(0, 4, 4000))
+    lines = [g[i:i + int(rng.integers(10, 300))] for i in range(0, 3600, 150)]
+    lines[3] = lines[3][:40] + "N" + lines[3][40:]
+    lines[5] = lines[5].lower()
+    data = ("\n".join(lines) + "\n").encode()
+    for k in (21, 51):
+        want = oracle.count(data, k, oracle.PLAIN)
+        keys, counts, st = gpu_count(data, k, K.INPUT_PLAIN)
+        assert st["input_kmers"] == want.total_windows
+        assert_same(keys, counts, want)
+
+
+@pytest.mark.parametrize("data", [b"", b">only a header", b">h\nACGT\n", b">h\n\n\n\n", b">a\n>b\n>c\n", b"\n\n\n",
+                                  b">h\n" + b"N" * 100 + b"\n"])
+def test_empty_and_degenerate(oracle, data):
+    want = oracle.count(data, 21)
+    keys, counts, st = gpu_count(data, 21)
+    assert st["input_kmers"] == want.total_windows == 0
+    assert len(counts) == 0
+
+
+def test_count_width_emulation(oracle):
+    """uint16 wrap (-m 0) and 14-bit saturation (-m 2) of the reported counts; golden from the reference"""
+    data = _read("g4_polya.fasta")
+    want = oracle.count(data, 21)
+    keys, counts, _ = gpu_count(data, 21, a=2, count_mode=K.COUNT_REFERENCE)
+    assert_same(keys, counts, want.filtered(2, oracle.TABLE_PLAIN))
+    keys, counts, _ = gpu_count(data, 21, a=2, count_mode=K.COUNT_EXACT)
+    assert_same(keys, counts, want.filtered(2, oracle.TABLE_EXACT))
+    assert int(counts.max()) == 89960
+
+
+def test_table_full_is_an_error():
+    rng = np.random.default_rng(3)
+    data = make_fasta(rng, 20000, 20, 1000)
+    with kg.Counter(k=31, min_slots=1000) as c:
+        c.pass_begin(K.PASS_COUNT)
+        c.stream_begin()
+        c.feed(data)
+        with pytest.raises(kg.TableFull):
+            c.pass_end()
+
+
+def test_host_pinned_and_device_feeds_agree(oracle):
+    import torch
+    rng = np.random.default_rng(11)
+    data = make_fasta(rng, 30000, 100, 1000, wrap=80, err=0.01)
+    want = oracle.count(data, 51)
+    t = torch.frombuffer(bytearray(data), dtype=torch.uint8)
+    for src in (data, t.pin_memory(), t.cuda()):
+        keys, counts, st = gpu_count(src, 51, batch_bytes=16384)
+        assert st["input_kmers"] == want.total_windows
+        assert_same(keys, counts, want)
+
+
+def test_min_abundance_zero_writes_nothing():
+    data = b">r\nACGTACGTACGTACGTACGTACGTACGTACGT\n"
+    keys, counts, _ = gpu_count(data, 21, a=0)
+    assert len(counts) == 0
+
+
+def test_medium_config3_shape(oracle):
+    """BASELINE config 3 shape at 1/50 scale (5 Mbp x 1x coverage of 150 bp reads, 1 % error, k=31): exact parity,
+    plus the size-independent checks used at full size: sum(counts) == input k-mers, sorted unique keys."""
+    rng = np.random.default_rng(42)
+    data = make_fasta(rng, 5_000_000, 33_000, 150, err=0.01)
+    want = oracle.count(data, 31)
+    keys, counts, st = gpu_count(data, 31, slots=16_000_000)
+    assert st["input_kmers"] == want.total_windows
+    assert int(counts.astype(np.uint64).sum()) == st["input_kmers"]
+    assert_same(keys, counts, want)
