@@ -1,0 +1,357 @@
+#!/usr/bin/env python3
+"""bench.py -- the driver's measurement contract for the k-mer counting hot path.
+
+    python bench.py --gpus N --steps K --warmup W          (N > 1: launched under torchrun, one rank per GPU)
+    python bench.py --impl reference --gpus N --steps K --warmup W
+
+metric   input k-mers/s (BASELINE.json), k=51, config C4 (100 Mbp genome, 20x of 10 kbp reads, -m 0
+         -s 250000000): the configuration the metric is quoted on; fits one GPU (2.03 GB FASTA + 8 GB table).
+step     one full counting pass over the whole synthetic read set into a freshly cleared table
+         (kg_pass_begin .. kg_pass_end through the C ABI).
+value    device-timed (CUDA events inside the library, compute stream), input already resident in HBM.
+e2e      same pass fed from PINNED HOST memory through kg_feed (H2D inside the timed region) + the D2H read of
+         the pass statistics; wall clock bracketed by synchronize.
+N > 1    weak scaling: every rank draws its own 20x read set from a genome N times larger, k-mers are
+         hash-sharded across ranks and exchanged with NCCL.
+Only the cpu_baseline / --impl reference legs execute anything under oracle/ (the unmodified reference
+binary oracle/_ref/kaarme when it was built, else the C port) -- as the thing being compared against.
+"""
+import argparse
+import importlib
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "input_kmers_per_sec_k51"
+UNIT = "k-mers/s"
+WORKLOAD = "C4"
+K = 51
+
+
+def parse_args():
+    p = argparse.ArgumentParser()
+    p.add_argument("--gpus", type=int, default=1)
+    p.add_argument("--steps", type=int, default=5)
+    p.add_argument("--warmup", type=int, default=3)
+    p.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    p.add_argument("--scale", type=float, default=float(os.environ.get("KAARME_BENCH_SCALE", "1.0")),
+                   help="fraction of the named workload (1.0 = the BASELINE configuration; <1 only for debugging)")
+    p.add_argument("--k", type=int, default=K)
+    p.add_argument("--workload", default=WORKLOAD)
+    p.add_argument("--no-cpu-baseline", action="store_true")
+    p.add_argument("--no-e2e", action="store_true")
+    return p.parse_args()
+
+
+# ---- clocks ------------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if self.proc:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=5)
+            except Exception:
+                self.proc.kill()
+        sm = [float(r[0]) for r in self.rows if len(r) >= 7 and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) >= 7 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({n for r in self.rows if len(r) >= 7 for n, v in zip(names, r[3:7]) if v == "Active"})
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(sm)}
+
+
+# ---- CPU reference leg -----------------------------------------------------------------------------------------
+def cpu_reference_run(sample_path, k, slots, threads, timeout=1500):
+    """Time the reference's own CPU implementation (oracle/_ref/kaarme) on a sample file; returns seconds
+    ('Time used to build hash table', parallel_parser.hpp:865-867: file read + count, no writing)."""
+    import oracle.oracle_py as o  # the one place bench.py executes oracle/: as the baseline being measured
+    out = sample_path + ".out"
+    cmd = [o.REF_BIN, sample_path, str(k), "-m", "0", "-s", str(slots), "-a", "2", "-t", str(threads), "-o", out]
+    p = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, timeout=timeout, text=True)
+    if os.path.exists(out):
+        os.remove(out)
+    for line in p.stdout.splitlines():
+        if line.startswith("Time used to build hash table:"):
+            return int(line.split()[-2]) * 1e-6
+    raise RuntimeError("reference run failed: " + p.stdout[-500:])
+
+
+def cpu_port_run(sample_bytes, k):
+    import oracle.oracle_py as o
+    t0 = time.perf_counter()
+    c = o.count(sample_bytes, k)
+    return time.perf_counter() - t0, c.total_windows
+
+
+def make_sample(meta, fasta_cuda, max_bytes):
+    """First whole records of the workload, at most max_bytes -> (bytes, n_reads, input_kmers)."""
+    rec = meta["record_bytes"]
+    n = max(1, min(meta["n_reads"], max_bytes // rec))
+    data = fasta_cuda[: n * rec].cpu().numpy().tobytes()
+    return data, n, n * (meta["L"] - meta["k"] + 1)
+
+
+def cpu_baseline(meta, fasta_cuda, k, target_seconds=20.0):
+    import oracle.oracle_py as o
+    cores = os.cpu_count() or 1
+    if o.have_ref():
+        threads = max(3, min(64, cores))
+        # one 10 MiB chunk per worker is the reference's only parallelism (parallel_parser.hpp:834-843)
+        data, n, kmers = make_sample(meta, fasta_cuda, (threads - 2) * (10 << 20))
+        path = f"/dev/shm/kaarme_bench_sample_{os.getpid()}.fasta"
+        with open(path, "wb") as f:
+            f.write(data)
+        try:
+            secs = cpu_reference_run(path, k, max(1000, int(2.5 * min(kmers, meta["G"]))), threads)
+        finally:
+            os.remove(path)
+        return {"value": kmers / secs, "unit": UNIT, "cores": threads - 2, "kind": "reference", "host_cores": cores,
+                "sample": f"first {n} reads ({len(data)} bytes, {kmers} input k-mers) of {meta['name']}, "
+                          f"oracle/_ref/kaarme -m 0 -t {threads}, its own build-table timer", "seconds": secs}
+    data, n, kmers = make_sample(meta, fasta_cuda, 64 << 20)
+    secs, tw = cpu_port_run(data, k)
+    return {"value": tw / secs, "unit": UNIT, "cores": 1, "kind": "port", "host_cores": cores,
+            "sample": f"first {n} reads ({len(data)} bytes) of {meta['name']}, oracle/liboracle.so ko_count", "seconds": secs}
+
+
+# ---- main ------------------------------------------------------------------------------------------------------
+def main():
+    args = parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference" and rank != 0:
+        return 0
+    import torch
+    import torch.distributed as dist
+    import bench_data
+
+    k = args.k
+    if args.impl == "reference":
+        return run_reference(args, torch, bench_data)
+
+    if not torch.cuda.is_available():
+        print(json.dumps({"metric": METRIC, "error": "no CUDA device: the product path has no CPU fallback"}))
+        return 2
+    kg = importlib.import_module("canonical-k-mer-hash-table_b200")
+    KG = kg.kaarme_gpu
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    if args.gpus != world and rank == 0 and world > 1:
+        print(f"warning: --gpus {args.gpus} but WORLD_SIZE {world}", file=sys.stderr)
+
+    fasta, meta = bench_data.make_config(args.workload, dev, scale=args.scale, rank=rank, world=world)
+    meta["name"] = args.workload
+    meta["k"] = k
+    meta["input_kmers"] = meta["n_reads"] * (meta["L"] - k + 1)
+    torch.cuda.synchronize()
+    total_slots = meta["slots"] * world
+    ctr = kg.Counter(k=k, table_mode=KG.TABLE_PLAIN, input_mode=KG.INPUT_FASTA, min_slots=total_slots,
+                     device=local_rank, rank=rank, world=world, batch_bytes=256 << 20)
+    if world > 1:
+        uid = [kg.comm_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(uid, src=0)
+        ctr.comm_init(uid[0], rank, world)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step_device():
+        ctr.pass_begin(KG.PASS_COUNT)
+        ctr.stream_begin(False)
+        ctr.feed_device(fasta.data_ptr(), fasta.numel())
+        return ctr.pass_end()
+
+    # ---- device-resident metric -------------------------------------------------------------------------------
+    for _ in range(args.warmup):
+        st = step_device()
+    assert st["input_kmers"] == meta["input_kmers"], (st["input_kmers"], meta["input_kmers"])
+    launches0 = ctr.launch_count()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    barrier()
+    t0 = time.perf_counter()
+    dev_ms, count_ms, parse_ms = 0.0, 0.0, 0.0
+    for _ in range(args.steps):
+        st = step_device()
+        dev_ms += st["device_ms"]
+        count_ms += st["count_ms"]
+        parse_ms += st["parse_ms"]
+    barrier()
+    wall = time.perf_counter() - t0
+    clocks = sampler.stop()
+    launches = ctr.launch_count() - launches0
+    distinct = st["distinct"]
+    t = torch.tensor([dev_ms, wall * 1e3, count_ms, parse_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    dev_ms, wall_ms, count_ms, parse_ms = t.tolist()
+    total_kmers = meta["input_kmers"] * world
+    value = total_kmers * args.steps / (dev_ms * 1e-3)
+
+    # ---- end to end through the C ABI from pinned host memory --------------------------------------------------
+    e2e = None
+    if not args.no_e2e:
+        host = torch.empty(fasta.numel(), dtype=torch.uint8, pin_memory=True)
+        host.copy_(fasta)
+        torch.cuda.synchronize()
+
+        def step_host():
+            ctr.pass_begin(KG.PASS_COUNT)
+            ctr.stream_begin(False)
+            ctr.feed(host)
+            return ctr.pass_end()
+
+        for _ in range(min(args.warmup, 2)):
+            step_host()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            st2 = step_host()
+        barrier()
+        e2e_s = time.perf_counter() - t0
+        te = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(te, op=dist.ReduceOp.MAX)
+        assert st2["input_kmers"] == meta["input_kmers"]
+        import ctypes
+        e2e = {"value": total_kmers * args.steps / te.item(), "unit": UNIT,
+               "h2d_bytes_per_step": int(fasta.numel()) * world,
+               "d2h_bytes_per_step": ctypes.sizeof(KG.PassStats) * world,
+               "ms_per_step": te.item() * 1e3 / args.steps}
+        del host
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return 0
+
+    # ---- roofline of the dominant kernel (kg_count_kernel<W,TABLE>) --------------------------------------------
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(peaks_path):
+        peak, peak_src = json.load(open(peaks_path))["hbm_gbs"], "measured (MEASURED_PEAKS.json hbm_gbs)"
+    else:
+        peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
+    W = (k + 31) // 32
+    S = -(-(8 * W + 4) // 32)
+    rec = meta["record_bytes"]
+    bytes_per_kmer = rec / (meta["L"] - k + 1) + 2 * 32 * S
+    achieved = meta["input_kmers"] * args.steps * bytes_per_kmer / (count_ms * 1e-3) / 1e9
+    traffic = None
+    tp = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tp):
+        traffic = json.load(open(tp)).get(f"kg_count_kernel_W{W}", {}).get("dram_bytes_per_launch")
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": traffic, "kernel": f"kg_count_kernel<{W},TABLE>", "peak_source": peak_src,
+                "bytes_per_kmer": bytes_per_kmer, "kernel_share_of_step": count_ms / dev_ms}
+    try:
+        ceil_sectors = kg.atomic_ceiling(local_rank, region_bytes=8 << 30, n_ops=1 << 29, reps=2)
+        kmers_per_s_kernel = meta["input_kmers"] * args.steps / (count_ms * 1e-3)
+        roofline["atomic"] = {"ceiling_sectors_per_s": ceil_sectors, "achieved_sectors_per_s": kmers_per_s_kernel * S,
+                              "frac": kmers_per_s_kernel * S / ceil_sectors,
+                              "how": "uniform-random RED.ADD on 32-byte sectors over 8 GiB (kg_atomic_ceiling)"}
+    except Exception as e:  # noqa: BLE001
+        roofline["atomic"] = {"error": str(e)}
+
+    out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+           "ms_per_step": dev_ms / args.steps, "wall_ms_per_step": wall_ms / args.steps, "higher_is_better": True,
+           "scaling": "weak", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
+           "config": {"workload": f"{args.workload}: {meta['G']} bp genome, {meta['cov']}x of {meta['L']} bp reads, "
+                                  f"k={k}, -m 0 -s {total_slots}", "scale": args.scale, "fasta_bytes_per_gpu": int(fasta.numel()),
+                      "input_kmers_per_gpu": meta["input_kmers"], "distinct_rank0": distinct,
+                      "l2": "inputs (2 GB) and table (8 GB) are far larger than L2; no flush needed",
+                      "parallelism": f"hash-sharded x{world}" if world > 1 else "single GPU"},
+           "clocks": clocks, "gpu_launches": launches, "roofline": roofline, "e2e": e2e,
+           "stage_ms_per_step": {"parse": parse_ms / args.steps, "count": count_ms / args.steps}}
+    if world == 1 and not args.no_cpu_baseline:
+        try:
+            out["cpu_baseline"] = cpu_baseline(meta, fasta, k)
+        except Exception as e:  # noqa: BLE001
+            out["cpu_baseline"] = {"error": str(e)}
+    print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+def run_reference(args, torch, bench_data):
+    """--impl reference: the reference's own CPU counter on this box's host cores, bounded sample per step."""
+    import oracle.oracle_py as o
+    k = args.k
+    dev = torch.device("cuda", 0) if torch.cuda.is_available() else torch.device("cpu")
+    cores = os.cpu_count() or 1
+    threads = max(3, min(64, cores))
+    c = dict(bench_data.CONFIGS[args.workload])
+    # generate only what the sample needs (same generator, same seeds as the GPU arm's rank 0)
+    rec = bench_data.record_bytes(c["L"], c["wrap"], 9)
+    sample_bytes = (threads - 2) * (10 << 20) if o.have_ref() else (64 << 20)
+    n = max(1, min(int(c["G"] * c["cov"] / c["L"] * args.scale), sample_bytes // rec))
+    genome = bench_data.make_genome(int(c["G"] * args.scale), c["seed"], dev)
+    fasta = bench_data.make_reads_fasta(genome, n, c["L"], seed=c["seed"] * 1000, err=c["err"], wrap=c["wrap"])
+    data = fasta.cpu().numpy().tobytes()
+    kmers = n * (c["L"] - k + 1)
+    times = []
+    if o.have_ref():
+        path = f"/dev/shm/kaarme_bench_ref_{os.getpid()}.fasta"
+        with open(path, "wb") as f:
+            f.write(data)
+        try:
+            for i in range(args.warmup + args.steps):
+                s = cpu_reference_run(path, k, max(1000, int(2.5 * min(kmers, c["G"] * args.scale))), threads)
+                if i >= args.warmup:
+                    times.append(s)
+        finally:
+            os.remove(path)
+        kind, used = "reference", threads - 2
+    else:
+        for i in range(args.warmup + args.steps):
+            s, _ = cpu_port_run(data, k)
+            if i >= args.warmup:
+                times.append(s)
+        kind, used = "port", 1
+    value = kmers * len(times) / sum(times)
+    sample = f"first {n} reads ({len(data)} bytes, {kmers} input k-mers) of {args.workload} per step"
+    out = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+           "warmup": args.warmup, "ms_per_step": 1e3 * sum(times) / len(times), "higher_is_better": True, "scaling": "weak",
+           "vs_baseline": None, "dtype": "u64", "data": "synthetic",
+           "config": {"workload": f"{args.workload}: {int(c['G'] * args.scale)} bp genome, {c['cov']}x of {c['L']} bp reads, k={k}, -m 0",
+                      "scale": args.scale},
+           "cpu_baseline": {"value": value, "unit": UNIT, "cores": used, "kind": kind, "sample": sample, "host_cores": cores},
+           "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(out))
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())
