@@ -5,6 +5,6 @@ kaarme_gpu.py (ctypes binding used by tests and bench).  Import with
     importlib.import_module("canonical-k-mer-hash-table_b200")
 """
 from .kaarme_gpu import *  # noqa: F401,F403
-from .kaarme_gpu import (Counter, KaarmeError, TableFull, lib, device_count, atomic_ceiling, keys_to_text,
+from .kaarme_gpu import (Counter, KaarmeError, TableFull, lib, device_count, atomic_ceiling, keys_to_text, comm_unique_id,
                          parse_input_atomic_flag, parse_input_atomic_flag_BF, parse_input_pointer_atomic_variable,
                          parse_input_pointer_atomic_variable_BF, EXPORTS, LIB_PATH)

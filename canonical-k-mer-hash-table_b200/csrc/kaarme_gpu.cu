@@ -11,6 +11,9 @@
 #include <string>
 #include <vector>
 
+#include <dlfcn.h>
+#include <nccl.h>   // types and prototypes only: the library is bound at run time (see kg_nccl below)
+
 #include "kg_count.cuh"
 #include "kg_device.cuh"
 #include "kg_parse.cuh"
@@ -43,7 +46,7 @@ struct kg_ctx {
     u32 carry_max_words = 0;
     KgStream* d_stream = nullptr;
     KgStats* d_stats = nullptr;
-    KgTable table{nullptr, 0, 0, 0};
+    KgTable table{nullptr, 0, 0, 0, 1, 0};
     size_t table_bytes = 0;
     KgBloom bloom{nullptr, 0, 0};
     size_t bloom_bytes = 0;
@@ -67,10 +70,57 @@ struct kg_ctx {
     u32* h_out_n = nullptr;
     size_t out_chunk = 0;
     cudaEvent_t ev_out[2] = {nullptr, nullptr};
+    // bucketed path (multi-GPU exchange, or partitions > 1 on one GPU)
+    bool bucketed = false;
+    u32 nb = 0;                         // buckets = world (multi-GPU) or partitions (single GPU)
+    ncclComm_t comm = nullptr;
+    cudaStream_t s_comm = nullptr, s_insert = nullptr;
+    u64* d_send[2] = {nullptr, nullptr};
+    u64* d_recv[2] = {nullptr, nullptr};
+    size_t send_cap = 0, recv_cap = 0;  // in keys
+    u32 *d_blk_hist = nullptr, *d_blk_base = nullptr;
+    u32 max_blocks = 0;
+    u32 *d_bucket_counts = nullptr, *d_bucket_offs = nullptr, *d_matrix = nullptr, *h_matrix = nullptr;
+    cudaEvent_t ev_counts = nullptr, ev_scatter = nullptr, ev_matrix = nullptr, ev_pass_ready = nullptr, ev_tail = nullptr;
+    cudaEvent_t ev_send_free[2] = {nullptr, nullptr}, ev_recv_free[2] = {nullptr, nullptr}, ev_recv_full[2] = {nullptr, nullptr};
+    uint64_t round = 0, subround = 0;
     std::string err;
 };
 
 static thread_local std::string g_err;
+
+// NCCL is resolved with dlopen at first use instead of a link-time dependency: inside a Python process torch
+// has already loaded its own (newer) libnccl.so.2, and a DT_NEEDED on the system copy would either shadow it
+// (breaking `import torch`) or be shadowed by it.  dlopen by soname returns whichever copy is already mapped.
+struct KgNccl {
+    void* handle = nullptr;
+    decltype(&ncclGetUniqueId) GetUniqueId = nullptr;
+    decltype(&ncclCommInitRank) CommInitRank = nullptr;
+    decltype(&ncclCommDestroy) CommDestroy = nullptr;
+    decltype(&ncclAllGather) AllGather = nullptr;
+    decltype(&ncclSend) Send = nullptr;
+    decltype(&ncclRecv) Recv = nullptr;
+    decltype(&ncclGroupStart) GroupStart = nullptr;
+    decltype(&ncclGroupEnd) GroupEnd = nullptr;
+    decltype(&ncclGetErrorString) GetErrorString = nullptr;
+    bool ok = false;
+};
+static KgNccl& kg_nccl() {
+    static KgNccl n;
+    if (!n.handle) {
+        n.handle = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+        if (!n.handle) n.handle = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+        if (n.handle) {
+#define KG_SYM(name) n.name = (decltype(n.name))dlsym(n.handle, "nccl" #name)
+            KG_SYM(GetUniqueId); KG_SYM(CommInitRank); KG_SYM(CommDestroy); KG_SYM(AllGather); KG_SYM(Send);
+            KG_SYM(Recv); KG_SYM(GroupStart); KG_SYM(GroupEnd); KG_SYM(GetErrorString);
+#undef KG_SYM
+            n.ok = n.GetUniqueId && n.CommInitRank && n.CommDestroy && n.AllGather && n.Send && n.Recv &&
+                   n.GroupStart && n.GroupEnd && n.GetErrorString;
+        }
+    }
+    return n;
+}
 
 #define KG_CUDA(ctx, call)                                                                            \
     do {                                                                                              \
@@ -166,6 +216,20 @@ static void free_all(kg_ctx* c) {
         if (c->ev_out[i]) cudaEventDestroy(c->ev_out[i]);
     }
     if (c->h_out_n) cudaFreeHost(c->h_out_n);
+    if (c->s_comm) cudaStreamSynchronize(c->s_comm);
+    if (c->s_insert) cudaStreamSynchronize(c->s_insert);
+    if (c->comm) { kg_nccl().CommDestroy(c->comm); c->comm = nullptr; }
+    for (int i = 0; i < 2; i++) {
+        cudaFree(c->d_send[i]); cudaFree(c->d_recv[i]);
+        if (c->ev_send_free[i]) cudaEventDestroy(c->ev_send_free[i]);
+        if (c->ev_recv_free[i]) cudaEventDestroy(c->ev_recv_free[i]);
+        if (c->ev_recv_full[i]) cudaEventDestroy(c->ev_recv_full[i]);
+    }
+    cudaFree(c->d_blk_hist); cudaFree(c->d_blk_base); cudaFree(c->d_bucket_counts); cudaFree(c->d_bucket_offs); cudaFree(c->d_matrix);
+    if (c->h_matrix) cudaFreeHost(c->h_matrix);
+    for (cudaEvent_t e : {c->ev_counts, c->ev_scatter, c->ev_matrix, c->ev_pass_ready, c->ev_tail}) if (e) cudaEventDestroy(e);
+    if (c->s_comm) cudaStreamDestroy(c->s_comm);
+    if (c->s_insert) cudaStreamDestroy(c->s_insert);
     cudaFree(c->d_tile_hdr_eff); cudaFree(c->d_tile_hdr_in); cudaFree(c->d_tile_nbases);
     cudaFree(c->d_tile_pend_eff); cudaFree(c->d_tile_pend_in); cudaFree(c->d_tile_off);
     cudaFree(c->d_words); cudaFree(c->d_brk); cudaFree(c->d_carry_words); cudaFree(c->d_carry_brk);
@@ -189,6 +253,8 @@ extern "C" int kg_create(const kg_config* cfg, kg_ctx** out) {
         if (cfg->expected_unique == 0 || !(cfg->fpr > 0.0 && cfg->fpr < 1.0)) { g_err = "bloom needs expected_unique > 0 and 0 < fpr < 1"; return KG_EBADARG; }
     } else if (cfg->min_slots == 0) { g_err = "min_slots must be > 0"; return KG_EBADARG; }
     if (cfg->world < 1 || cfg->rank < 0 || cfg->rank >= cfg->world) { g_err = "bad rank/world"; return KG_EBADARG; }
+    if (cfg->world > KG_MAX_BUCKETS || cfg->partitions > KG_MAX_BUCKETS) { g_err = "world / partitions must be <= 32"; return KG_EBADARG; }
+    if (cfg->world > 1 && cfg->partitions > 1) { g_err = "partitions > 1 is a single-GPU option"; return KG_EBADARG; }
 
     int ndev = 0;
     cudaError_t e = cudaGetDeviceCount(&ndev);
@@ -260,6 +326,34 @@ extern "C" int kg_create(const kg_config* cfg, kg_ctx** out) {
         c->bloom_bytes = nblocks * 64;
         KG_TRY(cudaMalloc(&c->bloom.bits, c->bloom_bytes));
     }
+    c->bucketed = cfg->world > 1 || cfg->partitions > 1;
+    if (c->bucketed) {
+        c->nb = cfg->world > 1 ? (u32)cfg->world : cfg->partitions;
+        const size_t max_words = c->batch_bytes / 32 + c->carry_max_words + 2;
+        c->max_blocks = (u32)((max_words + 255) / 256);
+        c->send_cap = c->batch_bytes + 64;                       // a batch of n bytes holds < n k-mers
+        c->recv_cap = cfg->world > 1 ? 2 * c->send_cap : 0;      // single GPU inserts straight from the send buffer
+        KG_TRY(cudaStreamCreateWithFlags(&c->s_comm, cudaStreamNonBlocking));
+        KG_TRY(cudaStreamCreateWithFlags(&c->s_insert, cudaStreamNonBlocking));
+        for (int i = 0; i < 2; i++) {
+            KG_TRY(cudaMalloc(&c->d_send[i], c->send_cap * c->W * sizeof(u64)));
+            if (c->recv_cap) KG_TRY(cudaMalloc(&c->d_recv[i], c->recv_cap * c->W * sizeof(u64)));
+            KG_TRY(cudaEventCreateWithFlags(&c->ev_send_free[i], cudaEventDisableTiming));
+            KG_TRY(cudaEventCreateWithFlags(&c->ev_recv_free[i], cudaEventDisableTiming));
+            KG_TRY(cudaEventCreateWithFlags(&c->ev_recv_full[i], cudaEventDisableTiming));
+        }
+        KG_TRY(cudaMalloc(&c->d_blk_hist, sizeof(u32) * (size_t)c->max_blocks * c->nb));
+        KG_TRY(cudaMalloc(&c->d_blk_base, sizeof(u32) * (size_t)c->max_blocks * c->nb));
+        KG_TRY(cudaMalloc(&c->d_bucket_counts, sizeof(u32) * (c->nb + 1)));
+        KG_TRY(cudaMalloc(&c->d_bucket_offs, sizeof(u32) * (c->nb + 1)));
+        KG_TRY(cudaMalloc(&c->d_matrix, sizeof(u32) * (size_t)(c->nb + 1) * cfg->world));
+        KG_TRY(cudaHostAlloc((void**)&c->h_matrix, sizeof(u32) * (size_t)(c->nb + 1) * cfg->world, cudaHostAllocDefault));
+        KG_TRY(cudaEventCreateWithFlags(&c->ev_counts, cudaEventDisableTiming));
+        KG_TRY(cudaEventCreateWithFlags(&c->ev_scatter, cudaEventDisableTiming));
+        KG_TRY(cudaEventCreateWithFlags(&c->ev_matrix, cudaEventDisableTiming));
+        KG_TRY(cudaEventCreateWithFlags(&c->ev_pass_ready, cudaEventDisableTiming));
+        KG_TRY(cudaEventCreateWithFlags(&c->ev_tail, cudaEventDisableTiming));
+    }
 #undef KG_TRY
     *out = c;
     return KG_OK;
@@ -272,15 +366,39 @@ extern "C" int kg_destroy(kg_ctx* c) {
     return KG_OK;
 }
 
+#define KG_NCCL(ctx, call)                                                                           \
+    do {                                                                                              \
+        ncclResult_t r_ = (call);                                                                     \
+        if (r_ != ncclSuccess) {                                                                      \
+            char buf_[512];                                                                           \
+            snprintf(buf_, sizeof(buf_), "%s:%d %s -> %s", __FILE__, __LINE__, #call, kg_nccl().GetErrorString(r_)); \
+            if (ctx) (ctx)->err = buf_;                                                               \
+            g_err = buf_;                                                                             \
+            return KG_ENCCL;                                                                          \
+        }                                                                                             \
+    } while (0)
+
 extern "C" int kg_comm_unique_id(void* id_out) {
-    (void)id_out;
-    g_err = "multi-GPU exchange not built into this library yet";
-    return KG_ENCCL;
+    if (!id_out) return KG_EBADARG;
+    static_assert(sizeof(ncclUniqueId) <= KG_UNIQUE_ID_BYTES, "unique id size");
+    ncclUniqueId id;
+    kg_ctx* none = nullptr;
+    if (!kg_nccl().ok) { g_err = "libnccl.so.2 could not be loaded"; return KG_ENCCL; }
+    KG_NCCL(none, kg_nccl().GetUniqueId(&id));
+    memset(id_out, 0, KG_UNIQUE_ID_BYTES);
+    memcpy(id_out, &id, sizeof(id));
+    return KG_OK;
 }
-extern "C" int kg_comm_init(kg_ctx* ctx, const void* id, int rank, int world) {
-    (void)id; (void)rank; (void)world;
-    if (ctx) ctx->err = "multi-GPU exchange not built into this library yet";
-    return KG_ENCCL;
+
+extern "C" int kg_comm_init(kg_ctx* c, const void* id, int rank, int world) {
+    if (!c || !id) return KG_EBADARG;
+    if (rank != c->cfg.rank || world != c->cfg.world || world < 2) { c->err = "kg_comm_init: rank/world differ from kg_config"; return KG_EBADARG; }
+    KG_CUDA(c, cudaSetDevice(c->cfg.device));
+    ncclUniqueId uid;
+    memcpy(&uid, id, sizeof(uid));
+    if (!kg_nccl().ok) { c->err = "libnccl.so.2 could not be loaded"; return KG_ENCCL; }
+    KG_NCCL(c, kg_nccl().CommInitRank(&c->comm, world, uid, rank));
+    return KG_OK;
 }
 
 // -----------------------------------------------------------------------------------------------------------
@@ -288,6 +406,7 @@ extern "C" int kg_pass_begin(kg_ctx* c, int pass) {
     if (!c || (pass != KG_PASS_BLOOM && pass != KG_PASS_COUNT)) return KG_EBADARG;
     if (pass == KG_PASS_BLOOM && !c->cfg.use_bloom) { c->err = "Bloom pass without use_bloom"; return KG_EBADARG; }
     if (pass == KG_PASS_COUNT && c->cfg.use_bloom && !c->bloom_done) { c->err = "count pass before Bloom pass"; return KG_EBADARG; }
+    if (c->cfg.world > 1 && !c->comm) { c->err = "world > 1 needs kg_comm_init first"; return KG_EBADARG; }
     KG_CUDA(c, cudaSetDevice(c->cfg.device));
     c->pass = pass;
     c->stream_open = false;
@@ -313,7 +432,12 @@ extern "C" int kg_pass_begin(kg_ctx* c, int pass) {
         c->table.nslots = nslots;
         c->table.stride = stride;
         c->table.kaarme = c->cfg.table_mode == KG_TABLE_KAARME;
+        c->table.world = (u32)c->cfg.world;
         KG_CUDA(c, cudaMemsetAsync(c->table.slots, 0, bytes, c->s_compute));
+    }
+    if (c->cfg.world > 1) {   // inserts run on their own stream: order them after the clears above
+        KG_CUDA(c, cudaEventRecord(c->ev_pass_ready, c->s_compute));
+        KG_CUDA(c, cudaStreamWaitEvent(c->s_insert, c->ev_pass_ready, 0));
     }
     return KG_OK;
 }
@@ -355,6 +479,151 @@ static void launch_count(kg_ctx* c, const KgCountArgs& a, u32 nthreads_words, in
     c->launches++;
 }
 
+static int current_sink(const kg_ctx* c) {
+    return c->pass == KG_PASS_BLOOM ? KG_SINK_BLOOM1 : (c->cfg.use_bloom ? KG_SINK_BLOOM2 : KG_SINK_TABLE);
+}
+
+template <int W>
+static void launch_insert_keys(kg_ctx* c, cudaStream_t s, const u64* keys, u64 n_upper, const u32* n_dev, int sink) {
+    const u32 block = 256;
+    const u64 grid = (n_upper + block - 1) / block;
+    if (grid == 0) return;
+    switch (sink) {
+        case KG_SINK_TABLE: kg_insert_keys_kernel<W, KG_SINK_TABLE><<<(u32)grid, block, 0, s>>>(keys, n_upper, n_dev, c->table, c->bloom, c->d_stats); break;
+        case KG_SINK_BLOOM1: kg_insert_keys_kernel<W, KG_SINK_BLOOM1><<<(u32)grid, block, 0, s>>>(keys, n_upper, n_dev, c->table, c->bloom, c->d_stats); break;
+        case KG_SINK_BLOOM2: kg_insert_keys_kernel<W, KG_SINK_BLOOM2><<<(u32)grid, block, 0, s>>>(keys, n_upper, n_dev, c->table, c->bloom, c->d_stats); break;
+        default: break;
+    }
+    c->launches++;
+}
+
+static void insert_keys(kg_ctx* c, cudaStream_t s, const u64* keys, u64 n_upper, const u32* n_dev) {
+    const int sink = current_sink(c);
+    switch (c->W) {
+        case 1: launch_insert_keys<1>(c, s, keys, n_upper, n_dev, sink); break;
+        case 2: launch_insert_keys<2>(c, s, keys, n_upper, n_dev, sink); break;
+        case 3: launch_insert_keys<3>(c, s, keys, n_upper, n_dev, sink); break;
+        case 4: launch_insert_keys<4>(c, s, keys, n_upper, n_dev, sink); break;
+        case 5: launch_insert_keys<5>(c, s, keys, n_upper, n_dev, sink); break;
+        case 6: launch_insert_keys<6>(c, s, keys, n_upper, n_dev, sink); break;
+        case 7: launch_insert_keys<7>(c, s, keys, n_upper, n_dev, sink); break;
+        case 8: launch_insert_keys<8>(c, s, keys, n_upper, n_dev, sink); break;
+    }
+}
+
+template <int W>
+static void launch_bucket(kg_ctx* c, const KgBucketArgs& a, u32 grid, bool scatter) {
+    if (scatter) kg_owner_scatter<W><<<grid, 256, 0, c->s_compute>>>(a);
+    else kg_owner_hist<W><<<grid, 256, 0, c->s_compute>>>(a);
+    c->launches++;
+}
+static void bucket_kernel(kg_ctx* c, const KgBucketArgs& a, u32 grid, bool scatter) {
+    switch (c->W) {
+        case 1: launch_bucket<1>(c, a, grid, scatter); break;
+        case 2: launch_bucket<2>(c, a, grid, scatter); break;
+        case 3: launch_bucket<3>(c, a, grid, scatter); break;
+        case 4: launch_bucket<4>(c, a, grid, scatter); break;
+        case 5: launch_bucket<5>(c, a, grid, scatter); break;
+        case 6: launch_bucket<6>(c, a, grid, scatter); break;
+        case 7: launch_bucket<7>(c, a, grid, scatter); break;
+        case 8: launch_bucket<8>(c, a, grid, scatter); break;
+    }
+}
+
+// One exchange round (collective when world > 1).  have_batch: this rank's send buffer (round & 1) was just
+// filled by bucket_batch; otherwise the rank contributes nothing and reports "done".  Returns via *all_done
+// whether every rank reported done in this round.
+//   s_comm:   all-gather of the per-destination counts -> host; grouped ncclSend/ncclRecv of the key slices
+//   s_insert: insert kernel over what arrived, overlapping the next batch's parse + bucketing on s_compute
+static int exchange_round(kg_ctx* c, bool have_batch, bool* all_done) {
+    const u32 nb = c->nb, world = (u32)c->cfg.world, rank = (u32)c->cfg.rank;
+    const int sb = (int)(c->round & 1);
+    const size_t row = nb + 1;
+    if (!have_batch) {
+        KG_CUDA(c, cudaMemsetAsync(c->d_bucket_counts, 0, sizeof(u32) * nb, c->s_compute));
+        KG_CUDA(c, cudaMemsetAsync(c->d_bucket_counts + nb, 1, sizeof(u32), c->s_compute));   // non-zero = done
+        KG_CUDA(c, cudaEventRecord(c->ev_counts, c->s_compute));
+    }
+    KG_CUDA(c, cudaStreamWaitEvent(c->s_comm, c->ev_counts, 0));
+    KG_NCCL(c, kg_nccl().AllGather(c->d_bucket_counts, c->d_matrix, row, ncclUint32, c->comm, c->s_comm));
+    KG_CUDA(c, cudaMemcpyAsync(c->h_matrix, c->d_matrix, sizeof(u32) * row * world, cudaMemcpyDeviceToHost, c->s_comm));
+    KG_CUDA(c, cudaEventRecord(c->ev_matrix, c->s_comm));
+    KG_CUDA(c, cudaEventSynchronize(c->ev_matrix));
+    const u32* M = c->h_matrix;   // M[r*row + d] = keys rank r holds for destination d; M[r*row + nb] = done flag
+    bool done = true;
+    u64 max_in = 0, any = 0;
+    for (u32 r = 0; r < world; r++) done = done && M[r * row + nb] != 0;
+    for (u32 d = 0; d < world; d++) {
+        u64 in = 0;
+        for (u32 r = 0; r < world; r++) in += M[r * row + d];
+        if (in > max_in) max_in = in;
+        any += in;
+    }
+    *all_done = done;
+    if (any) {
+        // sub-rounds so that no rank receives more than recv_cap keys at once (identical on every rank)
+        const u64 S = (max_in + c->recv_cap - 1) / c->recv_cap;
+        std::vector<u64> send_off(world + 1, 0);
+        for (u32 d = 0; d < world; d++) send_off[d + 1] = send_off[d] + M[rank * row + d];
+        if (have_batch) KG_CUDA(c, cudaStreamWaitEvent(c->s_comm, c->ev_scatter, 0));
+        for (u64 sr = 0; sr < S; sr++) {
+            const int rb = (int)(c->subround & 1);
+            KG_CUDA(c, cudaStreamWaitEvent(c->s_comm, c->ev_recv_free[rb], 0));
+            u64 recv_pos = 0;
+            KG_NCCL(c, kg_nccl().GroupStart());
+            for (u32 peer = 0; peer < world; peer++) {
+                const u64 ns = M[rank * row + peer], lo = ns * sr / S, hi = ns * (sr + 1) / S;       // my slice for peer
+                const u64 nr = M[peer * row + rank], rlo = nr * sr / S, rhi = nr * (sr + 1) / S;    // peer's slice for me
+                const u64* src = c->d_send[sb] + (send_off[peer] + lo) * c->W;
+                u64* dst = c->d_recv[rb] + recv_pos * c->W;
+                if (peer == rank) {
+                    if (hi > lo) KG_CUDA(c, cudaMemcpyAsync(dst, src, (hi - lo) * c->W * sizeof(u64), cudaMemcpyDeviceToDevice, c->s_comm));
+                } else {
+                    if (hi > lo) KG_NCCL(c, kg_nccl().Send(src, (hi - lo) * c->W, ncclUint64, (int)peer, c->comm, c->s_comm));
+                    if (rhi > rlo) KG_NCCL(c, kg_nccl().Recv(dst, (rhi - rlo) * c->W, ncclUint64, (int)peer, c->comm, c->s_comm));
+                }
+                recv_pos += rhi - rlo;
+            }
+            KG_NCCL(c, kg_nccl().GroupEnd());
+            KG_CUDA(c, cudaEventRecord(c->ev_recv_full[rb], c->s_comm));
+            KG_CUDA(c, cudaStreamWaitEvent(c->s_insert, c->ev_recv_full[rb], 0));
+            if (recv_pos) insert_keys(c, c->s_insert, c->d_recv[rb], recv_pos, nullptr);
+            KG_CUDA(c, cudaEventRecord(c->ev_recv_free[rb], c->s_insert));
+            c->subround++;
+        }
+    }
+    KG_CUDA(c, cudaEventRecord(c->ev_send_free[sb], c->s_comm));
+    c->round++;
+    return KG_OK;
+}
+
+// bucket the k-mers of the batch that was just packed (hist -> scan -> scatter), then hand them on
+static int bucket_batch(kg_ctx* c, u32 nthreads) {
+    const u32 grid = (nthreads + 255) / 256;
+    const int sb = c->cfg.world > 1 ? (int)(c->round & 1) : 0;
+    KgBucketArgs a;
+    a.words = c->d_words; a.brk = c->d_brk; a.st = c->d_stream;
+    a.blk_hist = c->d_blk_hist; a.blk_base = c->d_blk_base; a.out_keys = c->d_send[sb];
+    a.stats = c->d_stats; a.k = c->cfg.k; a.nb = c->nb; a.world = (u32)c->cfg.world;
+    bucket_kernel(c, a, grid, false);
+    kg_bucket_scan<<<1, 1024, 0, c->s_compute>>>(c->d_blk_hist, c->d_blk_base, grid, c->nb, c->d_bucket_counts, c->d_bucket_offs);
+    c->launches++;
+    if (c->cfg.world > 1) {
+        KG_CUDA(c, cudaMemsetAsync(c->d_bucket_counts + c->nb, 0, sizeof(u32), c->s_compute));   // not done
+        KG_CUDA(c, cudaEventRecord(c->ev_counts, c->s_compute));
+        KG_CUDA(c, cudaStreamWaitEvent(c->s_compute, c->ev_send_free[sb], 0));   // round-2 sends have left this buffer
+        bucket_kernel(c, a, grid, true);
+        KG_CUDA(c, cudaEventRecord(c->ev_scatter, c->s_compute));
+        bool all_done;
+        return exchange_round(c, true, &all_done);
+    }
+    // single GPU, partitioned: the send buffer is partition-major; one insert launch walks it in order, so the
+    // blocks in flight at any moment hit one or two table regions (L2-resident)
+    bucket_kernel(c, a, grid, true);
+    insert_keys(c, c->s_compute, c->d_send[0], (u64)nthreads * 32u, c->d_bucket_offs + c->nb);
+    return KG_OK;
+}
+
 // parse + count one device-resident batch (n <= batch_bytes, 16-byte aligned) on the compute stream
 static int process_batch(kg_ctx* c, const uint8_t* d_in, size_t n, uint32_t flags) {
     if (n == 0) return KG_OK;
@@ -385,22 +654,26 @@ static int process_batch(kg_ctx* c, const uint8_t* d_in, size_t n, uint32_t flag
     c->launches += 4;
     if (e1) cudaEventRecord(e1, s);
     if (!(flags & KG_FEED_CONTEXT)) {
-        KgCountArgs a;
-        a.words = c->d_words; a.brk = c->d_brk; a.st = c->d_stream;
-        a.table = c->table; a.bloom = c->bloom;
-        memset(&a.buckets, 0, sizeof(a.buckets));
-        a.stats = c->d_stats; a.k = c->cfg.k; a.rank = (u32)c->cfg.rank; a.world = (u32)c->cfg.world;
-        int sink = c->pass == KG_PASS_BLOOM ? KG_SINK_BLOOM1 : (c->cfg.use_bloom ? KG_SINK_BLOOM2 : KG_SINK_TABLE);
         const u32 nthreads = (u32)(n / 32 + c->carry_max_words + 2);   // upper bound on packed words
-        switch (c->W) {
-            case 1: launch_count<1>(c, a, nthreads, sink); break;
-            case 2: launch_count<2>(c, a, nthreads, sink); break;
-            case 3: launch_count<3>(c, a, nthreads, sink); break;
-            case 4: launch_count<4>(c, a, nthreads, sink); break;
-            case 5: launch_count<5>(c, a, nthreads, sink); break;
-            case 6: launch_count<6>(c, a, nthreads, sink); break;
-            case 7: launch_count<7>(c, a, nthreads, sink); break;
-            case 8: launch_count<8>(c, a, nthreads, sink); break;
+        if (c->bucketed) {
+            int rc = bucket_batch(c, nthreads);
+            if (rc) return rc;
+        } else {
+            KgCountArgs a;
+            a.words = c->d_words; a.brk = c->d_brk; a.st = c->d_stream;
+            a.table = c->table; a.bloom = c->bloom;
+            a.stats = c->d_stats; a.k = c->cfg.k; a.rank = (u32)c->cfg.rank; a.world = (u32)c->cfg.world;
+            const int sink = current_sink(c);
+            switch (c->W) {
+                case 1: launch_count<1>(c, a, nthreads, sink); break;
+                case 2: launch_count<2>(c, a, nthreads, sink); break;
+                case 3: launch_count<3>(c, a, nthreads, sink); break;
+                case 4: launch_count<4>(c, a, nthreads, sink); break;
+                case 5: launch_count<5>(c, a, nthreads, sink); break;
+                case 6: launch_count<6>(c, a, nthreads, sink); break;
+                case 7: launch_count<7>(c, a, nthreads, sink); break;
+                case 8: launch_count<8>(c, a, nthreads, sink); break;
+            }
         }
     }
     kg_carry_save<<<1, 32, 0, s>>>(c->d_words, c->d_brk, c->d_stream, c->d_carry_words, c->d_carry_brk, c->cfg.k, c->carry_max_words);
@@ -482,6 +755,18 @@ extern "C" int kg_feed(kg_ctx* c, const uint8_t* bytes, size_t n, uint32_t flags
 extern "C" int kg_pass_end(kg_ctx* c, kg_pass_stats* out) {
     if (!c || !c->pass) return KG_EBADARG;
     KG_CUDA(c, cudaSetDevice(c->cfg.device));
+    if (c->cfg.world > 1) {
+        // keep taking part in exchange rounds until every rank has fed its last batch
+        bool all_done = false;
+        while (!all_done) {
+            int rc = exchange_round(c, false, &all_done);
+            if (rc) return rc;
+        }
+        KG_CUDA(c, cudaEventRecord(c->ev_tail, c->s_insert));
+        KG_CUDA(c, cudaStreamWaitEvent(c->s_compute, c->ev_tail, 0));
+        KG_CUDA(c, cudaEventRecord(c->ev_tail, c->s_comm));
+        KG_CUDA(c, cudaStreamWaitEvent(c->s_compute, c->ev_tail, 0));
+    }
     KG_CUDA(c, cudaEventRecord(c->ev_pass_end, c->s_compute));
     KG_CUDA(c, cudaStreamSynchronize(c->s_compute));
     KgStats st;

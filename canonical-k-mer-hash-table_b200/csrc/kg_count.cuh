@@ -16,9 +16,7 @@
 enum KgSink : int {
     KG_SINK_TABLE = 0,   // insert into the local table
     KG_SINK_BLOOM1 = 1,  // Bloom pass 1: test-and-set F1/F2
-    KG_SINK_BLOOM2 = 2,  // Bloom pass 2: insert only if F2 admits
-    KG_SINK_BUCKET = 3,  // multi-GPU: append (key) to the owner's send bucket
-    KG_SINK_BUCKET_BLOOM = 4
+    KG_SINK_BLOOM2 = 2   // Bloom pass 2: insert only if F2 admits
 };
 
 // blocked double Bloom filter: block = 64 B = [F1: 256 bits][F2: 256 bits]; all nh bits of a k-mer fall in
@@ -28,14 +26,6 @@ struct KgBloom {
     u32* bits;     // nblocks * 16 words
     u64 nblocks;
     u32 nh;        // ceil(h) (main.cpp:417)
-};
-
-struct KgBuckets {
-    u64* keys;        // world * capacity * W words
-    u32* fill;        // world counters
-    u32 capacity;     // keys per destination
-    u32 world;
-    u32 overflow;     // unused (kernel reports through KgStats.table_full)
 };
 
 // the nh bit positions of a k-mer inside its 256-bit block, as 8 x 32-bit masks
@@ -82,20 +72,28 @@ __device__ __forceinline__ void kg_bloom_insert(const KgBloom& bf, u64 h, u32& n
     }
     bool to_second = in1;
     if (!in1) {
-        // set F1; "mine" = I flipped every bit that was missing when I looked
-        bool mine = true;
+        // set F1; "all_mine" = I flipped every bit that was missing when I looked
+        bool all_mine = true, any_mine = false;
 #pragma unroll
         for (int w = 0; w < 8; w++)
-            if (miss1[w]) { u32 old = atomicOr(blk + w, miss1[w]); mine = mine && ((old & miss1[w]) == 0); }
-        if (mine) new1++;
-        else to_second = true;  // somebody raced me on a bit: the k-mer was seen twice concurrently (:401-411)
+            if (miss1[w]) {
+                u32 old = atomicOr(blk + w, miss1[w]);
+                all_mine = all_mine && ((old & miss1[w]) == 0);
+                any_mine = any_mine || ((old & miss1[w]) != miss1[w]);
+            }
+        if (any_mine) new1++;
+        if (!all_mine) to_second = true;  // somebody raced me on a bit: the k-mer was seen twice concurrently (:401-411)
     }
     if (to_second) {
-        bool mine = true;
+        // The reference counts a k-mer only when ONE thread flipped all of its missing bits (:353-368), which
+        // under-counts when occurrences race (it reports run-to-run variation itself).
+        // With ~300k threads in flight that would under-size the table (main.cpp:454), so count every thread
+        // that flipped at least one bit: exact without races, a slight over-count with them.
+        bool any_mine = false;
 #pragma unroll
         for (int w = 0; w < 8; w++)
-            if (miss2[w]) { u32 old = atomicOr(blk + 8 + w, miss2[w]); mine = mine && ((old & miss2[w]) == 0); }
-        if (mine) new2++;
+            if (miss2[w]) { u32 old = atomicOr(blk + 8 + w, miss2[w]); any_mine = any_mine || ((old & miss2[w]) != miss2[w]); }
+        if (any_mine) new2++;
     }
 }
 
@@ -119,153 +117,220 @@ struct KgCountArgs {
     const KgStream* st;
     KgTable table;
     KgBloom bloom;
-    KgBuckets buckets;
     KgStats* stats;
     u32 k;
     u32 rank, world;
 };
 
-template <int W>
-__device__ __forceinline__ void kg_bucket_append(const KgBuckets& b, u32 owner, const u64 (&key)[W], KgStats* stats) {
-    u32 pos = atomicAdd(b.fill + owner, 1u);
-    if (pos >= b.capacity) { stats->table_full = 2; return; }
-    u64* dst = b.keys + ((u64)owner * b.capacity + pos) * W;
+// Walk the k-mer windows that END inside packed word t: calls f(key, hash) once per complete window whose
+// end position is >= C (positions below C belong to the previous batch).  Returns the number of windows.
+template <int W, typename F>
+__device__ __forceinline__ u32 kg_for_each_window(const u64* __restrict__ words, const u32* __restrict__ brk,
+                                                  u32 T, u32 C, u32 k, u32 t, F&& f) {
+    if ((u64)t * 32u >= T) return 0;
+    const KgKGeom g = kg_geom(k);
+    const u64 myword = words[t];
+    const u32 mybrk = brk[t];
+    const u32 nvalid = min(32u, T - t * 32u);
+    // run length at the base just before this word: distance back to the most recent run start
+    u32 run = 0;
+    {
+        bool found = false;
+#pragma unroll 1
+        for (int i = 1; i <= W + 1 && !found; i++) {
+            if ((int)t - i < 0) break;                          // position 0 always carries a break bit
+            u32 b = brk[t - i];
+            if (b) { run += __ffs(b); found = true; }           // lowest set bit = most recent base of that word
+            else run += 32;
+        }
+    }
+    KgKmerWindow<W> w;
+    // forward window = the k-1 bases before this word, right-aligned
 #pragma unroll
-    for (int i = 0; i < W; i++) dst[i] = key[i];
+    for (int i = 0; i < W; i++) {
+        int src = (int)t - 1 - i;
+        w.f[W - 1 - i] = src >= 0 ? words[src] : 0ULL;
+    }
+    {
+        const u32 keep = 2 * (k - 1);                                             // bits of the k-1 prefix
+        const u32 topkeep = keep > 64u * (W - 1) ? keep - 64u * (W - 1) : 0u;     // of which in word 0
+        w.f[0] = topkeep == 0 ? 0ULL : (topkeep >= 64 ? w.f[0] : (w.f[0] & ((1ULL << topkeep) - 1)));
+    }
+    kg_revcomp<W>(w.f, w.r, g);
+    const u32 base_pos = t * 32u;
+    u32 n_windows = 0;
+#pragma unroll 1
+    for (u32 j = 0; j < nvalid; j++) {
+        const u32 c = (u32)(myword >> (62 - 2 * j)) & 3u;
+        kg_push<W>(w, g, c);
+        run = ((mybrk >> (31 - j)) & 1u) ? 1u : run + 1u;
+        if (run >= k && base_pos + j >= C) {
+            n_windows++;
+            u64 key[W];
+            const bool fwd = kg_forward_is_canonical<W>(w);
+#pragma unroll
+            for (int i = 0; i < W; i++) key[i] = fwd ? w.f[i] : w.r[i];
+            f(key, kg_hash_key<W>(key));
+        }
+    }
+    return n_windows;
 }
+
+#define KG_WARP_ADD(stats, var, field)                                            \
+    {                                                                             \
+        u32 v_ = var;                                                             \
+        for (int d = 16; d; d >>= 1) v_ += __shfl_xor_sync(0xffffffffu, v_, d);   \
+        if ((threadIdx.x & 31u) == 0 && v_) atomicAdd(&(stats)->field, (u64)v_);  \
+    }
+
+// what to do with one canonical k-mer on the shard that owns it
+template <int W, int SINK>
+struct KgConsume {
+    KgTable table;
+    KgBloom bloom;
+    u32 n_new = 0, n_ins = 0, n_b1 = 0, n_b2 = 0, n_rej = 0;
+    bool full = false;
+    __device__ __forceinline__ void operator()(const u64 (&key)[W], u64 h) {
+        if (SINK == KG_SINK_BLOOM1) {
+            kg_bloom_insert(bloom, h, n_b1, n_b2);
+            return;
+        }
+        if (SINK == KG_SINK_BLOOM2 && !kg_bloom_admits(bloom, h)) { n_rej++; return; }
+        bool is_new;
+        u64 slot = kg_table_add<W>(table, key, h, is_new);
+        if (slot == ~0ULL) full = true;
+        else { n_ins++; n_new += is_new ? 1u : 0u; }
+    }
+    __device__ __forceinline__ void flush(KgStats* stats) {
+        if (SINK == KG_SINK_TABLE || SINK == KG_SINK_BLOOM2) {
+            KG_WARP_ADD(stats, n_ins, inserted)
+            KG_WARP_ADD(stats, n_new, distinct)
+        }
+        if (SINK == KG_SINK_BLOOM1) {
+            KG_WARP_ADD(stats, n_b1, new_in_first)
+            KG_WARP_ADD(stats, n_b2, new_in_second)
+        }
+        if (SINK == KG_SINK_BLOOM2) { KG_WARP_ADD(stats, n_rej, bloom_rejected) }
+        if (full) stats->table_full = 1;
+    }
+};
 
 template <int W, int SINK>
 __global__ void __launch_bounds__(256) kg_count_kernel(KgCountArgs a) {
     const u32 T = a.st->total_bases;
     const u32 C = a.st->carry_bases;
     const u32 t = blockIdx.x * blockDim.x + threadIdx.x;
-    u32 n_windows = 0, n_new = 0, n_ins = 0, n_b1 = 0, n_b2 = 0, n_rej = 0;
-    bool full = false;
-    if ((u64)t * 32u < T) {
-        const KgKGeom g = kg_geom(a.k);
-        const u32 k = a.k;
-        const u64 myword = a.words[t];
-        const u32 mybrk = a.brk[t];
-        const u32 nvalid = min(32u, T - t * 32u);
-        // Quick reject: can any window end inside this word?  Needs run >= k at some position.
-        // run before this word
-        u32 run = 0;
-        {
-            bool found = false;
-#pragma unroll 1
-            for (int i = 1; i <= W + 1 && !found; i++) {
-                if ((int)t - i < 0) { found = true; break; }   // position 0 carries a break bit, handled below
-                u32 b = a.brk[t - i];
-                if (b) { run += __ffs(b) - 1 + 1; found = true; }   // lowest set bit = most recent base
-                else run += 32;
-            }
-            // when the scan ran off the start of the stream, `run` already equals 32*t (position 0 has its bit)
-        }
-        KgKmerWindow<W> w;
-        // forward window = the k-1 bases before this word, right-aligned
-#pragma unroll
-        for (int i = 0; i < W; i++) {
-            int src = (int)t - 1 - i;
-            w.f[W - 1 - i] = src >= 0 ? a.words[src] : 0ULL;
-        }
-        {
-            // keep only 2(k-1) bits
-            const u32 keep = 2 * (k - 1);             // bits
-            const u32 topkeep = keep > 64u * (W - 1) ? keep - 64u * (W - 1) : 0u;   // bits kept in word 0
-            w.f[0] = topkeep == 0 ? 0ULL : (topkeep >= 64 ? w.f[0] : (w.f[0] & ((1ULL << topkeep) - 1)));
-        }
-        kg_revcomp<W>(w.f, w.r, g);
-        const u32 base_pos = t * 32u;
-#pragma unroll 1
-        for (u32 j = 0; j < nvalid; j++) {
-            const u32 c = (u32)(myword >> (62 - 2 * j)) & 3u;
-            kg_push<W>(w, g, c);
-            run = ((mybrk >> (31 - j)) & 1u) ? 1u : run + 1u;
-            if (run >= k && base_pos + j >= C) {
-                n_windows++;
-                u64 key[W];
-                const bool fwd = kg_forward_is_canonical<W>(w);
-#pragma unroll
-                for (int i = 0; i < W; i++) key[i] = fwd ? w.f[i] : w.r[i];
-                const u64 h = kg_hash_key<W>(key);
-                if (SINK == KG_SINK_BLOOM1) {
-                    if (a.world > 1) {
-                        // (multi-GPU Bloom pass goes through buckets; not this sink)
-                    }
-                    kg_bloom_insert(a.bloom, h, n_b1, n_b2);
-                } else if (SINK == KG_SINK_BUCKET) {
-                    kg_bucket_append<W>(a.buckets, kg_owner(h, a.world), key, a.stats);
-                } else {
-                    if (SINK == KG_SINK_BLOOM2) {
-                        if (!kg_bloom_admits(a.bloom, h)) { n_rej++; continue; }
-                    }
-                    bool is_new;
-                    u64 slot = kg_table_add<W>(a.table, key, h, is_new);
-                    if (slot == ~0ULL) full = true;
-                    else { n_ins++; n_new += is_new ? 1u : 0u; }
-                }
-            }
-        }
-    }
-    // statistics: warp-reduce, one atomic per warp and counter
-    const u32 lane = threadIdx.x & 31u;
-#define KG_WARP_ADD(var, field)                                                   \
-    {                                                                             \
-        u32 v_ = var;                                                             \
-        for (int d = 16; d; d >>= 1) v_ += __shfl_xor_sync(0xffffffffu, v_, d);   \
-        if (lane == 0 && v_) atomicAdd(&a.stats->field, (u64)v_);                 \
-    }
-    KG_WARP_ADD(n_windows, input_kmers)
-    if (SINK == KG_SINK_TABLE || SINK == KG_SINK_BLOOM2) {
-        KG_WARP_ADD(n_ins, inserted)
-        KG_WARP_ADD(n_new, distinct)
-    }
-    if (SINK == KG_SINK_BLOOM1) {
-        KG_WARP_ADD(n_b1, new_in_first)
-        KG_WARP_ADD(n_b2, new_in_second)
-    }
-    if (SINK == KG_SINK_BLOOM2) { KG_WARP_ADD(n_rej, bloom_rejected) }
-    if (full) a.stats->table_full = 1;
+    KgConsume<W, SINK> sink;
+    sink.table = a.table;
+    sink.bloom = a.bloom;
+    u32 n_windows = kg_for_each_window<W>(a.words, a.brk, T, C, a.k, t, sink);
+    KG_WARP_ADD(a.stats, n_windows, input_kmers)
+    sink.flush(a.stats);
 }
 
 // insert keys that arrived from other shards (multi-GPU), one thread per key
 template <int W, int SINK>
-__global__ void __launch_bounds__(256) kg_insert_keys_kernel(const u64* __restrict__ keys, u64 n, KgTable table,
-                                                             KgBloom bloom, KgStats* stats) {
+__global__ void __launch_bounds__(256) kg_insert_keys_kernel(const u64* __restrict__ keys, u64 n, const u32* n_dev,
+                                                             KgTable table, KgBloom bloom, KgStats* stats) {
     const u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
-    u32 n_new = 0, n_ins = 0, n_b1 = 0, n_b2 = 0, n_rej = 0;
-    bool full = false;
+    if (n_dev) n = *n_dev;
+    KgConsume<W, SINK> sink;
+    sink.table = table;
+    sink.bloom = bloom;
     if (i < n) {
         u64 key[W];
 #pragma unroll
         for (int j = 0; j < W; j++) key[j] = keys[i * W + j];
-        const u64 h = kg_hash_key<W>(key);
-        if (SINK == KG_SINK_BLOOM1) {
-            kg_bloom_insert(bloom, h, n_b1, n_b2);
-        } else {
-            bool admit = true;
-            if (SINK == KG_SINK_BLOOM2) admit = kg_bloom_admits(bloom, h);
-            if (admit) {
-                bool is_new;
-                u64 slot = kg_table_add<W>(table, key, h, is_new);
-                if (slot == ~0ULL) full = true;
-                else { n_ins++; n_new += is_new ? 1u : 0u; }
-            } else n_rej++;
+        sink(key, kg_hash_key<W>(key));
+    }
+    sink.flush(stats);
+}
+
+// ---- multi-GPU bucketing: exact, deterministic layout without global atomics --------------------------------
+//   kg_owner_hist    per block: how many of its k-mers go to each owner shard      -> blk_hist[block][owner]
+//   kg_bucket_scan   one block: bucket totals, bucket offsets, per-block bases     -> blk_base[block][owner]
+//   kg_owner_scatter per block: write each key at blk_base[owner] + (shared cursor)++   -> send buffer
+// hist and scatter MUST be launched with the same grid (a block sees the same k-mers in both).
+#define KG_MAX_BUCKETS 32
+
+struct KgBucketArgs {
+    const u64* words;
+    const u32* brk;
+    const KgStream* st;
+    u32* blk_hist;      // [nblocks][nb]
+    u32* blk_base;      // [nblocks][nb]
+    u64* out_keys;      // send buffer, W words per key
+    KgStats* stats;
+    u32 k;
+    u32 nb;             // number of buckets: world (multi-GPU) or partitions (single GPU)
+    u32 world;          // > 1: bucket = owner shard; 1: bucket = partition of the local hash
+};
+
+__device__ __forceinline__ u32 kg_bucket_of(u64 h, u32 world, u32 nb) {
+    return world > 1 ? kg_owner(h, world) : (u32)__umul64hi(h, (u64)nb);
+}
+
+template <int W>
+__global__ void __launch_bounds__(256) kg_owner_hist(KgBucketArgs a) {
+    __shared__ u32 s_hist[KG_MAX_BUCKETS];
+    if (threadIdx.x < KG_MAX_BUCKETS) s_hist[threadIdx.x] = 0;
+    __syncthreads();
+    const u32 T = a.st->total_bases, C = a.st->carry_bases;
+    const u32 t = blockIdx.x * blockDim.x + threadIdx.x;
+    const u32 nb = a.nb;
+    u32 n_windows = kg_for_each_window<W>(a.words, a.brk, T, C, a.k, t,
+                                          [&](const u64 (&key)[W], u64 h) { (void)key; atomicAdd(&s_hist[kg_bucket_of(h, a.world, nb)], 1u); });
+    KG_WARP_ADD(a.stats, n_windows, input_kmers)
+    __syncthreads();
+    if (threadIdx.x < nb) a.blk_hist[(u64)blockIdx.x * nb + threadIdx.x] = s_hist[threadIdx.x];
+}
+
+// counts_out[b] = keys for bucket b; offs_out[b] = first key index of bucket b in the send buffer
+__global__ void __launch_bounds__(1024) kg_bucket_scan(const u32* __restrict__ blk_hist, u32* __restrict__ blk_base,
+                                                       u32 nblocks, u32 nb, u32* counts_out, u32* offs_out) {
+    __shared__ u32 sm[1024];
+    __shared__ u32 s_running;
+    if (threadIdx.x == 0) s_running = 0;
+    const u32 per = (nblocks + 1023) / 1024;
+    const u32 b0 = threadIdx.x * per, b1 = min(b0 + per, nblocks);
+    for (u32 b = 0; b < nb; b++) {
+        u32 mine = 0;
+        for (u32 i = b0; i < b1; i++) mine += blk_hist[(u64)i * nb + b];
+        sm[threadIdx.x] = mine;
+        __syncthreads();
+        // inclusive scan over 1024 partial sums (Hillis-Steele in shared memory)
+        for (u32 d = 1; d < 1024; d <<= 1) {
+            u32 v = threadIdx.x >= d ? sm[threadIdx.x - d] : 0;
+            __syncthreads();
+            sm[threadIdx.x] += v;
+            __syncthreads();
         }
+        const u32 bucket_off = s_running;
+        u32 cur = bucket_off + sm[threadIdx.x] - mine;
+        for (u32 i = b0; i < b1; i++) { blk_base[(u64)i * nb + b] = cur; cur += blk_hist[(u64)i * nb + b]; }
+        const u32 total = sm[1023];
+        __syncthreads();
+        if (threadIdx.x == 0) { counts_out[b] = total; offs_out[b] = bucket_off; s_running = bucket_off + total; }
+        __syncthreads();
     }
-    const u32 lane = threadIdx.x & 31u;
-#define KG_WARP_ADD2(var, field)                                                  \
-    {                                                                             \
-        u32 v_ = var;                                                             \
-        for (int d = 16; d; d >>= 1) v_ += __shfl_xor_sync(0xffffffffu, v_, d);   \
-        if (lane == 0 && v_) atomicAdd(&stats->field, (u64)v_);                   \
-    }
-    KG_WARP_ADD2(n_ins, inserted)
-    KG_WARP_ADD2(n_new, distinct)
-    KG_WARP_ADD2(n_b1, new_in_first)
-    KG_WARP_ADD2(n_b2, new_in_second)
-    KG_WARP_ADD2(n_rej, bloom_rejected)
-    if (full) stats->table_full = 1;
+    if (threadIdx.x == 0) offs_out[nb] = s_running;   // total keys in the send buffer
+}
+
+template <int W>
+__global__ void __launch_bounds__(256) kg_owner_scatter(KgBucketArgs a) {
+    __shared__ u32 s_cur[KG_MAX_BUCKETS];
+    const u32 nb = a.nb;
+    if (threadIdx.x < nb) s_cur[threadIdx.x] = a.blk_base[(u64)blockIdx.x * nb + threadIdx.x];
+    __syncthreads();
+    const u32 T = a.st->total_bases, C = a.st->carry_bases;
+    const u32 t = blockIdx.x * blockDim.x + threadIdx.x;
+    u64* out = a.out_keys;
+    kg_for_each_window<W>(a.words, a.brk, T, C, a.k, t, [&](const u64 (&key)[W], u64 h) {
+        const u32 pos = atomicAdd(&s_cur[kg_bucket_of(h, a.world, nb)], 1u);
+        u64* dst = out + (u64)pos * W;
+#pragma unroll
+        for (int i = 0; i < W; i++) dst[i] = key[i];
+    });
 }
 
 // ---- K5 export: stream-compact slots whose reported count >= min_abundance -------------------------------

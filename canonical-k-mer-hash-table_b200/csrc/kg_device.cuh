@@ -56,11 +56,13 @@ __device__ __forceinline__ u64 kg_hash_key(const u64 (&key)[W]) {
     return h;
 }
 
-// owner shard of a hash (multi-GPU) and slot within the shard use decorrelated bits
+// Range partitioning of the 64-bit hash: owner shard = floor(h * world / 2^64); inside the shard the
+// fractional part (low 64 bits of h * world) is uniform again, and slot = floor(frac * nslots / 2^64).
+// A partition p of `nb` (single GPU) is floor(frac * nb / 2^64), so partition p maps to the CONTIGUOUS slot
+// range [p*nslots/nb, (p+1)*nslots/nb): inserting one partition at a time keeps the live table region in L2.
 __device__ __forceinline__ u32 kg_owner(u64 h, u32 world) { return (u32)__umul64hi(h, (u64)world); }
-__device__ __forceinline__ u64 kg_slot(u64 h, u64 nslots) {
-    return __umul64hi(h * 0xD6E8FEB86659FD93ULL + 0x2545F4914F6CDD1DULL, nslots);
-}
+__device__ __forceinline__ u64 kg_local_hash(u64 h, u32 world) { return h * (u64)world; }
+__device__ __forceinline__ u64 kg_slot(u64 h, u64 nslots, u32 world) { return __umul64hi(kg_local_hash(h, world), nslots); }
 
 // ---- strong (L2-coherent, L1-bypassing) accesses used on the table -----------------------------------
 __device__ __forceinline__ u32 kg_ld_u32(const void* p) {
@@ -89,6 +91,8 @@ struct KgTable {
     u64 nslots;      // next_prime3mod4(...)
     u32 stride;      // u64 words per slot
     u32 kaarme;      // slot carries a first-occurrence word at [1+W]
+    u32 world;       // shards the hash space is split into (slot uses the in-shard fraction of the hash)
+    u32 pad;
 };
 
 __host__ __device__ inline u32 kg_slot_stride_words(u32 W, bool kaarme) {
@@ -103,7 +107,7 @@ __host__ __device__ inline u32 kg_slot_stride_words(u32 W, bool kaarme) {
 //   data-dependent) the key words, all as L2-coherent accesses; key words never change once published.
 template <int W>
 __device__ __forceinline__ u64 kg_table_add(const KgTable& t, const u64 (&key)[W], u64 h, bool& is_new) {
-    u64 slot = kg_slot(h, t.nslots);
+    u64 slot = kg_slot(h, t.nslots, t.world);
     is_new = false;
     const u64 max_probe = t.nslots < 4096 ? t.nslots : 4096;
     for (u64 probe = 0; probe < max_probe; probe++) {
@@ -147,7 +151,7 @@ __device__ __forceinline__ u64 kg_table_add(const KgTable& t, const u64 (&key)[W
 // read-only lookup (compaction / decode); returns slot or ~0
 template <int W>
 __device__ __forceinline__ u64 kg_table_find(const KgTable& t, const u64 (&key)[W], u64 h) {
-    u64 slot = kg_slot(h, t.nslots);
+    u64 slot = kg_slot(h, t.nslots, t.world);
     const u64 max_probe = t.nslots < 4096 ? t.nslots : 4096;
     for (u64 probe = 0; probe < max_probe; probe++) {
         const u64* p = t.slots + slot * t.stride;

@@ -37,7 +37,8 @@ class Config(C.Structure):
     _fields_ = [("abi_version", C.c_uint32), ("k", C.c_uint32), ("table_mode", C.c_int32),
                 ("input_mode", C.c_int32), ("min_slots", C.c_uint64), ("use_bloom", C.c_int32),
                 ("device", C.c_int32), ("fpr", C.c_double), ("expected_unique", C.c_uint64),
-                ("batch_bytes", C.c_uint64), ("rank", C.c_int32), ("world", C.c_int32)]
+                ("batch_bytes", C.c_uint64), ("rank", C.c_int32), ("world", C.c_int32),
+                ("partitions", C.c_uint32), ("reserved", C.c_uint32)]
 
 
 class PassStats(C.Structure):
@@ -101,6 +102,15 @@ def lib():
     return _lib
 
 
+def comm_unique_id() -> bytes:
+    """rank 0 calls this and broadcasts the 128 bytes (e.g. torch.distributed.broadcast_object_list)."""
+    buf = C.create_string_buffer(128)
+    rc = lib().kg_comm_unique_id(buf)
+    if rc:
+        raise KaarmeError(rc, "kg_comm_unique_id", lib().kg_last_error(None).decode())
+    return buf.raw
+
+
 def device_count() -> int:
     n = C.c_int(0)
     lib().kg_device_count(C.byref(n))
@@ -133,9 +143,9 @@ class Counter:
     """One kg_ctx (one GPU / one hash shard)."""
 
     def __init__(self, k, table_mode=TABLE_PLAIN, input_mode=INPUT_FASTA, min_slots=0, use_bloom=False,
-                 fpr=0.01, expected_unique=0, device=0, batch_bytes=0, rank=0, world=1):
+                 fpr=0.01, expected_unique=0, device=0, batch_bytes=0, rank=0, world=1, partitions=0):
         self.cfg = Config(ABI_VERSION, k, table_mode, input_mode, min_slots, int(bool(use_bloom)), device,
-                          fpr, expected_unique, batch_bytes, rank, world)
+                          fpr, expected_unique, batch_bytes, rank, world, partitions, 0)
         self.k, self.W = k, (k + 31) // 32
         self._h = C.c_void_p()
         rc = lib().kg_create(C.byref(self.cfg), C.byref(self._h))
@@ -235,6 +245,40 @@ class Counter:
         self.stream_begin(starts_in_header)
         self.feed(data)
         return self.pass_end()
+
+
+def slice_context(data, lo, k, input_mode=INPUT_FASTA):
+    """Host-side sharding of one input across ranks (the role of text_reader.h:141-184 in the reference).
+
+    A rank that owns bytes [lo, hi) of the file must also see the k-1 bases before `lo` (fed with
+    FEED_CONTEXT so they are not counted twice) and must know whether its first byte lies inside a FASTA
+    header.  Returns (ctx_lo, starts_in_header): feed data[ctx_lo:lo] as context after
+    stream_begin(starts_in_header), then data[lo:hi].
+    """
+    buf = memoryview(data) if not isinstance(data, memoryview) else data
+    need = k - 1
+    i = lo
+    while i > 0 and need > 0:       # walk back over k-1 non-newline bytes (newlines inside records are skipped)
+        i -= 1
+        if buf[i] != 10:
+            need -= 1
+    ctx_lo = i
+    in_header = False
+    if input_mode == INPUT_FASTA:   # header state at ctx_lo: a '>' since the last newline (parallel_parser.hpp:602-620)
+        j = ctx_lo
+        while j > 0:
+            j -= 1
+            if buf[j] == 10:
+                break
+            if buf[j] == 62:
+                in_header = True
+                break
+    return ctx_lo, in_header
+
+
+def shard_ranges(nbytes, world):
+    """Even byte ranges [lo, hi) per rank; any cut is legal because slice_context repairs the boundary."""
+    return [(nbytes * r // world, nbytes * (r + 1) // world) for r in range(world)]
 
 
 def keys_to_text(keys, counts, k) -> bytes:

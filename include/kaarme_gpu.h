@@ -63,7 +63,7 @@ typedef enum kg_status {
 #define KG_COUNT_EXACT 0    /* 32-bit true multiplicity                                             */
 #define KG_COUNT_REFERENCE 1 /* -m 0: N mod 65536 (uint16 wrap); -m 2: min(N, 16383)                */
 
-#define KG_MAX_K 512 /* keys are ceil(k/32) 64-bit words, up to 16 */
+#define KG_MAX_K 256 /* keys are ceil(k/32) 64-bit words, up to 8 */
 
 typedef struct kg_ctx kg_ctx;
 
@@ -80,6 +80,9 @@ typedef struct kg_config {
     uint64_t batch_bytes;     /* raw bytes per device batch; 0 = default (128 MiB)                  */
     int32_t rank;             /* hash-sharded multi-GPU: this context's shard                       */
     int32_t world;            /* number of shards (1 = single GPU)                                  */
+    uint32_t partitions;      /* single GPU: > 1 buckets every batch by hash into this many table regions
+                                 before inserting (L2-blocked insert); 0/1 = insert directly              */
+    uint32_t reserved;
 } kg_config;
 
 typedef struct kg_pass_stats {

@@ -29,8 +29,9 @@ def _imode(name):
 
 
 def gpu_count(data, k, input_mode=K.INPUT_FASTA, table_mode=K.TABLE_PLAIN, slots=400000, a=1,
-              count_mode=K.COUNT_EXACT, batch_bytes=0, feeder=None, starts_in_header=False):
-    with kg.Counter(k=k, table_mode=table_mode, input_mode=input_mode, min_slots=slots, batch_bytes=batch_bytes) as c:
+              count_mode=K.COUNT_EXACT, batch_bytes=0, feeder=None, starts_in_header=False, partitions=0):
+    with kg.Counter(k=k, table_mode=table_mode, input_mode=input_mode, min_slots=slots, batch_bytes=batch_bytes,
+                    partitions=partitions) as c:
         c.pass_begin(K.PASS_COUNT)
         c.stream_begin(starts_in_header)
         if feeder:
@@ -228,3 +229,86 @@ def test_medium_config3_shape(oracle):
     assert st["input_kmers"] == want.total_windows
     assert int(counts.astype(np.uint64).sum()) == st["input_kmers"]
     assert_same(keys, counts, want)
+
+
+# ---- double Bloom filter (-b): the north-star rule ------------------------------------------------------------
+def gpu_bloom(data, k, unique, fpr, input_mode=K.INPUT_FASTA, table_mode=K.TABLE_PLAIN, a=1, batch_bytes=0):
+    with kg.Counter(k=k, table_mode=table_mode, input_mode=input_mode, use_bloom=True, expected_unique=unique,
+                    fpr=fpr, batch_bytes=batch_bytes) as c:
+        b = c.run_pass(K.PASS_BLOOM, data)
+        st = c.run_pass(K.PASS_COUNT, data)
+        keys, counts = c.export(a, K.COUNT_EXACT)
+    return keys, counts, b, st
+
+
+@pytest.mark.parametrize("case", [c for c in CASES if c["unique"] is not None and c["mode"] == 0 and c["a"] == 2],
+                         ids=lambda c: f"{c['input']}-k{c['k']}-u{c['unique']}-f{c['fpr']}")
+def test_bloom_golden(oracle, case):
+    """-m 0 -b: at -a >= 2 the output equals the reference's (== the no-Bloom ground truth): no false negatives.
+    False positives (singletons admitted) are reported, not hidden."""
+    data = _read(case["input"])
+    keys, counts, b, st = gpu_bloom(data, case["k"], case["unique"], case["fpr"], _imode(case["input"]), a=2)
+    txt = kg.keys_to_text(keys, counts, case["k"])
+    assert txt.count(b"\n") == case["n_lines"]
+    assert hashlib.sha256(txt).hexdigest() == case["sha256"]
+    m, nh, _ = oracle.bloom_params(case["unique"], case["fpr"])
+    assert (b["bloom_bits"], b["bloom_hashes"]) == (m, nh)
+    assert st["table_slots"] == oracle.lib().ko_next_prime3mod4(2 * b["new_in_second"])   # main.cpp:454
+    # the counters track the reference's (different hash functions => not identical)
+    # (racing occurrences are counted once per racer: a small over-count, never the reference's under-count)
+    assert -0.01 * case["new_in_second"] - 5 <= b["new_in_second"] - case["new_in_second"] <= 0.06 * case["new_in_second"] + 5
+    assert abs(b["new_in_first"] - case["new_in_first"]) <= 0.06 * case["new_in_first"] + 5
+
+
+@pytest.mark.parametrize("k,fpr", [(21, 0.01), (51, 0.01), (31, 0.2), (127, 0.05)])
+def test_bloom_fp_fn_vs_truth(oracle, k, fpr):
+    rng = np.random.default_rng(k)
+    data = make_fasta(rng, 60000, 400, 600, wrap=70, err=0.02)
+    truth = oracle.count(data, k)
+    n_single = int((truth.counts == 1).sum())
+    keys, counts, b, st = gpu_bloom(data, k, unique=truth.n, fpr=fpr, a=1, batch_bytes=65536)
+    got = dict(zip(map(bytes, keys.view(np.uint8).reshape(len(counts), -1)), counts.astype(np.uint64)))
+    want = dict(zip(map(bytes, truth.keys.view(np.uint8).reshape(truth.n, -1)), truth.counts))
+    fn = [kk for kk, cc in want.items() if cc >= 2 and kk not in got]
+    assert not fn, f"{len(fn)} false negatives"
+    for kk, cc in got.items():
+        assert want[kk] == cc                      # admitted k-mers carry their exact count
+    fp = sum(1 for kk, cc in got.items() if cc == 1)
+    assert fp <= max(10, 3.0 * fpr * n_single), (fp, n_single)   # blocked filter: allow 3x the nominal rate
+    assert st["input_kmers"] == truth.total_windows
+    print(f"k={k} fpr={fpr}: singletons={n_single} false_positives={fp} ({fp / max(1, n_single):.4f}) false_negatives=0")
+
+
+def test_bloom_kmer_repeated_only_inside_one_warp(oracle):
+    """two occurrences processed concurrently by neighbouring threads must still reach filter 2 (race branch,
+    double_bloomfilter.hpp:401-411)"""
+    rng = np.random.default_rng(2)
+    unit = "".join("ACGT"[x] for x in rng.integers(0, 4, 64))
+    data = (">r\n" + unit * 2 + "\n").encode()      # every 31-mer of the unit occurs exactly twice, 64 bases apart
+    truth = oracle.count(data, 31).filtered(2)
+    keys, counts, b, st = gpu_bloom(data, 31, unique=1000, fpr=0.01, a=2)
+    assert_same(keys, counts, truth)
+
+
+# ---- bucketed path on one GPU (hist -> scan -> scatter -> insert), the same kernels the multi-GPU exchange uses --
+@pytest.mark.parametrize("partitions", [2, 8, 32])
+@pytest.mark.parametrize("k", [31, 51, 255])
+def test_partitioned_insert(oracle, k, partitions):
+    rng = np.random.default_rng(k * 100 + partitions)
+    data = make_fasta(rng, 40000, 150, 1200, wrap=80, err=0.01, n_rate=0.0005)
+    want = oracle.count(data, k)
+    keys, counts, st = gpu_count(data, k, batch_bytes=32768, partitions=partitions)
+    assert st["input_kmers"] == want.total_windows
+    assert st["inserted_kmers"] == want.total_windows
+    assert_same(keys, counts, want)
+
+
+def test_partitioned_bloom(oracle):
+    rng = np.random.default_rng(8)
+    data = make_fasta(rng, 60000, 400, 600, wrap=70, err=0.02)
+    truth = oracle.count(data, 51)
+    with kg.Counter(k=51, use_bloom=True, expected_unique=truth.n, fpr=0.01, partitions=16, batch_bytes=65536) as c:
+        c.run_pass(K.PASS_BLOOM, data)
+        c.run_pass(K.PASS_COUNT, data)
+        keys, counts = c.export(2, K.COUNT_EXACT)
+    assert_same(keys, counts, truth.filtered(2))
