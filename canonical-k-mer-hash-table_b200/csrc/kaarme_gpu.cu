@@ -253,7 +253,7 @@ extern "C" int kg_create(const kg_config* cfg, kg_ctx** out) {
         if (cfg->expected_unique == 0 || !(cfg->fpr > 0.0 && cfg->fpr < 1.0)) { g_err = "bloom needs expected_unique > 0 and 0 < fpr < 1"; return KG_EBADARG; }
     } else if (cfg->min_slots == 0) { g_err = "min_slots must be > 0"; return KG_EBADARG; }
     if (cfg->world < 1 || cfg->rank < 0 || cfg->rank >= cfg->world) { g_err = "bad rank/world"; return KG_EBADARG; }
-    if (cfg->world > KG_MAX_BUCKETS || cfg->partitions > KG_MAX_BUCKETS) { g_err = "world / partitions must be <= 32"; return KG_EBADARG; }
+    if (cfg->world > 64 || cfg->partitions > KG_MAX_BUCKETS) { g_err = "world must be <= 64 and partitions <= 1024"; return KG_EBADARG; }
     if (cfg->world > 1 && cfg->partitions > 1) { g_err = "partitions > 1 is a single-GPU option"; return KG_EBADARG; }
 
     int ndev = 0;
@@ -486,7 +486,7 @@ static int current_sink(const kg_ctx* c) {
 template <int W>
 static void launch_insert_keys(kg_ctx* c, cudaStream_t s, const u64* keys, u64 n_upper, const u32* n_dev, int sink) {
     const u32 block = 256;
-    const u64 grid = (n_upper + block - 1) / block;
+    const u64 grid = (n_upper + KG_KEYS_PER_BLOCK - 1) / KG_KEYS_PER_BLOCK;
     if (grid == 0) return;
     switch (sink) {
         case KG_SINK_TABLE: kg_insert_keys_kernel<W, KG_SINK_TABLE><<<(u32)grid, block, 0, s>>>(keys, n_upper, n_dev, c->table, c->bloom, c->d_stats); break;
@@ -513,7 +513,17 @@ static void insert_keys(kg_ctx* c, cudaStream_t s, const u64* keys, u64 n_upper,
 
 template <int W>
 static void launch_bucket(kg_ctx* c, const KgBucketArgs& a, u32 grid, bool scatter) {
-    if (scatter) kg_owner_scatter<W><<<grid, 256, 0, c->s_compute>>>(a);
+    if (scatter) {
+        // occupancy throttle: the scatter's in-flight partially written runs (blocks x 128 KB) must stay within
+        // L2, else sectors are evicted half-written; dynamic shared memory caps the resident blocks per SM
+        static int smem = -1;
+        if (smem < 0) {
+            const char* e = getenv("KG_SCATTER_SMEM");
+            smem = e ? atoi(e) : 0;
+            if (smem > 48 * 1024) cudaFuncSetAttribute(kg_owner_scatter<W>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        }
+        kg_owner_scatter<W><<<grid, 256, smem, c->s_compute>>>(a);
+    }
     else kg_owner_hist<W><<<grid, 256, 0, c->s_compute>>>(a);
     c->launches++;
 }
@@ -603,11 +613,12 @@ static int bucket_batch(kg_ctx* c, u32 nthreads) {
     const int sb = c->cfg.world > 1 ? (int)(c->round & 1) : 0;
     KgBucketArgs a;
     a.words = c->d_words; a.brk = c->d_brk; a.st = c->d_stream;
-    a.blk_hist = c->d_blk_hist; a.blk_base = c->d_blk_base; a.out_keys = c->d_send[sb];
+    a.blk_hist = c->d_blk_hist; a.blk_base = c->d_blk_base; a.bucket_offs = c->d_bucket_offs; a.out_keys = c->d_send[sb];
     a.stats = c->d_stats; a.k = c->cfg.k; a.nb = c->nb; a.world = (u32)c->cfg.world;
     bucket_kernel(c, a, grid, false);
-    kg_bucket_scan<<<1, 1024, 0, c->s_compute>>>(c->d_blk_hist, c->d_blk_base, grid, c->nb, c->d_bucket_counts, c->d_bucket_offs);
-    c->launches++;
+    kg_bucket_colscan<<<c->nb, 1024, 0, c->s_compute>>>(c->d_blk_hist, c->d_blk_base, grid, c->nb, c->d_bucket_counts);
+    kg_bucket_offsets<<<1, 1024, 0, c->s_compute>>>(c->d_bucket_counts, c->nb, c->d_bucket_offs);
+    c->launches += 2;
     if (c->cfg.world > 1) {
         KG_CUDA(c, cudaMemsetAsync(c->d_bucket_counts + c->nb, 0, sizeof(u32), c->s_compute));   // not done
         KG_CUDA(c, cudaEventRecord(c->ev_counts, c->s_compute));

@@ -228,22 +228,55 @@ __global__ void __launch_bounds__(256) kg_count_kernel(KgCountArgs a) {
     sink.flush(a.stats);
 }
 
-// insert keys that arrived from other shards (multi-GPU), one thread per key
+// insert keys from a key array (received from other shards, or this GPU's partition-major bucket buffer).
+// A block walks KG_KEYS_PER_BLOCK consecutive keys (coalesced); statistics leave the block as one atomic per
+// counter (one atomic per warp would put millions of RMWs on a single address).
+#define KG_KEYS_PER_THREAD 16
+#define KG_KEYS_PER_BLOCK (256 * KG_KEYS_PER_THREAD)
+
+__device__ __forceinline__ void kg_block_add(u32 v, u64* dst, u32* smem /*8 words*/) {
+    for (int d = 16; d; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
+    if ((threadIdx.x & 31u) == 0) smem[threadIdx.x >> 5] = v;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        u32 t = 0;
+        for (u32 w = 0; w < blockDim.x / 32; w++) t += smem[w];
+        if (t) atomicAdd(dst, (u64)t);
+    }
+    __syncthreads();
+}
+
 template <int W, int SINK>
 __global__ void __launch_bounds__(256) kg_insert_keys_kernel(const u64* __restrict__ keys, u64 n, const u32* n_dev,
                                                              KgTable table, KgBloom bloom, KgStats* stats) {
-    const u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    __shared__ u32 sm[8];
     if (n_dev) n = *n_dev;
+    const u64 base = (u64)blockIdx.x * KG_KEYS_PER_BLOCK;
     KgConsume<W, SINK> sink;
     sink.table = table;
     sink.bloom = bloom;
-    if (i < n) {
-        u64 key[W];
+    if (base < n) {
+#pragma unroll 1
+        for (int j = 0; j < KG_KEYS_PER_THREAD; j++) {
+            const u64 i = base + (u64)j * 256u + threadIdx.x;
+            if (i < n) {
+                u64 key[W];
 #pragma unroll
-        for (int j = 0; j < W; j++) key[j] = keys[i * W + j];
-        sink(key, kg_hash_key<W>(key));
+                for (int q = 0; q < W; q++) key[q] = __ldcs(keys + i * W + q);   // streamed once: evict-first
+                sink(key, kg_hash_key<W>(key));
+            }
+        }
     }
-    sink.flush(stats);
+    if (SINK == KG_SINK_TABLE || SINK == KG_SINK_BLOOM2) {
+        kg_block_add(sink.n_ins, &stats->inserted, sm);
+        kg_block_add(sink.n_new, &stats->distinct, sm);
+    }
+    if (SINK == KG_SINK_BLOOM1) {
+        kg_block_add(sink.n_b1, &stats->new_in_first, sm);
+        kg_block_add(sink.n_b2, &stats->new_in_second, sm);
+    }
+    if (SINK == KG_SINK_BLOOM2) kg_block_add(sink.n_rej, &stats->bloom_rejected, sm);
+    if (sink.full) stats->table_full = 1;
 }
 
 // ---- multi-GPU bucketing: exact, deterministic layout without global atomics --------------------------------
@@ -251,14 +284,15 @@ __global__ void __launch_bounds__(256) kg_insert_keys_kernel(const u64* __restri
 //   kg_bucket_scan   one block: bucket totals, bucket offsets, per-block bases     -> blk_base[block][owner]
 //   kg_owner_scatter per block: write each key at blk_base[owner] + (shared cursor)++   -> send buffer
 // hist and scatter MUST be launched with the same grid (a block sees the same k-mers in both).
-#define KG_MAX_BUCKETS 32
+#define KG_MAX_BUCKETS 1024
 
 struct KgBucketArgs {
     const u64* words;
     const u32* brk;
     const KgStream* st;
     u32* blk_hist;      // [nblocks][nb]
-    u32* blk_base;      // [nblocks][nb]
+    u32* blk_base;      // [nblocks][nb], relative to the bucket start
+    const u32* bucket_offs;  // [nb+1] bucket start in the send buffer
     u64* out_keys;      // send buffer, W words per key
     KgStats* stats;
     u32 k;
@@ -273,7 +307,7 @@ __device__ __forceinline__ u32 kg_bucket_of(u64 h, u32 world, u32 nb) {
 template <int W>
 __global__ void __launch_bounds__(256) kg_owner_hist(KgBucketArgs a) {
     __shared__ u32 s_hist[KG_MAX_BUCKETS];
-    if (threadIdx.x < KG_MAX_BUCKETS) s_hist[threadIdx.x] = 0;
+    for (u32 i = threadIdx.x; i < a.nb; i += blockDim.x) s_hist[i] = 0;
     __syncthreads();
     const u32 T = a.st->total_bases, C = a.st->carry_bases;
     const u32 t = blockIdx.x * blockDim.x + threadIdx.x;
@@ -282,45 +316,53 @@ __global__ void __launch_bounds__(256) kg_owner_hist(KgBucketArgs a) {
                                           [&](const u64 (&key)[W], u64 h) { (void)key; atomicAdd(&s_hist[kg_bucket_of(h, a.world, nb)], 1u); });
     KG_WARP_ADD(a.stats, n_windows, input_kmers)
     __syncthreads();
-    if (threadIdx.x < nb) a.blk_hist[(u64)blockIdx.x * nb + threadIdx.x] = s_hist[threadIdx.x];
+    for (u32 i = threadIdx.x; i < nb; i += blockDim.x) a.blk_hist[(u64)blockIdx.x * nb + i] = s_hist[i];
 }
 
-// counts_out[b] = keys for bucket b; offs_out[b] = first key index of bucket b in the send buffer
-__global__ void __launch_bounds__(1024) kg_bucket_scan(const u32* __restrict__ blk_hist, u32* __restrict__ blk_base,
-                                                       u32 nblocks, u32 nb, u32* counts_out, u32* offs_out) {
+// Column scan, one block per bucket b: blk_base[block][b] = keys of bucket b held by earlier blocks
+// (exclusive, RELATIVE to the bucket start); counts_out[b] = bucket total.
+__global__ void __launch_bounds__(1024) kg_bucket_colscan(const u32* __restrict__ blk_hist, u32* __restrict__ blk_base,
+                                                          u32 nblocks, u32 nb, u32* counts_out) {
     __shared__ u32 sm[1024];
-    __shared__ u32 s_running;
-    if (threadIdx.x == 0) s_running = 0;
+    const u32 b = blockIdx.x;
     const u32 per = (nblocks + 1023) / 1024;
     const u32 b0 = threadIdx.x * per, b1 = min(b0 + per, nblocks);
-    for (u32 b = 0; b < nb; b++) {
-        u32 mine = 0;
-        for (u32 i = b0; i < b1; i++) mine += blk_hist[(u64)i * nb + b];
-        sm[threadIdx.x] = mine;
+    u32 mine = 0;
+    for (u32 i = b0; i < b1; i++) mine += blk_hist[(u64)i * nb + b];
+    sm[threadIdx.x] = mine;
+    __syncthreads();
+    for (u32 d = 1; d < 1024; d <<= 1) {          // inclusive Hillis-Steele scan of the 1024 partial sums
+        u32 v = threadIdx.x >= d ? sm[threadIdx.x - d] : 0;
         __syncthreads();
-        // inclusive scan over 1024 partial sums (Hillis-Steele in shared memory)
-        for (u32 d = 1; d < 1024; d <<= 1) {
-            u32 v = threadIdx.x >= d ? sm[threadIdx.x - d] : 0;
-            __syncthreads();
-            sm[threadIdx.x] += v;
-            __syncthreads();
-        }
-        const u32 bucket_off = s_running;
-        u32 cur = bucket_off + sm[threadIdx.x] - mine;
-        for (u32 i = b0; i < b1; i++) { blk_base[(u64)i * nb + b] = cur; cur += blk_hist[(u64)i * nb + b]; }
-        const u32 total = sm[1023];
-        __syncthreads();
-        if (threadIdx.x == 0) { counts_out[b] = total; offs_out[b] = bucket_off; s_running = bucket_off + total; }
+        sm[threadIdx.x] += v;
         __syncthreads();
     }
-    if (threadIdx.x == 0) offs_out[nb] = s_running;   // total keys in the send buffer
+    u32 cur = sm[threadIdx.x] - mine;
+    for (u32 i = b0; i < b1; i++) { u32 h = blk_hist[(u64)i * nb + b]; blk_base[(u64)i * nb + b] = cur; cur += h; }
+    if (threadIdx.x == 1023) counts_out[b] = sm[1023];
+}
+
+// offs_out[b] = first key index of bucket b in the send buffer; offs_out[nb] = total keys
+__global__ void __launch_bounds__(1024) kg_bucket_offsets(const u32* __restrict__ counts, u32 nb, u32* offs_out) {
+    __shared__ u32 sm[1024];
+    const u32 v = threadIdx.x < nb ? counts[threadIdx.x] : 0;
+    sm[threadIdx.x] = v;
+    __syncthreads();
+    for (u32 d = 1; d < 1024; d <<= 1) {
+        u32 t = threadIdx.x >= d ? sm[threadIdx.x - d] : 0;
+        __syncthreads();
+        sm[threadIdx.x] += t;
+        __syncthreads();
+    }
+    if (threadIdx.x < nb) offs_out[threadIdx.x] = sm[threadIdx.x] - v;
+    if (threadIdx.x == 1023) offs_out[nb] = sm[1023];
 }
 
 template <int W>
 __global__ void __launch_bounds__(256) kg_owner_scatter(KgBucketArgs a) {
     __shared__ u32 s_cur[KG_MAX_BUCKETS];
     const u32 nb = a.nb;
-    if (threadIdx.x < nb) s_cur[threadIdx.x] = a.blk_base[(u64)blockIdx.x * nb + threadIdx.x];
+    for (u32 i = threadIdx.x; i < nb; i += blockDim.x) s_cur[i] = a.bucket_offs[i] + a.blk_base[(u64)blockIdx.x * nb + i];
     __syncthreads();
     const u32 T = a.st->total_bases, C = a.st->carry_bases;
     const u32 t = blockIdx.x * blockDim.x + threadIdx.x;

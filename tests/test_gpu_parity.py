@@ -291,7 +291,7 @@ def test_bloom_kmer_repeated_only_inside_one_warp(oracle):
 
 
 # ---- bucketed path on one GPU (hist -> scan -> scatter -> insert), the same kernels the multi-GPU exchange uses --
-@pytest.mark.parametrize("partitions", [2, 8, 32])
+@pytest.mark.parametrize("partitions", [2, 8, 32, 256, 1000])
 @pytest.mark.parametrize("k", [31, 51, 255])
 def test_partitioned_insert(oracle, k, partitions):
     rng = np.random.default_rng(k * 100 + partitions)
