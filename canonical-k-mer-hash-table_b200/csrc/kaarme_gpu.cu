@@ -16,6 +16,7 @@
 
 #include "kg_count.cuh"
 #include "kg_device.cuh"
+#include "kg_kaarme.cuh"
 #include "kg_parse.cuh"
 
 #define KG_MAX_W 8
@@ -84,6 +85,10 @@ struct kg_ctx {
     cudaEvent_t ev_counts = nullptr, ev_scatter = nullptr, ev_matrix = nullptr, ev_pass_ready = nullptr, ev_tail = nullptr;
     cudaEvent_t ev_send_free[2] = {nullptr, nullptr}, ev_recv_free[2] = {nullptr, nullptr}, ev_recv_full[2] = {nullptr, nullptr};
     uint64_t round = 0, subround = 0;
+    // Kaarme representation (after kg_compact)
+    KgKaarme kaarme{nullptr, nullptr, 0, 0};
+    KgCompactStats* d_cstats = nullptr;
+    bool compacted = false, counted = false;
     std::string err;
 };
 
@@ -216,6 +221,7 @@ static void free_all(kg_ctx* c) {
         if (c->ev_out[i]) cudaEventDestroy(c->ev_out[i]);
     }
     if (c->h_out_n) cudaFreeHost(c->h_out_n);
+    cudaFree(c->kaarme.slots); cudaFree(c->kaarme.roots); cudaFree(c->d_cstats);
     if (c->s_comm) cudaStreamSynchronize(c->s_comm);
     if (c->s_insert) cudaStreamSynchronize(c->s_insert);
     if (c->comm) { kg_nccl().CommDestroy(c->comm); c->comm = nullptr; }
@@ -326,7 +332,7 @@ extern "C" int kg_create(const kg_config* cfg, kg_ctx** out) {
         c->bloom_bytes = nblocks * 64;
         KG_TRY(cudaMalloc(&c->bloom.bits, c->bloom_bytes));
     }
-    c->bucketed = cfg->world > 1 || cfg->partitions > 1;
+    c->bucketed = cfg->world > 1 || (cfg->partitions > 1 && cfg->table_mode != KG_TABLE_KAARME);
     if (c->bucketed) {
         c->nb = cfg->world > 1 ? (u32)cfg->world : cfg->partitions;
         const size_t max_words = c->batch_bytes / 32 + c->carry_max_words + 2;
@@ -418,6 +424,12 @@ extern "C" int kg_pass_begin(kg_ctx* c, int pass) {
         KG_CUDA(c, cudaMemsetAsync(c->bloom.bits, 0, c->bloom_bytes, c->s_compute));
         c->bloom_done = false;
     } else {
+        if (c->compacted) {
+            cudaFree(c->kaarme.slots); cudaFree(c->kaarme.roots);
+            c->kaarme = KgKaarme{nullptr, nullptr, 0, 0};
+            c->compacted = false;
+        }
+        c->counted = false;
         uint64_t want;
         if (c->cfg.use_bloom) want = 2 * c->new_in_second;                      // main.cpp:454
         else want = (c->cfg.min_slots + (uint64_t)c->cfg.world - 1) / (uint64_t)c->cfg.world;
@@ -810,15 +822,107 @@ extern "C" int kg_pass_end(kg_ctx* c, kg_pass_stats* out) {
     const int pass = c->pass;
     c->pass = 0;
     c->stream_open = false;
+    if (pass == KG_PASS_COUNT) c->counted = true;
     if (pass == KG_PASS_COUNT && st.table_full) { c->err = "Hash table is full"; c->pass = 0; return KG_ETABLE_FULL; }
     return KG_OK;
 }
 
+template <int W>
+static void launch_kaarme_build(kg_ctx* c, const u32* bitmap, const u64* prefix, KgKaarme out, u64* root_counter) {
+    const u32 grid = (u32)((c->table.nslots + 255) / 256);
+    kg_kaarme_build<W><<<grid, 256, 0, c->s_compute>>>(c->table, c->cfg.k, bitmap, prefix, out, root_counter);
+    c->launches++;
+}
+template <int W>
+static void launch_kaarme_chain(kg_ctx* c) {
+    const u32 grid = (u32)((c->kaarme.n_kmers + 255) / 256);
+    if (grid) kg_kaarme_chain_stats<W><<<grid, 256, 0, c->s_compute>>>(c->kaarme, c->cfg.k, c->d_cstats);
+    c->launches++;
+}
+#define KG_DISPATCH_W(W_, fn, ...)                     \
+    switch (W_) {                                      \
+        case 1: fn<1>(__VA_ARGS__); break;             \
+        case 2: fn<2>(__VA_ARGS__); break;             \
+        case 3: fn<3>(__VA_ARGS__); break;             \
+        case 4: fn<4>(__VA_ARGS__); break;             \
+        case 5: fn<5>(__VA_ARGS__); break;             \
+        case 6: fn<6>(__VA_ARGS__); break;             \
+        case 7: fn<7>(__VA_ARGS__); break;             \
+        case 8: fn<8>(__VA_ARGS__); break;             \
+    }
+
 extern "C" int kg_compact(kg_ctx* c, kg_compact_stats* stats) {
-    (void)stats;
     if (!c) return KG_EBADARG;
-    c->err = "kg_compact: not built yet";
-    return KG_EBADARG;
+    if (c->cfg.table_mode != KG_TABLE_KAARME) { c->err = "kg_compact needs table_mode KG_TABLE_KAARME"; return KG_EBADARG; }
+    if (c->cfg.world > 1) { c->err = "kg_compact: occurrence positions are not exchanged between shards yet (single GPU only)"; return KG_EBADARG; }
+    if (!c->counted || !c->table.slots) { c->err = "kg_compact before the count pass"; return KG_EBADARG; }
+    if (c->compacted) return KG_OK;
+    KG_CUDA(c, cudaSetDevice(c->cfg.device));
+    cudaStream_t s = c->s_compute;
+    cudaEvent_t e0, e1;
+    KG_CUDA(c, cudaEventCreate(&e0));
+    KG_CUDA(c, cudaEventCreate(&e1));
+    KG_CUDA(c, cudaEventRecord(e0, s));
+    const u64 nslots = c->table.nslots;
+    const u32 grid = (u32)((nslots + 255) / 256);
+    const u64 nwords = (u64)grid * 8;
+    const u64 nsb = (nwords + 1023) / 1024;
+    u32 *bitmap = nullptr, *wcount = nullptr;
+    u64 *prefix = nullptr, *bsum = nullptr, *scalars = nullptr;   // scalars[0] = n_kmers, scalars[1] = root counter
+    KG_CUDA(c, cudaMalloc(&bitmap, sizeof(u32) * nwords));
+    KG_CUDA(c, cudaMalloc(&wcount, sizeof(u32) * nwords));
+    KG_CUDA(c, cudaMalloc(&prefix, sizeof(u64) * nwords));
+    KG_CUDA(c, cudaMalloc(&bsum, sizeof(u64) * nsb));
+    KG_CUDA(c, cudaMalloc(&scalars, sizeof(u64) * 2));
+    if (!c->d_cstats) KG_CUDA(c, cudaMalloc(&c->d_cstats, sizeof(KgCompactStats)));
+    KG_CUDA(c, cudaMemsetAsync(scalars, 0, sizeof(u64) * 2, s));
+    KG_CUDA(c, cudaMemsetAsync(c->d_cstats, 0, sizeof(KgCompactStats), s));
+    kg_occupancy_bitmap<<<grid, 256, 0, s>>>(c->table, bitmap, wcount);
+    kg_scan_blocks<<<(u32)nsb, 1024, 0, s>>>(wcount, bsum, nwords);
+    kg_scan_block_sums<<<1, 1024, 0, s>>>(bsum, nsb, scalars);
+    kg_scan_finish<<<(u32)nsb, 1024, 0, s>>>(wcount, bsum, prefix, nwords);
+    c->launches += 4;
+    u64 h[2];
+    KG_CUDA(c, cudaMemcpyAsync(h, scalars, sizeof(u64) * 2, cudaMemcpyDeviceToHost, s));
+    KG_CUDA(c, cudaStreamSynchronize(s));
+    const u64 n_kmers = h[0];
+    // sizing pass: how many roots?
+    KgKaarme probe{nullptr, nullptr, n_kmers, 0};
+    KG_DISPATCH_W(c->W, launch_kaarme_build, c, bitmap, prefix, probe, scalars + 1);
+    KG_CUDA(c, cudaMemcpyAsync(h, scalars, sizeof(u64) * 2, cudaMemcpyDeviceToHost, s));
+    KG_CUDA(c, cudaStreamSynchronize(s));
+    const u64 n_roots = h[1];
+    KgKaarme ks{nullptr, nullptr, n_kmers, n_roots};
+    KG_CUDA(c, cudaMalloc(&ks.slots, sizeof(u64) * (n_kmers ? n_kmers : 1)));
+    KG_CUDA(c, cudaMalloc(&ks.roots, sizeof(u64) * (n_roots ? n_roots : 1) * c->W));
+    KG_CUDA(c, cudaMemsetAsync(scalars + 1, 0, sizeof(u64), s));
+    KG_DISPATCH_W(c->W, launch_kaarme_build, c, bitmap, prefix, ks, scalars + 1);
+    c->kaarme = ks;
+    KG_DISPATCH_W(c->W, launch_kaarme_chain, c);
+    KG_CUDA(c, cudaEventRecord(e1, s));
+    KgCompactStats cs;
+    KG_CUDA(c, cudaMemcpyAsync(&cs, c->d_cstats, sizeof(cs), cudaMemcpyDeviceToHost, s));
+    KG_CUDA(c, cudaStreamSynchronize(s));
+    KG_CUDA(c, cudaGetLastError());
+    cudaFree(bitmap); cudaFree(wcount); cudaFree(prefix); cudaFree(bsum); cudaFree(scalars);
+    // the plain table has served its purpose: from here on only the compact structure exists
+    cudaFree(c->table.slots);
+    c->table.slots = nullptr;
+    c->table_bytes = 0;
+    c->compacted = true;
+    float ms = 0;
+    cudaEventElapsedTime(&ms, e0, e1);
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    if (cs.bad) { c->err = "kg_compact: malformed predecessor chain"; return KG_ECUDA; }
+    if (stats) {
+        stats->kmers = n_kmers;
+        stats->roots = n_roots;
+        stats->bytes = 8 * n_kmers + 8 * (uint64_t)c->W * n_roots;
+        stats->reference_bytes = 8 * nslots + (8 * (uint64_t)c->W + 1) * n_roots;   // kmer.hpp:107, kmer_hash_table.cpp:2144-2145
+        stats->max_chain = cs.max_chain;
+        stats->device_ms = ms;
+    }
+    return KG_OK;
 }
 
 // -----------------------------------------------------------------------------------------------------------
@@ -826,13 +930,17 @@ template <int W>
 static void launch_export(kg_ctx* c, u64 b, u64 e, uint64_t min_ab, int count_mode, int buf) {
     const u32 block = 256;
     const u32 grid = (u32)((e - b + block - 1) / block);
-    kg_export_kernel<W><<<grid, block, 0, c->s_compute>>>(c->table, b, e, min_ab, count_mode, c->cfg.table_mode,
-                                                        c->d_out_keys[buf], c->d_out_counts[buf], c->d_out_n[buf]);
+    if (c->compacted)
+        kg_kaarme_export<W><<<grid, block, 0, c->s_compute>>>(c->kaarme, c->cfg.k, b, e, min_ab, c->d_out_keys[buf],
+                                                            c->d_out_counts[buf], c->d_out_n[buf], c->d_cstats);
+    else
+        kg_export_kernel<W><<<grid, block, 0, c->s_compute>>>(c->table, b, e, min_ab, count_mode, c->cfg.table_mode,
+                                                            c->d_out_keys[buf], c->d_out_counts[buf], c->d_out_n[buf]);
     c->launches++;
 }
 
 extern "C" int kg_export(kg_ctx* c, uint64_t min_abundance, int count_mode, kg_sink_fn sink, void* user) {
-    if (!c || !sink || !c->table.slots) return KG_EBADARG;
+    if (!c || !sink || (!c->table.slots && !c->compacted)) return KG_EBADARG;
     if (min_abundance == 0) return KG_OK;  // parallel_parser.hpp:860-861
     KG_CUDA(c, cudaSetDevice(c->cfg.device));
     const int W = c->W;
@@ -847,7 +955,7 @@ extern "C" int kg_export(kg_ctx* c, uint64_t min_abundance, int count_mode, kg_s
         }
         KG_CUDA(c, cudaHostAlloc((void**)&c->h_out_n, 2 * sizeof(u32), cudaHostAllocDefault));
     }
-    const u64 nslots = c->table.nslots;
+    const u64 nslots = c->compacted ? c->kaarme.n_kmers : c->table.nslots;
     const u64 nchunks = (nslots + c->out_chunk - 1) / c->out_chunk;
     auto finish = [&](u64 i) -> int {
         const int b = (int)(i & 1);
@@ -881,6 +989,19 @@ extern "C" int kg_export(kg_ctx* c, uint64_t min_abundance, int count_mode, kg_s
     }
     if (nchunks > 0) { int rc = finish(nchunks - 1); if (rc) return rc; }
     KG_CUDA(c, cudaGetLastError());
+    if (c->compacted) {
+        KgCompactStats cs;
+        KG_CUDA(c, cudaMemcpy(&cs, c->d_cstats, sizeof(cs), cudaMemcpyDeviceToHost));
+        if (cs.bad) { c->err = "kg_export: malformed predecessor chain while decoding"; return KG_ECUDA; }
+    }
+    return KG_OK;
+}
+
+extern "C" int kg_kaarme_download(kg_ctx* c, uint64_t* slots, uint64_t* roots) {
+    if (!c || !c->compacted) return KG_EBADARG;
+    KG_CUDA(c, cudaSetDevice(c->cfg.device));
+    if (slots && c->kaarme.n_kmers) KG_CUDA(c, cudaMemcpy(slots, c->kaarme.slots, sizeof(u64) * c->kaarme.n_kmers, cudaMemcpyDeviceToHost));
+    if (roots && c->kaarme.n_roots) KG_CUDA(c, cudaMemcpy(roots, c->kaarme.roots, sizeof(u64) * c->kaarme.n_roots * c->W, cudaMemcpyDeviceToHost));
     return KG_OK;
 }
 

@@ -122,11 +122,22 @@ struct KgCountArgs {
     u32 rank, world;
 };
 
-// Walk the k-mer windows that END inside packed word t: calls f(key, hash) once per complete window whose
+// What the Kaarme representation needs to know about one occurrence of a k-mer (kmer.hpp:108-123 flags):
+// packed as (global_end_position << 4) | has_pred << 3 | self_forward_canonical << 2 | dropped_char
+struct KgOcc {
+    u64 word;
+};
+__device__ __forceinline__ KgOcc kg_make_occ(u64 global_pos, bool has_pred, bool fwd, u32 c_out) {
+    KgOcc o;
+    o.word = (global_pos << 4) | ((u64)has_pred << 3) | ((u64)fwd << 2) | (u64)c_out;
+    return o;
+}
+
+// Walk the k-mer windows that END inside packed word t: calls f(key, hash, occ) once per complete window whose
 // end position is >= C (positions below C belong to the previous batch).  Returns the number of windows.
 template <int W, typename F>
 __device__ __forceinline__ u32 kg_for_each_window(const u64* __restrict__ words, const u32* __restrict__ brk,
-                                                  u32 T, u32 C, u32 k, u32 t, F&& f) {
+                                                  u32 T, u32 C, u32 k, u32 t, u64 pos0, F&& f) {
     if ((u64)t * 32u >= T) return 0;
     const KgKGeom g = kg_geom(k);
     const u64 myword = words[t];
@@ -145,23 +156,21 @@ __device__ __forceinline__ u32 kg_for_each_window(const u64* __restrict__ words,
         }
     }
     KgKmerWindow<W> w;
-    // forward window = the k-1 bases before this word, right-aligned
+    // forward window = the k bases before this word, right-aligned (the oldest one is the base that drops out
+    // at the first step: the predecessor's first base, needed by the Kaarme occurrence record)
 #pragma unroll
     for (int i = 0; i < W; i++) {
         int src = (int)t - 1 - i;
         w.f[W - 1 - i] = src >= 0 ? words[src] : 0ULL;
     }
-    {
-        const u32 keep = 2 * (k - 1);                                             // bits of the k-1 prefix
-        const u32 topkeep = keep > 64u * (W - 1) ? keep - 64u * (W - 1) : 0u;     // of which in word 0
-        w.f[0] = topkeep == 0 ? 0ULL : (topkeep >= 64 ? w.f[0] : (w.f[0] & ((1ULL << topkeep) - 1)));
-    }
+    w.f[0] &= g.topmask;
     kg_revcomp<W>(w.f, w.r, g);
     const u32 base_pos = t * 32u;
     u32 n_windows = 0;
 #pragma unroll 1
     for (u32 j = 0; j < nvalid; j++) {
         const u32 c = (u32)(myword >> (62 - 2 * j)) & 3u;
+        const u32 c_out = (u32)(w.f[0] >> (g.topbits - 2)) & 3u;   // base leaving the window = first base of the predecessor
         kg_push<W>(w, g, c);
         run = ((mybrk >> (31 - j)) & 1u) ? 1u : run + 1u;
         if (run >= k && base_pos + j >= C) {
@@ -170,7 +179,7 @@ __device__ __forceinline__ u32 kg_for_each_window(const u64* __restrict__ words,
             const bool fwd = kg_forward_is_canonical<W>(w);
 #pragma unroll
             for (int i = 0; i < W; i++) key[i] = fwd ? w.f[i] : w.r[i];
-            f(key, kg_hash_key<W>(key));
+            f(key, kg_hash_key<W>(key), kg_make_occ(pos0 + base_pos + j, run > k, fwd, c_out));
         }
     }
     return n_windows;
@@ -190,7 +199,7 @@ struct KgConsume {
     KgBloom bloom;
     u32 n_new = 0, n_ins = 0, n_b1 = 0, n_b2 = 0, n_rej = 0;
     bool full = false;
-    __device__ __forceinline__ void operator()(const u64 (&key)[W], u64 h) {
+    __device__ __forceinline__ void operator()(const u64 (&key)[W], u64 h, KgOcc occ) {
         if (SINK == KG_SINK_BLOOM1) {
             kg_bloom_insert(bloom, h, n_b1, n_b2);
             return;
@@ -198,8 +207,12 @@ struct KgConsume {
         if (SINK == KG_SINK_BLOOM2 && !kg_bloom_admits(bloom, h)) { n_rej++; return; }
         bool is_new;
         u64 slot = kg_table_add<W>(table, key, h, is_new);
-        if (slot == ~0ULL) full = true;
-        else { n_ins++; n_new += is_new ? 1u : 0u; }
+        if (slot == ~0ULL) { full = true; return; }
+        n_ins++;
+        n_new += is_new ? 1u : 0u;
+        // Kaarme mode: remember the EARLIEST occurrence (atomicMax of the complement; the table starts zeroed).
+        // Same sector as the slot that was just touched, so it stays an L2 hit.
+        if (table.kaarme) atomicMax(table.slots + slot * table.stride + 1 + W, ~occ.word);
     }
     __device__ __forceinline__ void flush(KgStats* stats) {
         if (SINK == KG_SINK_TABLE || SINK == KG_SINK_BLOOM2) {
@@ -223,7 +236,7 @@ __global__ void __launch_bounds__(256) kg_count_kernel(KgCountArgs a) {
     KgConsume<W, SINK> sink;
     sink.table = a.table;
     sink.bloom = a.bloom;
-    u32 n_windows = kg_for_each_window<W>(a.words, a.brk, T, C, a.k, t, sink);
+    u32 n_windows = kg_for_each_window<W>(a.words, a.brk, T, C, a.k, t, a.st->bases_seen, sink);
     KG_WARP_ADD(a.stats, n_windows, input_kmers)
     sink.flush(a.stats);
 }
@@ -263,7 +276,8 @@ __global__ void __launch_bounds__(256) kg_insert_keys_kernel(const u64* __restri
                 u64 key[W];
 #pragma unroll
                 for (int q = 0; q < W; q++) key[q] = __ldcs(keys + i * W + q);   // streamed once: evict-first
-                sink(key, kg_hash_key<W>(key));
+                KgOcc none; none.word = ~0ULL;
+                sink(key, kg_hash_key<W>(key), none);
             }
         }
     }
@@ -312,8 +326,8 @@ __global__ void __launch_bounds__(256) kg_owner_hist(KgBucketArgs a) {
     const u32 T = a.st->total_bases, C = a.st->carry_bases;
     const u32 t = blockIdx.x * blockDim.x + threadIdx.x;
     const u32 nb = a.nb;
-    u32 n_windows = kg_for_each_window<W>(a.words, a.brk, T, C, a.k, t,
-                                          [&](const u64 (&key)[W], u64 h) { (void)key; atomicAdd(&s_hist[kg_bucket_of(h, a.world, nb)], 1u); });
+    u32 n_windows = kg_for_each_window<W>(a.words, a.brk, T, C, a.k, t, 0,
+                                          [&](const u64 (&key)[W], u64 h, KgOcc) { (void)key; atomicAdd(&s_hist[kg_bucket_of(h, a.world, nb)], 1u); });
     KG_WARP_ADD(a.stats, n_windows, input_kmers)
     __syncthreads();
     for (u32 i = threadIdx.x; i < nb; i += blockDim.x) a.blk_hist[(u64)blockIdx.x * nb + i] = s_hist[i];
@@ -367,7 +381,7 @@ __global__ void __launch_bounds__(256) kg_owner_scatter(KgBucketArgs a) {
     const u32 T = a.st->total_bases, C = a.st->carry_bases;
     const u32 t = blockIdx.x * blockDim.x + threadIdx.x;
     u64* out = a.out_keys;
-    kg_for_each_window<W>(a.words, a.brk, T, C, a.k, t, [&](const u64 (&key)[W], u64 h) {
+    kg_for_each_window<W>(a.words, a.brk, T, C, a.k, t, 0, [&](const u64 (&key)[W], u64 h, KgOcc) {
         const u32 pos = atomicAdd(&s_cur[kg_bucket_of(h, a.world, nb)], 1u);
         u64* dst = out + (u64)pos * W;
 #pragma unroll

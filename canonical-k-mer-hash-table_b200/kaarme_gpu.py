@@ -65,7 +65,7 @@ SINK_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.POINTER(C.c_uint64), C.POINTER(C.c_
 EXPORTS = ["kg_abi_version", "kg_strerror", "kg_last_error", "kg_device_count", "kg_create", "kg_destroy",
            "kg_host_alloc", "kg_host_free", "kg_comm_unique_id", "kg_comm_init", "kg_pass_begin",
            "kg_stream_begin", "kg_feed", "kg_feed_device", "kg_pass_end", "kg_compact", "kg_export",
-           "kg_table_info", "kg_atomic_ceiling", "kg_launch_count"]
+           "kg_table_info", "kg_atomic_ceiling", "kg_launch_count", "kg_kaarme_download"]
 
 _lib = None
 
@@ -98,6 +98,7 @@ def lib():
         L.kg_table_info.argtypes = [C.c_void_p, C.POINTER(C.c_uint64), C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]
         L.kg_atomic_ceiling.argtypes = [C.c_int, C.c_uint64, C.c_uint64, C.c_int, C.POINTER(C.c_double)]
         L.kg_launch_count.argtypes = [C.c_void_p, C.POINTER(C.c_uint64)]
+        L.kg_kaarme_download.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
         _lib = L
     return _lib
 
@@ -204,7 +205,16 @@ class Counter:
     def compact(self) -> dict:
         st = CompactStats()
         self._check(lib().kg_compact(self._h, C.byref(st)), "kg_compact")
-        return st.as_dict()
+        self._compact = st.as_dict()
+        return self._compact
+
+    def kaarme_download(self):
+        """-> (slots [kmers] uint64, roots [roots, W] uint64) of the compact structure built by compact()."""
+        st = self._compact
+        slots = np.zeros(max(1, st["kmers"]), np.uint64)
+        roots = np.zeros(max(1, st["roots"]) * self.W, np.uint64)
+        self._check(lib().kg_kaarme_download(self._h, slots.ctypes.data, roots.ctypes.data), "kg_kaarme_download")
+        return slots[:st["kmers"]], roots[:st["roots"] * self.W].reshape(-1, self.W)
 
     def export(self, min_abundance=1, count_mode=COUNT_EXACT, sort=True):
         """-> (keys [n, W] uint64, counts [n] uint32), sorted by key when sort=True."""

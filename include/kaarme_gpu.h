@@ -159,6 +159,10 @@ int kg_compact(kg_ctx* ctx, kg_compact_stats* stats);
  * parallel_parser.hpp:860-861).  In KG_TABLE_KAARME mode after kg_compact the k-mers are DECODED from
  * the compact structure (chain walk, kmer_hash_table.cpp:3848-4058), not read from the plain table. */
 int kg_export(kg_ctx* ctx, uint64_t min_abundance, int count_mode, kg_sink_fn sink, void* user);
+/* Copy the compact structure to host memory after kg_compact: slots = kmers words (kmer.hpp:108-123 layout,
+ * pointers are indices into this same array), roots = roots*W words (the secondary array,
+ * kmer_hash_table.cpp:2144-2145).  Either pointer may be NULL.  Sizes come from kg_compact_stats.           */
+int kg_kaarme_download(kg_ctx* ctx, uint64_t* slots, uint64_t* roots);
 /* Table geometry for reports: bytes per slot and slots. */
 int kg_table_info(const kg_ctx* ctx, uint64_t* slots, uint32_t* slot_bytes, uint32_t* key_words);
 

@@ -533,7 +533,7 @@ int64_t ko_kaarme_decode(const uint64_t* table, uint64_t n_slots, const uint64_t
         if (s != p) pir = !pir;
         pos = KS_PTR(d);
         if (pos >= n_slots) return -1;
-        if (++hops > (int64_t)k + 1) return -1;
+        if (++hops > (int64_t)n_slots) return -1; /* acyclic chains are shorter than the table */
     }
     {
         uint64_t r = KS_PTR(table[pos]);

@@ -312,3 +312,76 @@ def test_partitioned_bloom(oracle):
         c.run_pass(K.PASS_COUNT, data)
         keys, counts = c.export(2, K.COUNT_EXACT)
     assert_same(keys, counts, truth.filtered(2))
+
+
+# ---- Kaarme (-m 2): compaction of the counted table into 8-byte slots + roots, decoded on export -----------------
+def gpu_kaarme(data, k, input_mode=K.INPUT_FASTA, slots=400000, a=1, bloom=None, batch_bytes=0, download=False):
+    kw = dict(use_bloom=True, expected_unique=bloom[0], fpr=bloom[1]) if bloom else dict(min_slots=slots)
+    with kg.Counter(k=k, table_mode=K.TABLE_KAARME, input_mode=input_mode, batch_bytes=batch_bytes, **kw) as c:
+        if bloom:
+            c.run_pass(K.PASS_BLOOM, data)
+        st = c.run_pass(K.PASS_COUNT, data)
+        cs = c.compact()
+        arrays = c.kaarme_download() if download else None
+        keys, counts = c.export(a, K.COUNT_REFERENCE)
+    return keys, counts, st, cs, arrays
+
+
+@pytest.mark.parametrize("case", [c for c in CASES if c["mode"] == 2 and c["k"] in (21, 33, 51, 127, 255)],
+                         ids=lambda c: f"{c['input']}-k{c['k']}-a{c['a']}-{'b' if c['unique'] else 's'}")
+def test_golden_kaarme(case):
+    """-m 2 against the reference binary's sorted output; with -b only -a 2 is hash-independent"""
+    if case["unique"] and case["a"] < 2:
+        pytest.skip("-a 1 output of the Bloom mode depends on the filter's false positives")
+    data = _read(case["input"])
+    keys, counts, st, cs, _ = gpu_kaarme(data, case["k"], _imode(case["input"]), case["slots"] or 0, case["a"],
+                                         bloom=(case["unique"], case["fpr"]) if case["unique"] else None)
+    txt = kg.keys_to_text(keys, counts, case["k"])
+    assert txt.count(b"\n") == case["n_lines"]
+    assert hashlib.sha256(txt).hexdigest() == case["sha256"]
+    assert cs["kmers"] == st["distinct"] and cs["bytes"] == 8 * cs["kmers"] + 8 * ((case["k"] + 31) // 32) * cs["roots"]
+
+
+@pytest.mark.parametrize("k", [5, 21, 31, 32, 33, 51, 64, 65, 96, 127, 128, 200, 255, 256])
+def test_kaarme_vs_oracle(oracle, k):
+    """every k, including k = 0 mod 32 where the reference's own -m 2 is broken"""
+    rng = np.random.default_rng(7000 + k)
+    data = make_fasta(rng, 30000, 80, 1500, wrap=70, err=0.01, n_rate=0.0005)
+    want = oracle.count(data, k).filtered(1, oracle.TABLE_KAARME)
+    keys, counts, st, cs, _ = gpu_kaarme(data, k, batch_bytes=16384)
+    assert_same(keys, counts, want)
+    assert cs["kmers"] == want.n and 0 < cs["roots"] < want.n
+    print(f"k={k}: {cs['kmers']} k-mers, {cs['roots']} roots, {cs['bytes'] / cs['kmers']:.2f} B/k-mer, max chain {cs['max_chain']}")
+
+
+def test_kaarme_structure_decodes_with_reference_algorithm(oracle):
+    """the downloaded slots/roots, decoded by the oracle's restatement of reconstruct_kmer_in_slot
+    (kmer_hash_table.cpp:3848-4058), give exactly the exported k-mers: the structure is bit-compatible"""
+    rng = np.random.default_rng(99)
+    k = 51
+    data = make_fasta(rng, 20000, 60, 1200, wrap=80, err=0.01)
+    keys, counts, st, cs, (slots, roots) = gpu_kaarme(data, k, download=True)
+    assert len(slots) == cs["kmers"] and roots.shape[0] == cs["roots"]
+    got = set()
+    for i in range(len(slots)):
+        hops, codes = oracle.kaarme_decode(slots, roots, k, i)
+        assert hops >= 0
+        got.add(("".join("ACGT"[c] for c in codes), int((slots[i] >> np.uint64(12)) & np.uint64(16383))))
+    want = set(zip(oracle.key_strings(keys, k), (int(c) for c in counts)))
+    assert got == want
+    assert cs["bytes"] < 10 * cs["kmers"]          # ~8 B per k-mer + a few roots
+
+
+def test_kaarme_after_bloom(oracle):
+    rng = np.random.default_rng(31)
+    data = make_fasta(rng, 60000, 300, 800, wrap=70, err=0.02)
+    truth = oracle.count(data, 31)
+    keys, counts, st, cs, _ = gpu_kaarme(data, 31, a=2, bloom=(truth.n, 0.01))
+    assert_same(keys, counts, truth.filtered(2, oracle.TABLE_KAARME))
+
+
+def test_kaarme_count_saturation(oracle):
+    data = _read("g4_polya.fasta")
+    keys, counts, st, cs, _ = gpu_kaarme(data, 21, a=2)
+    assert_same(keys, counts, oracle.count(data, 21).filtered(2, oracle.TABLE_KAARME))
+    assert int(counts.max()) == 16383
