@@ -60,3 +60,20 @@ def test_cli_plain_text_input_and_ill_formed(tmp_path):
 def test_cli_table_full_exits_nonzero(tmp_path):
     p = run_cli([os.path.join(GOLDEN, "g5_long.fasta"), 31, "-m", 0, "-s", 1000, "-o", tmp_path / "o"])
     assert p.returncode == 1 and "Hash table is full" in p.stdout
+
+
+@pytest.mark.parametrize("case", [c for c in CASES if c["mode"] == 2 and c["k"] in (21, 51, 127) and c["a"] == 2
+                                  and c["input"] in ("g1_multiline.fasta", "g5_long.fasta", "g4_polya.fasta")],
+                         ids=lambda c: f"{c['input']}-k{c['k']}-{'b' if c['unique'] else 's'}")
+def test_cli_kaarme_mode(case, tmp_path):
+    """-m 2 (the CLI default): counted, compacted to 8-byte slots, decoded on export; same output as the reference"""
+    out, js = tmp_path / "out.txt", tmp_path / "stats.json"
+    args = [os.path.join(GOLDEN, case["input"]), case["k"], "-a", case["a"], "-t", 4, "-o", out, "--stats-json", js]
+    args += ["-b", "-u", case["unique"], "-f", case["fpr"]] if case["unique"] else ["-s", case["slots"]]
+    p = run_cli(args)
+    assert p.returncode == 0, p.stderr
+    assert sorted_sha(out) == (case["n_lines"], case["sha256"])
+    assert "Starting atomic variable pointer hash table" in p.stdout and "Written k-mers:" in p.stdout
+    st = json.load(open(js))
+    assert st["kaarme"]["kmers"] == st["count"]["distinct"]
+    assert st["kaarme"]["bytes"] == 8 * st["kaarme"]["kmers"] + 8 * ((case["k"] + 31) // 32) * st["kaarme"]["roots"]
