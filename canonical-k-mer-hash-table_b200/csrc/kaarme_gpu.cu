@@ -336,7 +336,7 @@ extern "C" int kg_create(const kg_config* cfg, kg_ctx** out) {
     if (c->bucketed) {
         c->nb = cfg->world > 1 ? (u32)cfg->world : cfg->partitions;
         const size_t max_words = c->batch_bytes / 32 + c->carry_max_words + 2;
-        c->max_blocks = (u32)((max_words + 255) / 256);
+        c->max_blocks = (u32)((max_words + 31) / 32);   // smallest block of the hist/scatter pair covers 32 words
         c->send_cap = c->batch_bytes + 64;                       // a batch of n bytes holds < n k-mers
         c->recv_cap = cfg->world > 1 ? 2 * c->send_cap : 0;      // single GPU inserts straight from the send buffer
         KG_TRY(cudaStreamCreateWithFlags(&c->s_comm, cudaStreamNonBlocking));
@@ -524,20 +524,35 @@ static void insert_keys(kg_ctx* c, cudaStream_t s, const u64* keys, u64 n_upper,
 }
 
 template <int W>
-static void launch_bucket(kg_ctx* c, const KgBucketArgs& a, u32 grid, bool scatter) {
+static void launch_bucket(kg_ctx* c, const KgBucketArgs& a, u32 nwords, bool scatter) {
+    using G = KgBucketGeom<W>;
+    const u32 grid = (nwords + G::WPB - 1) / G::WPB;
     if (scatter) {
-        // occupancy throttle: the scatter's in-flight partially written runs (blocks x 128 KB) must stay within
-        // L2, else sectors are evicted half-written; dynamic shared memory caps the resident blocks per SM
-        static int smem = -1;
-        if (smem < 0) {
-            const char* e = getenv("KG_SCATTER_SMEM");
-            smem = e ? atoi(e) : 0;
-            if (smem > 48 * 1024) cudaFuncSetAttribute(kg_owner_scatter<W>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        const size_t smem = G::smem_bytes(a.nb);
+        static bool configured = false;
+        if (!configured) {
+            cudaFuncSetAttribute(kg_owner_scatter<W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G::smem_bytes(KG_MAX_BUCKETS));
+            configured = true;
         }
-        kg_owner_scatter<W><<<grid, 256, smem, c->s_compute>>>(a);
+        kg_owner_scatter<W><<<grid, G::TPB, smem, c->s_compute>>>(a);
+    } else {
+        kg_owner_hist<W><<<grid, G::WPB, 0, c->s_compute>>>(a);
     }
-    else kg_owner_hist<W><<<grid, 256, 0, c->s_compute>>>(a);
     c->launches++;
+}
+template <int W>
+static u32 bucket_grid(u32 nwords) { return (nwords + KgBucketGeom<W>::WPB - 1) / KgBucketGeom<W>::WPB; }
+static u32 bucket_blocks(const kg_ctx* c, u32 nwords) {
+    switch (c->W) {
+        case 1: return bucket_grid<1>(nwords);
+        case 2: return bucket_grid<2>(nwords);
+        case 3: return bucket_grid<3>(nwords);
+        case 4: return bucket_grid<4>(nwords);
+        case 5: return bucket_grid<5>(nwords);
+        case 6: return bucket_grid<6>(nwords);
+        case 7: return bucket_grid<7>(nwords);
+        default: return bucket_grid<8>(nwords);
+    }
 }
 static void bucket_kernel(kg_ctx* c, const KgBucketArgs& a, u32 grid, bool scatter) {
     switch (c->W) {
@@ -621,13 +636,14 @@ static int exchange_round(kg_ctx* c, bool have_batch, bool* all_done) {
 
 // bucket the k-mers of the batch that was just packed (hist -> scan -> scatter), then hand them on
 static int bucket_batch(kg_ctx* c, u32 nthreads) {
-    const u32 grid = (nthreads + 255) / 256;
+    const u32 grid = bucket_blocks(c, nthreads);   // blocks of the hist / scatter pair
     const int sb = c->cfg.world > 1 ? (int)(c->round & 1) : 0;
     KgBucketArgs a;
     a.words = c->d_words; a.brk = c->d_brk; a.st = c->d_stream;
     a.blk_hist = c->d_blk_hist; a.blk_base = c->d_blk_base; a.bucket_offs = c->d_bucket_offs; a.out_keys = c->d_send[sb];
     a.stats = c->d_stats; a.k = c->cfg.k; a.nb = c->nb; a.world = (u32)c->cfg.world;
-    bucket_kernel(c, a, grid, false);
+    { const char* e = getenv("KG_SCATTER_DBG"); a.dbg = e ? (u32)atoi(e) : 0; }
+    bucket_kernel(c, a, nthreads, false);
     kg_bucket_colscan<<<c->nb, 1024, 0, c->s_compute>>>(c->d_blk_hist, c->d_blk_base, grid, c->nb, c->d_bucket_counts);
     kg_bucket_offsets<<<1, 1024, 0, c->s_compute>>>(c->d_bucket_counts, c->nb, c->d_bucket_offs);
     c->launches += 2;
@@ -635,14 +651,14 @@ static int bucket_batch(kg_ctx* c, u32 nthreads) {
         KG_CUDA(c, cudaMemsetAsync(c->d_bucket_counts + c->nb, 0, sizeof(u32), c->s_compute));   // not done
         KG_CUDA(c, cudaEventRecord(c->ev_counts, c->s_compute));
         KG_CUDA(c, cudaStreamWaitEvent(c->s_compute, c->ev_send_free[sb], 0));   // round-2 sends have left this buffer
-        bucket_kernel(c, a, grid, true);
+        bucket_kernel(c, a, nthreads, true);
         KG_CUDA(c, cudaEventRecord(c->ev_scatter, c->s_compute));
         bool all_done;
         return exchange_round(c, true, &all_done);
     }
     // single GPU, partitioned: the send buffer is partition-major; one insert launch walks it in order, so the
     // blocks in flight at any moment hit one or two table regions (L2-resident)
-    bucket_kernel(c, a, grid, true);
+    bucket_kernel(c, a, nthreads, true);
     insert_keys(c, c->s_compute, c->d_send[0], (u64)nthreads * 32u, c->d_bucket_offs + c->nb);
     return KG_OK;
 }

@@ -137,38 +137,57 @@ __device__ __forceinline__ KgOcc kg_make_occ(u64 global_pos, bool has_pred, bool
 // end position is >= C (positions below C belong to the previous batch).  Returns the number of windows.
 template <int W, typename F>
 __device__ __forceinline__ u32 kg_for_each_window(const u64* __restrict__ words, const u32* __restrict__ brk,
-                                                  u32 T, u32 C, u32 k, u32 t, u64 pos0, F&& f) {
-    if ((u64)t * 32u >= T) return 0;
+                                                  u32 T, u32 C, u32 k, u32 t, u64 pos0, F&& f,
+                                                  u32 j0 = 0, u32 j1 = 32) {
+    if ((u64)t * 32u + j0 >= T) return 0;
     const KgKGeom g = kg_geom(k);
     const u64 myword = words[t];
     const u32 mybrk = brk[t];
-    const u32 nvalid = min(32u, T - t * 32u);
-    // run length at the base just before this word: distance back to the most recent run start
+    const u32 jend = min(j1, T - t * 32u);
+    // run length at the base just before position 32t + j0: distance back to the most recent run start
     u32 run = 0;
     {
-        bool found = false;
+        const u32 head = j0 ? (mybrk >> (32 - j0)) : 0u;         // break bits of bases 0..j0-1 of this word
+        if (head) {
+            run = __ffs(head);
+        } else {
+            run = j0;
+            bool found = false;
 #pragma unroll 1
-        for (int i = 1; i <= W + 1 && !found; i++) {
-            if ((int)t - i < 0) break;                          // position 0 always carries a break bit
-            u32 b = brk[t - i];
-            if (b) { run += __ffs(b); found = true; }           // lowest set bit = most recent base of that word
-            else run += 32;
+            for (int i = 1; i <= W + 1 && !found; i++) {
+                if ((int)t - i < 0) break;                          // position 0 always carries a break bit
+                u32 b = brk[t - i];
+                if (b) { run += __ffs(b); found = true; }           // lowest set bit = most recent base of that word
+                else run += 32;
+            }
         }
     }
     KgKmerWindow<W> w;
-    // forward window = the k bases before this word, right-aligned (the oldest one is the base that drops out
-    // at the first step: the predecessor's first base, needed by the Kaarme occurrence record)
+    // forward window = the k bases before position 32t + j0, right-aligned (the oldest one is the base that drops
+    // out at the first step: the predecessor's first base, needed by the Kaarme occurrence record)
+    if (j0 == 0) {
 #pragma unroll
-    for (int i = 0; i < W; i++) {
-        int src = (int)t - 1 - i;
-        w.f[W - 1 - i] = src >= 0 ? words[src] : 0ULL;
+        for (int i = 0; i < W; i++) {
+            int src = (int)t - 1 - i;
+            w.f[W - 1 - i] = src >= 0 ? words[src] : 0ULL;
+        }
+    } else {
+        const u32 s = 64 - 2 * j0;                                   // unread bits of this word, 2..62
+        u64 lo = myword;
+#pragma unroll
+        for (int i = 0; i < W; i++) {
+            int src = (int)t - 1 - i;
+            const u64 hi = src >= 0 ? words[src] : 0ULL;
+            w.f[W - 1 - i] = (hi << (64 - s)) | (lo >> s);
+            lo = hi;
+        }
     }
     w.f[0] &= g.topmask;
     kg_revcomp<W>(w.f, w.r, g);
     const u32 base_pos = t * 32u;
     u32 n_windows = 0;
 #pragma unroll 1
-    for (u32 j = 0; j < nvalid; j++) {
+    for (u32 j = j0; j < jend; j++) {
         const u32 c = (u32)(myword >> (62 - 2 * j)) & 3u;
         const u32 c_out = (u32)(w.f[0] >> (g.topbits - 2)) & 3u;   // base leaving the window = first base of the predecessor
         kg_push<W>(w, g, c);
@@ -179,7 +198,7 @@ __device__ __forceinline__ u32 kg_for_each_window(const u64* __restrict__ words,
             const bool fwd = kg_forward_is_canonical<W>(w);
 #pragma unroll
             for (int i = 0; i < W; i++) key[i] = fwd ? w.f[i] : w.r[i];
-            f(key, kg_hash_key<W>(key), kg_make_occ(pos0 + base_pos + j, run > k, fwd, c_out));
+            f(key, kg_hash_key<W>(key), kg_make_occ(pos0 + base_pos + j, run > k, fwd, c_out), j);
         }
     }
     return n_windows;
@@ -199,7 +218,7 @@ struct KgConsume {
     KgBloom bloom;
     u32 n_new = 0, n_ins = 0, n_b1 = 0, n_b2 = 0, n_rej = 0;
     bool full = false;
-    __device__ __forceinline__ void operator()(const u64 (&key)[W], u64 h, KgOcc occ) {
+    __device__ __forceinline__ void operator()(const u64 (&key)[W], u64 h, KgOcc occ, u32 = 0) {
         if (SINK == KG_SINK_BLOOM1) {
             kg_bloom_insert(bloom, h, n_b1, n_b2);
             return;
@@ -312,6 +331,7 @@ struct KgBucketArgs {
     u32 k;
     u32 nb;             // number of buckets: world (multi-GPU) or partitions (single GPU)
     u32 world;          // > 1: bucket = owner shard; 1: bucket = partition of the local hash
+    u32 dbg;            // experiments: 1 = skip the global stores, 2 = skip the shared atomics
 };
 
 __device__ __forceinline__ u32 kg_bucket_of(u64 h, u32 world, u32 nb) {
@@ -319,7 +339,7 @@ __device__ __forceinline__ u32 kg_bucket_of(u64 h, u32 world, u32 nb) {
 }
 
 template <int W>
-__global__ void __launch_bounds__(256) kg_owner_hist(KgBucketArgs a) {
+__global__ void __launch_bounds__(128) kg_owner_hist(KgBucketArgs a) {   // launched with KgBucketGeom<W>::WPB threads
     __shared__ u32 s_hist[KG_MAX_BUCKETS];
     for (u32 i = threadIdx.x; i < a.nb; i += blockDim.x) s_hist[i] = 0;
     __syncthreads();
@@ -327,7 +347,7 @@ __global__ void __launch_bounds__(256) kg_owner_hist(KgBucketArgs a) {
     const u32 t = blockIdx.x * blockDim.x + threadIdx.x;
     const u32 nb = a.nb;
     u32 n_windows = kg_for_each_window<W>(a.words, a.brk, T, C, a.k, t, 0,
-                                          [&](const u64 (&key)[W], u64 h, KgOcc) { (void)key; atomicAdd(&s_hist[kg_bucket_of(h, a.world, nb)], 1u); });
+                                          [&](const u64 (&key)[W], u64 h, KgOcc, u32) { (void)key; atomicAdd(&s_hist[kg_bucket_of(h, a.world, nb)], 1u); });
     KG_WARP_ADD(a.stats, n_windows, input_kmers)
     __syncthreads();
     for (u32 i = threadIdx.x; i < nb; i += blockDim.x) a.blk_hist[(u64)blockIdx.x * nb + i] = s_hist[i];
@@ -372,21 +392,95 @@ __global__ void __launch_bounds__(1024) kg_bucket_offsets(const u32* __restrict_
     if (threadIdx.x == 1023) offs_out[nb] = sm[1023];
 }
 
+// Geometry shared by hist and scatter: a block owns KgBucketGeom<W>::WPB packed words (32*WPB k-mer end positions).
+// hist runs one thread per word; scatter runs four threads per word (8 positions each) and stages the block's
+// keys in shared memory so that every bucket leaves the block as ONE contiguous, coalesced run.  (Writing each key
+// straight from its thread costs two 8-byte partial-sector stores per k-mer and runs at ~25 G keys/s; see
+// profiles/r01_partitioned_scatter_insert_ncu.txt and profiles/scatter_probe.sh.)
 template <int W>
-__global__ void __launch_bounds__(256) kg_owner_scatter(KgBucketArgs a) {
-    __shared__ u32 s_cur[KG_MAX_BUCKETS];
-    const u32 nb = a.nb;
-    for (u32 i = threadIdx.x; i < nb; i += blockDim.x) s_cur[i] = a.bucket_offs[i] + a.blk_base[(u64)blockIdx.x * nb + i];
+struct KgBucketGeom {
+    static constexpr int WPB = W <= 2 ? 128 : (W <= 4 ? 64 : 32);   // words per block: <= 64 KiB of staged keys
+    static constexpr int TPB = 4 * WPB;                             // scatter threads per block
+    static constexpr int KEYS = 32 * WPB;                           // staged keys per block (upper bound)
+    static constexpr size_t smem_bytes(u32 nb) {
+        return (size_t)KEYS * W * 8 + (size_t)KEYS * 2 /*bucket of a staged key*/ + (size_t)TPB * 8 * 4 /*ranks*/ +
+               (size_t)nb * 4 * 3 /*count, offset, global base*/ + 64;
+    }
+};
+
+template <int W>
+__global__ void __launch_bounds__(KgBucketGeom<W>::TPB) kg_owner_scatter(KgBucketArgs a) {
+    using G = KgBucketGeom<W>;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    u64* s_keys = reinterpret_cast<u64*>(smem_raw);                                  // KEYS * W
+    u32* s_rank = reinterpret_cast<u32*>(s_keys + (size_t)G::KEYS * W);                // TPB * 8
+    u32* s_cnt = s_rank + G::TPB * 8;                                                  // nb
+    u32* s_off = s_cnt + a.nb;                                                         // nb
+    u32* s_gbase = s_off + a.nb;                                                       // nb
+    unsigned short* s_kb = reinterpret_cast<unsigned short*>(s_gbase + a.nb);          // KEYS
+    __shared__ u32 s_warp[32];
+    const u32 nb = a.nb, tid = threadIdx.x;
+    for (u32 i = tid; i < nb; i += G::TPB) s_cnt[i] = 0;
     __syncthreads();
     const u32 T = a.st->total_bases, C = a.st->carry_bases;
-    const u32 t = blockIdx.x * blockDim.x + threadIdx.x;
-    u64* out = a.out_keys;
-    kg_for_each_window<W>(a.words, a.brk, T, C, a.k, t, 0, [&](const u64 (&key)[W], u64 h, KgOcc) {
-        const u32 pos = atomicAdd(&s_cur[kg_bucket_of(h, a.world, nb)], 1u);
-        u64* dst = out + (u64)pos * W;
+    const u32 t = blockIdx.x * G::WPB + (tid >> 2);
+    const u32 j0 = (tid & 3u) * 8u;
+    // pass 1: bucket and rank-in-bucket of each of my (<= 8) windows
 #pragma unroll
-        for (int i = 0; i < W; i++) dst[i] = key[i];
-    });
+    for (int q = 0; q < 8; q++) s_rank[q * G::TPB + tid] = 0xFFFFFFFFu;
+    kg_for_each_window<W>(a.words, a.brk, T, C, a.k, t, 0, [&](const u64 (&key)[W], u64 h, KgOcc, u32 j) {
+        (void)key;
+        const u32 b = kg_bucket_of(h, a.world, nb);
+        const u32 r = atomicAdd(&s_cnt[b], 1u);
+        s_rank[(j - j0) * G::TPB + tid] = (b << 16) | r;
+    }, j0, j0 + 8);
+    __syncthreads();
+    // exclusive scan of the bucket counts (nb <= 1024), and the global base of every bucket run
+    {
+        const u32 per = (nb + G::TPB - 1) / G::TPB;
+        const u32 b0 = tid * per, b1 = min(b0 + per, nb);
+        u32 mine = 0;
+        for (u32 i = b0; i < b1; i++) mine += s_cnt[i];
+        u32 incl = mine;
+        const u32 lane = tid & 31u, warp = tid >> 5;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) { u32 o = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= (u32)d) incl += o; }
+        if (lane == 31) s_warp[warp] = incl;
+        __syncthreads();
+        u32 pre = 0;
+        for (u32 w2 = 0; w2 < warp; w2++) pre += s_warp[w2];
+        u32 cur = pre + incl - mine;
+        for (u32 i = b0; i < b1; i++) {
+            s_off[i] = cur;
+            cur += s_cnt[i];
+            s_gbase[i] = a.bucket_offs[i] + a.blk_base[(u64)blockIdx.x * nb + i];
+        }
+    }
+    __syncthreads();
+    // pass 2: recompute the windows and drop each key at its staged position (keys grouped by bucket)
+    kg_for_each_window<W>(a.words, a.brk, T, C, a.k, t, 0, [&](const u64 (&key)[W], u64, KgOcc, u32 j) {
+        const u32 br = s_rank[(j - j0) * G::TPB + tid];
+        const u32 b = br >> 16, idx = s_off[b] + (br & 0xFFFFu);
+#pragma unroll
+        for (int i = 0; i < W; i++) s_keys[(size_t)idx * W + i] = key[i];
+        s_kb[idx] = (unsigned short)b;
+    }, j0, j0 + 8);
+    __syncthreads();
+    // coalesced write-out: consecutive staged keys of one bucket go to consecutive global addresses
+    const u32 n = s_off[nb - 1] + s_cnt[nb - 1];
+    if (a.dbg == 1) return;
+    for (u32 i = tid; i < n; i += G::TPB) {
+        const u32 b = s_kb[i];
+        u64* dst = a.out_keys + (u64)(s_gbase[b] + (i - s_off[b])) * W;
+        if (W % 2 == 0) {
+#pragma unroll
+            for (int q = 0; q < W; q += 2)
+                *reinterpret_cast<ulonglong2*>(dst + q) = make_ulonglong2(s_keys[(size_t)i * W + q], s_keys[(size_t)i * W + q + 1]);
+        } else {
+#pragma unroll
+            for (int q = 0; q < W; q++) dst[q] = s_keys[(size_t)i * W + q];
+        }
+    }
 }
 
 // ---- K5 export: stream-compact slots whose reported count >= min_abundance -------------------------------
