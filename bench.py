@@ -46,7 +46,7 @@ def parse_args():
     p.add_argument("--k", type=int, default=K)
     p.add_argument("--workload", default=WORKLOAD)
     p.add_argument("--partitions", type=int, default=int(os.environ.get("KAARME_PARTITIONS", "0")),
-                   help="single GPU: bucket each batch into this many table regions before inserting (0 = direct)")
+                   help="table regions each batch is bucketed into before inserting (0 = library default, 1 = direct insert)")
     p.add_argument("--batch-mb", type=int, default=int(os.environ.get("KAARME_BATCH_MB", "256")))
     p.add_argument("--no-cpu-baseline", action="store_true")
     p.add_argument("--no-e2e", action="store_true")
@@ -180,7 +180,7 @@ def main():
     total_slots = meta["slots"] * world
     ctr = kg.Counter(k=k, table_mode=KG.TABLE_PLAIN, input_mode=KG.INPUT_FASTA, min_slots=total_slots,
                      device=local_rank, rank=rank, world=world, batch_bytes=args.batch_mb << 20,
-                     partitions=args.partitions if world == 1 else 0)
+                     partitions=args.partitions)
     if world > 1:
         uid = [kg.comm_unique_id() if rank == 0 else None]
         dist.broadcast_object_list(uid, src=0)
@@ -296,7 +296,7 @@ def main():
                       "input_kmers_per_gpu": meta["input_kmers"], "distinct_rank0": distinct,
                       "l2": "inputs (2 GB) and table (8 GB) are far larger than L2; no flush needed",
                       "parallelism": f"hash-sharded x{world}" if world > 1 else "single GPU",
-                      "partitions": args.partitions, "batch_mb": args.batch_mb},
+                      "partitions": st["partitions"], "batch_mb": args.batch_mb},
            "clocks": clocks, "gpu_launches": launches, "roofline": roofline, "e2e": e2e,
            "stage_ms_per_step": {"parse": parse_ms / args.steps, "count": count_ms / args.steps}}
     if world == 1 and not args.no_cpu_baseline:

@@ -20,6 +20,19 @@
 #include "kg_parse.cuh"
 
 #define KG_MAX_W 8
+#define KG_DISPATCH_W(W_, fn, ...)                     \
+    switch (W_) {                                      \
+        case 1: fn<1>(__VA_ARGS__); break;             \
+        case 2: fn<2>(__VA_ARGS__); break;             \
+        case 3: fn<3>(__VA_ARGS__); break;             \
+        case 4: fn<4>(__VA_ARGS__); break;             \
+        case 5: fn<5>(__VA_ARGS__); break;             \
+        case 6: fn<6>(__VA_ARGS__); break;             \
+        case 7: fn<7>(__VA_ARGS__); break;             \
+        case 8: fn<8>(__VA_ARGS__); break;             \
+    }
+
+
 #define KG_DEFAULT_BATCH (128ull << 20)
 #define KG_MAX_BATCH (1ull << 30)
 
@@ -49,7 +62,7 @@ struct kg_ctx {
     KgStats* d_stats = nullptr;
     KgTable table{nullptr, 0, 0, 0, 1, 0};
     size_t table_bytes = 0;
-    KgBloom bloom{nullptr, 0, 0};
+    KgBloom bloom{nullptr, 0, 0, 1};
     size_t bloom_bytes = 0;
     uint64_t bloom_m = 0;
     int pass = 0;
@@ -72,8 +85,13 @@ struct kg_ctx {
     size_t out_chunk = 0;
     cudaEvent_t ev_out[2] = {nullptr, nullptr};
     // bucketed path (multi-GPU exchange, or partitions > 1 on one GPU)
-    bool bucketed = false;
-    u32 nb = 0;                         // buckets = world (multi-GPU) or partitions (single GPU)
+    bool bucketed = false;              // this context may bucket (streams/events exist)
+    bool pass_bucketed = false;         // the current pass buckets its batches
+    u32 nb = 0;                         // buckets of the current pass = world * local partitions
+    u32 pl = 1;                         // local partitions of the current pass
+    u32 nb_alloc = 0;                   // buckets the scratch below was sized for
+    u64 *d_seg[2] = {nullptr, nullptr}, *h_seg[2] = {nullptr, nullptr};   // segment tables (start[nseg+1], src[nseg])
+    u32 seg_cap = 0;
     ncclComm_t comm = nullptr;
     cudaStream_t s_comm = nullptr, s_insert = nullptr;
     u64* d_send[2] = {nullptr, nullptr};
@@ -233,6 +251,7 @@ static void free_all(kg_ctx* c) {
     }
     cudaFree(c->d_blk_hist); cudaFree(c->d_blk_base); cudaFree(c->d_bucket_counts); cudaFree(c->d_bucket_offs); cudaFree(c->d_matrix);
     if (c->h_matrix) cudaFreeHost(c->h_matrix);
+    for (int i = 0; i < 2; i++) { cudaFree(c->d_seg[i]); if (c->h_seg[i]) cudaFreeHost(c->h_seg[i]); }
     for (cudaEvent_t e : {c->ev_counts, c->ev_scatter, c->ev_matrix, c->ev_pass_ready, c->ev_tail}) if (e) cudaEventDestroy(e);
     if (c->s_comm) cudaStreamDestroy(c->s_comm);
     if (c->s_insert) cudaStreamDestroy(c->s_insert);
@@ -259,8 +278,7 @@ extern "C" int kg_create(const kg_config* cfg, kg_ctx** out) {
         if (cfg->expected_unique == 0 || !(cfg->fpr > 0.0 && cfg->fpr < 1.0)) { g_err = "bloom needs expected_unique > 0 and 0 < fpr < 1"; return KG_EBADARG; }
     } else if (cfg->min_slots == 0) { g_err = "min_slots must be > 0"; return KG_EBADARG; }
     if (cfg->world < 1 || cfg->rank < 0 || cfg->rank >= cfg->world) { g_err = "bad rank/world"; return KG_EBADARG; }
-    if (cfg->world > 64 || cfg->partitions > KG_MAX_BUCKETS) { g_err = "world must be <= 64 and partitions <= 1024"; return KG_EBADARG; }
-    if (cfg->world > 1 && cfg->partitions > 1) { g_err = "partitions > 1 is a single-GPU option"; return KG_EBADARG; }
+    if (cfg->world > 64 || (uint64_t)cfg->partitions * (uint64_t)cfg->world > KG_MAX_BUCKETS) { g_err = "world must be <= 64 and world * partitions <= 1024"; return KG_EBADARG; }
 
     int ndev = 0;
     cudaError_t e = cudaGetDeviceCount(&ndev);
@@ -329,12 +347,13 @@ extern "C" int kg_create(const kg_config* cfg, kg_ctx** out) {
         c->bloom_m = m;
         c->bloom.nblocks = nblocks;
         c->bloom.nh = nh;
+        c->bloom.world = (u32)cfg->world;
         c->bloom_bytes = nblocks * 64;
         KG_TRY(cudaMalloc(&c->bloom.bits, c->bloom_bytes));
     }
-    c->bucketed = cfg->world > 1 || (cfg->partitions > 1 && cfg->table_mode != KG_TABLE_KAARME);
+    // partitions: 0 = choose per pass from the table / filter size, 1 = never bucket on one GPU, > 1 = as given
+    c->bucketed = cfg->world > 1 || (cfg->partitions != 1 && cfg->table_mode != KG_TABLE_KAARME);
     if (c->bucketed) {
-        c->nb = cfg->world > 1 ? (u32)cfg->world : cfg->partitions;
         const size_t max_words = c->batch_bytes / 32 + c->carry_max_words + 2;
         c->max_blocks = (u32)((max_words + 31) / 32);   // smallest block of the hist/scatter pair covers 32 words
         c->send_cap = c->batch_bytes + 64;                       // a batch of n bytes holds < n k-mers
@@ -342,18 +361,10 @@ extern "C" int kg_create(const kg_config* cfg, kg_ctx** out) {
         KG_TRY(cudaStreamCreateWithFlags(&c->s_comm, cudaStreamNonBlocking));
         KG_TRY(cudaStreamCreateWithFlags(&c->s_insert, cudaStreamNonBlocking));
         for (int i = 0; i < 2; i++) {
-            KG_TRY(cudaMalloc(&c->d_send[i], c->send_cap * c->W * sizeof(u64)));
-            if (c->recv_cap) KG_TRY(cudaMalloc(&c->d_recv[i], c->recv_cap * c->W * sizeof(u64)));
             KG_TRY(cudaEventCreateWithFlags(&c->ev_send_free[i], cudaEventDisableTiming));
             KG_TRY(cudaEventCreateWithFlags(&c->ev_recv_free[i], cudaEventDisableTiming));
             KG_TRY(cudaEventCreateWithFlags(&c->ev_recv_full[i], cudaEventDisableTiming));
         }
-        KG_TRY(cudaMalloc(&c->d_blk_hist, sizeof(u32) * (size_t)c->max_blocks * c->nb));
-        KG_TRY(cudaMalloc(&c->d_blk_base, sizeof(u32) * (size_t)c->max_blocks * c->nb));
-        KG_TRY(cudaMalloc(&c->d_bucket_counts, sizeof(u32) * (c->nb + 1)));
-        KG_TRY(cudaMalloc(&c->d_bucket_offs, sizeof(u32) * (c->nb + 1)));
-        KG_TRY(cudaMalloc(&c->d_matrix, sizeof(u32) * (size_t)(c->nb + 1) * cfg->world));
-        KG_TRY(cudaHostAlloc((void**)&c->h_matrix, sizeof(u32) * (size_t)(c->nb + 1) * cfg->world, cudaHostAllocDefault));
         KG_TRY(cudaEventCreateWithFlags(&c->ev_counts, cudaEventDisableTiming));
         KG_TRY(cudaEventCreateWithFlags(&c->ev_scatter, cudaEventDisableTiming));
         KG_TRY(cudaEventCreateWithFlags(&c->ev_matrix, cudaEventDisableTiming));
@@ -408,6 +419,54 @@ extern "C" int kg_comm_init(kg_ctx* c, const void* id, int rank, int world) {
 }
 
 // -----------------------------------------------------------------------------------------------------------
+// Decide how the coming pass buckets its batches and size the scratch for it.  region_bytes = what the inserts
+// of this pass hit at random (count table, or the Bloom filter): local partitions are chosen so that one
+// partition's region is ~16-32 MiB, comfortably L2-resident next to the streaming keys.
+static int setup_pass_buckets(kg_ctx* c, size_t region_bytes) {
+    c->pass_bucketed = false;
+    c->pl = 1;
+    c->nb = (u32)c->cfg.world;
+    if (!c->bucketed) return KG_OK;
+    const u32 world = (u32)c->cfg.world;
+    u32 pl = c->cfg.partitions;
+    if (c->cfg.table_mode == KG_TABLE_KAARME) pl = 1;          // occurrence records do not travel with bare keys
+    else if (pl == 0) {
+        pl = 1;
+        if (region_bytes > (96u << 20)) while ((size_t)pl * (24u << 20) < region_bytes && pl * 2 * world <= KG_MAX_BUCKETS) pl *= 2;
+    }
+    if (pl * world > KG_MAX_BUCKETS) pl = KG_MAX_BUCKETS / world;
+    if (pl < 1) pl = 1;
+    c->pl = pl;
+    c->nb = world * pl;
+    c->pass_bucketed = world > 1 || pl > 1;
+    if (!c->pass_bucketed) return KG_OK;
+    for (int i = 0; i < 2; i++) {
+        if (!c->d_send[i] && (i == 0 || world > 1)) KG_CUDA(c, cudaMalloc(&c->d_send[i], c->send_cap * c->W * sizeof(u64)));
+        if (c->recv_cap && !c->d_recv[i]) KG_CUDA(c, cudaMalloc(&c->d_recv[i], c->recv_cap * c->W * sizeof(u64)));
+    }
+    if (c->nb > c->nb_alloc) {
+        cudaFree(c->d_blk_hist); cudaFree(c->d_blk_base); cudaFree(c->d_bucket_counts); cudaFree(c->d_bucket_offs); cudaFree(c->d_matrix);
+        if (c->h_matrix) cudaFreeHost(c->h_matrix);
+        c->d_blk_hist = c->d_blk_base = c->d_bucket_counts = c->d_bucket_offs = c->d_matrix = nullptr; c->h_matrix = nullptr;
+        KG_CUDA(c, cudaMalloc(&c->d_blk_hist, sizeof(u32) * (size_t)c->max_blocks * c->nb));
+        KG_CUDA(c, cudaMalloc(&c->d_blk_base, sizeof(u32) * (size_t)c->max_blocks * c->nb));
+        KG_CUDA(c, cudaMalloc(&c->d_bucket_counts, sizeof(u32) * (c->nb + 1)));
+        KG_CUDA(c, cudaMalloc(&c->d_bucket_offs, sizeof(u32) * (c->nb + 1)));
+        KG_CUDA(c, cudaMalloc(&c->d_matrix, sizeof(u32) * (size_t)(c->nb + 1) * world));
+        KG_CUDA(c, cudaHostAlloc((void**)&c->h_matrix, sizeof(u32) * (size_t)(c->nb + 1) * world, cudaHostAllocDefault));
+        c->nb_alloc = c->nb;
+    }
+    if (world > 1 && c->nb + 1 > c->seg_cap) {
+        for (int i = 0; i < 2; i++) {
+            cudaFree(c->d_seg[i]); if (c->h_seg[i]) cudaFreeHost(c->h_seg[i]);
+            KG_CUDA(c, cudaMalloc(&c->d_seg[i], sizeof(u64) * 2 * (c->nb + 2)));
+            KG_CUDA(c, cudaHostAlloc((void**)&c->h_seg[i], sizeof(u64) * 2 * (c->nb + 2), cudaHostAllocDefault));
+        }
+        c->seg_cap = c->nb + 1;
+    }
+    return KG_OK;
+}
+
 extern "C" int kg_pass_begin(kg_ctx* c, int pass) {
     if (!c || (pass != KG_PASS_BLOOM && pass != KG_PASS_COUNT)) return KG_EBADARG;
     if (pass == KG_PASS_BLOOM && !c->cfg.use_bloom) { c->err = "Bloom pass without use_bloom"; return KG_EBADARG; }
@@ -423,6 +482,7 @@ extern "C" int kg_pass_begin(kg_ctx* c, int pass) {
     if (pass == KG_PASS_BLOOM) {
         KG_CUDA(c, cudaMemsetAsync(c->bloom.bits, 0, c->bloom_bytes, c->s_compute));
         c->bloom_done = false;
+        { int rc = setup_pass_buckets(c, c->bloom_bytes); if (rc) return rc; }
     } else {
         if (c->compacted) {
             cudaFree(c->kaarme.slots); cudaFree(c->kaarme.roots);
@@ -435,6 +495,13 @@ extern "C" int kg_pass_begin(kg_ctx* c, int pass) {
         else want = (c->cfg.min_slots + (uint64_t)c->cfg.world - 1) / (uint64_t)c->cfg.world;
         uint64_t nslots = next_prime3mod4(want);                                 // parallel_parser.hpp:236
         u32 stride = kg_slot_stride_words((u32)c->W, c->cfg.table_mode == KG_TABLE_KAARME);
+        // packed 16-byte slots: two key words and >= 26 spare bits for the count (k = 33..51), plain table only;
+        // the count field stops at 2^(128-2k) - 2^17 (>= 66.9 M) instead of wrapping into the key
+        u32 packed_tb = 0;
+        if (c->W == 2 && c->cfg.table_mode == KG_TABLE_PLAIN && 2 * c->cfg.k - 64 <= 38 && !getenv("KG_NO_PACKED")) {
+            packed_tb = 2 * c->cfg.k - 64;
+            stride = 2;
+        }
         size_t bytes = (size_t)nslots * stride * sizeof(u64);
         if (!c->table.slots || bytes != c->table_bytes) {
             if (c->table.slots) { KG_CUDA(c, cudaFree(c->table.slots)); c->table.slots = nullptr; }
@@ -445,7 +512,9 @@ extern "C" int kg_pass_begin(kg_ctx* c, int pass) {
         c->table.stride = stride;
         c->table.kaarme = c->cfg.table_mode == KG_TABLE_KAARME;
         c->table.world = (u32)c->cfg.world;
+        c->table.packed_tb = packed_tb;
         KG_CUDA(c, cudaMemsetAsync(c->table.slots, 0, bytes, c->s_compute));
+        { int rc = setup_pass_buckets(c, bytes); if (rc) return rc; }
     }
     if (c->cfg.world > 1) {   // inserts run on their own stream: order them after the clears above
         KG_CUDA(c, cudaEventRecord(c->ev_pass_ready, c->s_compute));
@@ -567,13 +636,30 @@ static void bucket_kernel(kg_ctx* c, const KgBucketArgs& a, u32 grid, bool scatt
     }
 }
 
+template <int W>
+static void launch_insert_segs(kg_ctx* c, cudaStream_t s, const u64* keys, const u64* seg, u32 nseg, u64 n, int sink) {
+    const u64 grid = (n + KG_KEYS_PER_BLOCK - 1) / KG_KEYS_PER_BLOCK;
+    if (grid == 0) return;
+    const u64* start = seg;
+    const u64* src = seg + (nseg + 1);
+    switch (sink) {
+        case KG_SINK_TABLE: kg_insert_segs_kernel<W, KG_SINK_TABLE><<<(u32)grid, 256, 0, s>>>(keys, start, src, nseg, c->table, c->bloom, c->d_stats); break;
+        case KG_SINK_BLOOM1: kg_insert_segs_kernel<W, KG_SINK_BLOOM1><<<(u32)grid, 256, 0, s>>>(keys, start, src, nseg, c->table, c->bloom, c->d_stats); break;
+        case KG_SINK_BLOOM2: kg_insert_segs_kernel<W, KG_SINK_BLOOM2><<<(u32)grid, 256, 0, s>>>(keys, start, src, nseg, c->table, c->bloom, c->d_stats); break;
+        default: break;
+    }
+    c->launches++;
+}
+
 // One exchange round (collective when world > 1).  have_batch: this rank's send buffer (round & 1) was just
 // filled by bucket_batch; otherwise the rank contributes nothing and reports "done".  Returns via *all_done
 // whether every rank reported done in this round.
-//   s_comm:   all-gather of the per-destination counts -> host; grouped ncclSend/ncclRecv of the key slices
-//   s_insert: insert kernel over what arrived, overlapping the next batch's parse + bucketing on s_compute
+//   buckets are owner-major: owner d holds buckets [d*pl, (d+1)*pl) = its local partitions, in table order
+//   s_comm:   all-gather of the per-bucket counts -> host; grouped ncclSend/ncclRecv of the key slices
+//   s_insert: insert kernel over what arrived (partition-major across senders through a segment table),
+//             overlapping the next batch's parse + bucketing on s_compute
 static int exchange_round(kg_ctx* c, bool have_batch, bool* all_done) {
-    const u32 nb = c->nb, world = (u32)c->cfg.world, rank = (u32)c->cfg.rank;
+    const u32 nb = c->nb, pl = c->pl, world = (u32)c->cfg.world, rank = (u32)c->cfg.rank;
     const int sb = (int)(c->round & 1);
     const size_t row = nb + 1;
     if (!have_batch) {
@@ -586,13 +672,14 @@ static int exchange_round(kg_ctx* c, bool have_batch, bool* all_done) {
     KG_CUDA(c, cudaMemcpyAsync(c->h_matrix, c->d_matrix, sizeof(u32) * row * world, cudaMemcpyDeviceToHost, c->s_comm));
     KG_CUDA(c, cudaEventRecord(c->ev_matrix, c->s_comm));
     KG_CUDA(c, cudaEventSynchronize(c->ev_matrix));
-    const u32* M = c->h_matrix;   // M[r*row + d] = keys rank r holds for destination d; M[r*row + nb] = done flag
+    const u32* M = c->h_matrix;   // M[r*row + b] = keys rank r holds for bucket b; M[r*row + nb] = done flag
+    auto to_owner = [&](u32 r, u32 d) { u64 t = 0; for (u32 p = 0; p < pl; p++) t += M[r * row + d * pl + p]; return t; };
     bool done = true;
     u64 max_in = 0, any = 0;
     for (u32 r = 0; r < world; r++) done = done && M[r * row + nb] != 0;
     for (u32 d = 0; d < world; d++) {
         u64 in = 0;
-        for (u32 r = 0; r < world; r++) in += M[r * row + d];
+        for (u32 r = 0; r < world; r++) in += to_owner(r, d);
         if (in > max_in) max_in = in;
         any += in;
     }
@@ -601,30 +688,65 @@ static int exchange_round(kg_ctx* c, bool have_batch, bool* all_done) {
         // sub-rounds so that no rank receives more than recv_cap keys at once (identical on every rank)
         const u64 S = (max_in + c->recv_cap - 1) / c->recv_cap;
         std::vector<u64> send_off(world + 1, 0);
-        for (u32 d = 0; d < world; d++) send_off[d + 1] = send_off[d] + M[rank * row + d];
+        for (u32 d = 0; d < world; d++) send_off[d + 1] = send_off[d] + to_owner(rank, d);
         if (have_batch) KG_CUDA(c, cudaStreamWaitEvent(c->s_comm, c->ev_scatter, 0));
         for (u64 sr = 0; sr < S; sr++) {
             const int rb = (int)(c->subround & 1);
             KG_CUDA(c, cudaStreamWaitEvent(c->s_comm, c->ev_recv_free[rb], 0));
-            u64 recv_pos = 0;
+            if (sr >= 2) KG_CUDA(c, cudaEventSynchronize(c->ev_recv_full[rb]));   // h_seg[rb] was uploaded
+            std::vector<u64> recv_off(world + 1, 0), rlo_of(world), rhi_of(world);
             KG_NCCL(c, kg_nccl().GroupStart());
             for (u32 peer = 0; peer < world; peer++) {
-                const u64 ns = M[rank * row + peer], lo = ns * sr / S, hi = ns * (sr + 1) / S;       // my slice for peer
-                const u64 nr = M[peer * row + rank], rlo = nr * sr / S, rhi = nr * (sr + 1) / S;    // peer's slice for me
+                const u64 ns = to_owner(rank, peer), lo = ns * sr / S, hi = ns * (sr + 1) / S;      // my slice for peer
+                const u64 nr = to_owner(peer, rank), rlo = nr * sr / S, rhi = nr * (sr + 1) / S;    // peer's slice for me
                 const u64* src = c->d_send[sb] + (send_off[peer] + lo) * c->W;
-                u64* dst = c->d_recv[rb] + recv_pos * c->W;
+                u64* dst = c->d_recv[rb] + recv_off[peer] * c->W;
                 if (peer == rank) {
                     if (hi > lo) KG_CUDA(c, cudaMemcpyAsync(dst, src, (hi - lo) * c->W * sizeof(u64), cudaMemcpyDeviceToDevice, c->s_comm));
                 } else {
                     if (hi > lo) KG_NCCL(c, kg_nccl().Send(src, (hi - lo) * c->W, ncclUint64, (int)peer, c->comm, c->s_comm));
                     if (rhi > rlo) KG_NCCL(c, kg_nccl().Recv(dst, (rhi - rlo) * c->W, ncclUint64, (int)peer, c->comm, c->s_comm));
                 }
-                recv_pos += rhi - rlo;
+                rlo_of[peer] = rlo; rhi_of[peer] = rhi;
+                recv_off[peer + 1] = recv_off[peer] + (rhi - rlo);
             }
             KG_NCCL(c, kg_nccl().GroupEnd());
+            const u64 n_recv = recv_off[world];
+            // segment table, partition-major across senders: sender s delivered keys [rlo, rhi) of its run for me,
+            // which is its partitions 0..pl-1 back to back
+            u32 nseg = 0;
+            u64* hs = c->h_seg[rb];
+            const u32 maxseg = c->nb;                      // world * pl segments at most
+            u64* h_start = hs;
+            u64* h_src = hs + (maxseg + 1);
+            u64 acc = 0;
+            for (u32 p = 0; p < pl; p++) {
+                for (u32 sdr = 0; sdr < world; sdr++) {
+                    u64 pbeg = 0;                           // start of partition p inside sender sdr's run for me
+                    for (u32 q = 0; q < p; q++) pbeg += M[sdr * row + rank * pl + q];
+                    const u64 pend = pbeg + M[sdr * row + rank * pl + p];
+                    const u64 a0 = pbeg > rlo_of[sdr] ? pbeg : rlo_of[sdr];
+                    const u64 a1 = pend < rhi_of[sdr] ? pend : rhi_of[sdr];
+                    if (a1 > a0) {
+                        h_start[nseg] = acc;
+                        h_src[nseg] = recv_off[sdr] + (a0 - rlo_of[sdr]);
+                        acc += a1 - a0;
+                        nseg++;
+                    }
+                }
+            }
+            h_start[nseg] = acc;
+            if (n_recv) {
+                // device layout: start[0..nseg], then src[0..nseg-1]
+                KG_CUDA(c, cudaMemcpyAsync(c->d_seg[rb], h_start, sizeof(u64) * (nseg + 1), cudaMemcpyHostToDevice, c->s_comm));
+                KG_CUDA(c, cudaMemcpyAsync(c->d_seg[rb] + (nseg + 1), h_src, sizeof(u64) * nseg, cudaMemcpyHostToDevice, c->s_comm));
+            }
             KG_CUDA(c, cudaEventRecord(c->ev_recv_full[rb], c->s_comm));
             KG_CUDA(c, cudaStreamWaitEvent(c->s_insert, c->ev_recv_full[rb], 0));
-            if (recv_pos) insert_keys(c, c->s_insert, c->d_recv[rb], recv_pos, nullptr);
+            if (n_recv) {
+                const int sink = current_sink(c);
+                KG_DISPATCH_W(c->W, launch_insert_segs, c, c->s_insert, c->d_recv[rb], c->d_seg[rb], nseg, n_recv, sink);
+            }
             KG_CUDA(c, cudaEventRecord(c->ev_recv_free[rb], c->s_insert));
             c->subround++;
         }
@@ -694,7 +816,7 @@ static int process_batch(kg_ctx* c, const uint8_t* d_in, size_t n, uint32_t flag
     if (e1) cudaEventRecord(e1, s);
     if (!(flags & KG_FEED_CONTEXT)) {
         const u32 nthreads = (u32)(n / 32 + c->carry_max_words + 2);   // upper bound on packed words
-        if (c->bucketed) {
+        if (c->pass_bucketed) {
             int rc = bucket_batch(c, nthreads);
             if (rc) return rc;
         } else {
@@ -824,6 +946,7 @@ extern "C" int kg_pass_end(kg_ctx* c, kg_pass_stats* out) {
         out->new_in_second = st.new_in_second;
         out->bloom_bits = c->bloom_m;
         out->bloom_hashes = c->bloom.nh;
+        out->partitions = c->pass_bucketed ? c->pl : 1;
         out->raw_bytes = c->raw_bytes_pass;
         float ms = 0;
         cudaEventElapsedTime(&ms, c->ev_pass_begin, c->ev_pass_end);
@@ -855,18 +978,6 @@ static void launch_kaarme_chain(kg_ctx* c) {
     if (grid) kg_kaarme_chain_stats<W><<<grid, 256, 0, c->s_compute>>>(c->kaarme, c->cfg.k, c->d_cstats);
     c->launches++;
 }
-#define KG_DISPATCH_W(W_, fn, ...)                     \
-    switch (W_) {                                      \
-        case 1: fn<1>(__VA_ARGS__); break;             \
-        case 2: fn<2>(__VA_ARGS__); break;             \
-        case 3: fn<3>(__VA_ARGS__); break;             \
-        case 4: fn<4>(__VA_ARGS__); break;             \
-        case 5: fn<5>(__VA_ARGS__); break;             \
-        case 6: fn<6>(__VA_ARGS__); break;             \
-        case 7: fn<7>(__VA_ARGS__); break;             \
-        case 8: fn<8>(__VA_ARGS__); break;             \
-    }
-
 extern "C" int kg_compact(kg_ctx* c, kg_compact_stats* stats) {
     if (!c) return KG_EBADARG;
     if (c->cfg.table_mode != KG_TABLE_KAARME) { c->err = "kg_compact needs table_mode KG_TABLE_KAARME"; return KG_EBADARG; }

@@ -26,6 +26,7 @@ struct KgBloom {
     u32* bits;     // nblocks * 16 words
     u64 nblocks;
     u32 nh;        // ceil(h) (main.cpp:417)
+    u32 world;     // shards (the block index uses the in-shard part of the hash)
 };
 
 // the nh bit positions of a k-mer inside its 256-bit block, as 8 x 32-bit masks
@@ -41,15 +42,17 @@ __device__ __forceinline__ void kg_bloom_masks(u64 h, u32 nh, u32 (&mask)[8]) {
         for (int w = 0; w < 8; w++) if ((b >> 5) == (u32)w) mask[w] |= 1u << (b & 31u);
     }
 }
-__device__ __forceinline__ u64 kg_bloom_block(u64 h, u64 nblocks) {
-    return __umul64hi(kg_fmix64(h + 0x632BE59BD9B4E019ULL), nblocks);
+// block index = range partition of the in-shard hash (like the table slot), so a bucket of the partitioned path
+// touches one contiguous region of the filter; the bit positions inside the block come from an independent mix
+__device__ __forceinline__ u64 kg_bloom_block(u64 h, u64 nblocks, u32 world) {
+    return __umul64hi(kg_local_hash(h, world), nblocks);
 }
 
 // pass 1 (insertion_process, double_bloomfilter.hpp:371-413) on the blocked layout.
 __device__ __forceinline__ void kg_bloom_insert(const KgBloom& bf, u64 h, u32& new1, u32& new2) {
     u32 mask[8];
     kg_bloom_masks(h, bf.nh, mask);
-    u32* blk = bf.bits + kg_bloom_block(h, bf.nblocks) * 16;
+    u32* blk = bf.bits + kg_bloom_block(h, bf.nblocks, bf.world) * 16;
     // F2 first: "in second? done"
     bool in2 = true;
     u32 miss2[8];
@@ -101,7 +104,7 @@ __device__ __forceinline__ void kg_bloom_insert(const KgBloom& bf, u64 h, u32& n
 __device__ __forceinline__ bool kg_bloom_admits(const KgBloom& bf, u64 h) {
     u32 mask[8];
     kg_bloom_masks(h, bf.nh, mask);
-    const u32* blk = bf.bits + kg_bloom_block(h, bf.nblocks) * 16 + 8;
+    const u32* blk = bf.bits + kg_bloom_block(h, bf.nblocks, bf.world) * 16 + 8;
     uint4 a = __ldg(reinterpret_cast<const uint4*>(blk));
     uint4 b = __ldg(reinterpret_cast<const uint4*>(blk + 4));
     u32 cur[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
@@ -225,7 +228,9 @@ struct KgConsume {
         }
         if (SINK == KG_SINK_BLOOM2 && !kg_bloom_admits(bloom, h)) { n_rej++; return; }
         bool is_new;
-        u64 slot = kg_table_add<W>(table, key, h, is_new);
+        u64 slot;
+        if constexpr (W == 2) slot = table.packed_tb ? kg_table_add_packed(table, key, h, is_new) : kg_table_add<W>(table, key, h, is_new);
+        else slot = kg_table_add<W>(table, key, h, is_new);
         if (slot == ~0ULL) { full = true; return; }
         n_ins++;
         n_new += is_new ? 1u : 0u;
@@ -293,8 +298,58 @@ __global__ void __launch_bounds__(256) kg_insert_keys_kernel(const u64* __restri
             const u64 i = base + (u64)j * 256u + threadIdx.x;
             if (i < n) {
                 u64 key[W];
+                if constexpr (W % 2 == 0) {                                        // streamed once: evict-first, 16 B loads
 #pragma unroll
-                for (int q = 0; q < W; q++) key[q] = __ldcs(keys + i * W + q);   // streamed once: evict-first
+                    for (int q = 0; q < W; q += 2) {
+                        const ulonglong2 v = __ldcs(reinterpret_cast<const ulonglong2*>(keys + i * W + q));
+                        key[q] = v.x; key[q + 1] = v.y;
+                    }
+                } else {
+#pragma unroll
+                    for (int q = 0; q < W; q++) key[q] = __ldcs(keys + i * W + q);
+                }
+                KgOcc none; none.word = ~0ULL;
+                sink(key, kg_hash_key<W>(key), none);
+            }
+        }
+    }
+    if (SINK == KG_SINK_TABLE || SINK == KG_SINK_BLOOM2) {
+        kg_block_add(sink.n_ins, &stats->inserted, sm);
+        kg_block_add(sink.n_new, &stats->distinct, sm);
+    }
+    if (SINK == KG_SINK_BLOOM1) {
+        kg_block_add(sink.n_b1, &stats->new_in_first, sm);
+        kg_block_add(sink.n_b2, &stats->new_in_second, sm);
+    }
+    if (SINK == KG_SINK_BLOOM2) kg_block_add(sink.n_rej, &stats->bloom_rejected, sm);
+    if (sink.full) stats->table_full = 1;
+}
+
+// Same, but the keys are gathered through a segment table: logical key i lives at
+// keys[seg_src[j] + (i - seg_start[j])] for the segment j with seg_start[j] <= i < seg_start[j+1].
+// The receiver of an exchange orders the segments partition-major across senders, so that one launch still
+// walks the table region by region although every sender delivered its own partition-sorted run.
+template <int W, int SINK>
+__global__ void __launch_bounds__(256) kg_insert_segs_kernel(const u64* __restrict__ keys, const u64* __restrict__ seg_start,
+                                                             const u64* __restrict__ seg_src, u32 nseg,
+                                                             KgTable table, KgBloom bloom, KgStats* stats) {
+    __shared__ u32 sm[8];
+    const u64 n = seg_start[nseg];
+    const u64 base = (u64)blockIdx.x * KG_KEYS_PER_BLOCK;
+    KgConsume<W, SINK> sink;
+    sink.table = table;
+    sink.bloom = bloom;
+    if (base < n) {
+#pragma unroll 1
+        for (int j = 0; j < KG_KEYS_PER_THREAD; j++) {
+            const u64 i = base + (u64)j * 256u + threadIdx.x;
+            if (i < n) {
+                u32 lo = 0, hi = nseg;                       // last segment with seg_start <= i
+                while (hi - lo > 1) { const u32 mid = (lo + hi) >> 1; if (seg_start[mid] <= i) lo = mid; else hi = mid; }
+                const u64 src = seg_src[lo] + (i - seg_start[lo]);
+                u64 key[W];
+#pragma unroll
+                for (int q = 0; q < W; q++) key[q] = __ldcs(keys + src * W + q);
                 KgOcc none; none.word = ~0ULL;
                 sink(key, kg_hash_key<W>(key), none);
             }
@@ -334,8 +389,12 @@ struct KgBucketArgs {
     u32 dbg;            // experiments: 1 = skip the global stores, 2 = skip the shared atomics
 };
 
+// bucket = floor(h * nb / 2^64) with nb = world * local_partitions: the high part is the owner shard
+// (floor(h*world/2^64)), the low part the partition of the in-shard hash -- buckets are owner-major, and the
+// buckets of one owner map to consecutive, contiguous regions of that owner's table.
 __device__ __forceinline__ u32 kg_bucket_of(u64 h, u32 world, u32 nb) {
-    return world > 1 ? kg_owner(h, world) : (u32)__umul64hi(h, (u64)nb);
+    (void)world;
+    return (u32)__umul64hi(h, (u64)nb);
 }
 
 template <int W>
@@ -499,9 +558,17 @@ __global__ void __launch_bounds__(256) kg_export_kernel(KgTable table, u64 slot_
     bool emit = false;
     u32 rep = 0;
     const u64* p = nullptr;
+    u64 pk0 = 0, pk1 = 0;
     if (s < slot_end) {
         p = table.slots + s * table.stride;
-        u32 n = (u32)p[0];
+        u32 n;
+        if (W == 2 && table.packed_tb) {
+            pk0 = p[0] & ((1ULL << table.packed_tb) - 1);
+            pk1 = p[1];
+            n = (u32)(p[0] >> table.packed_tb);
+        } else {
+            n = (u32)p[0];
+        }
         if (n != 0 && n != KG_LOCKED) {
             rep = kg_reported_count(n, count_mode, table_mode);
             emit = min_abundance > 0 && (u64)rep >= min_abundance;
@@ -515,8 +582,13 @@ __global__ void __launch_bounds__(256) kg_export_kernel(KgTable table, u64 slot_
     base = __shfl_sync(0xffffffffu, base, 0);
     if (emit) {
         const u32 idx = base + __popc(ballot & ((1u << lane) - 1u));
+        if (W == 2 && table.packed_tb) {
+            out_keys[(u64)idx * 2] = pk0;
+            out_keys[(u64)idx * 2 + 1] = pk1;
+        } else {
 #pragma unroll
-        for (int i = 0; i < W; i++) out_keys[(u64)idx * W + i] = p[1 + i];
+            for (int i = 0; i < W; i++) out_keys[(u64)idx * W + i] = p[1 + i];
+        }
         out_counts[idx] = rep;
     }
 }

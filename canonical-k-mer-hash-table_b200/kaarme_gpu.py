@@ -44,12 +44,12 @@ class Config(C.Structure):
 class PassStats(C.Structure):
     _fields_ = [("input_kmers", C.c_uint64), ("inserted_kmers", C.c_uint64), ("distinct", C.c_uint64),
                 ("table_slots", C.c_uint64), ("new_in_first", C.c_uint64), ("new_in_second", C.c_uint64),
-                ("bloom_bits", C.c_uint64), ("bloom_hashes", C.c_uint32), ("reserved", C.c_uint32),
+                ("bloom_bits", C.c_uint64), ("bloom_hashes", C.c_uint32), ("partitions", C.c_uint32),
                 ("raw_bytes", C.c_uint64), ("bases", C.c_uint64), ("device_ms", C.c_double),
                 ("parse_ms", C.c_double), ("count_ms", C.c_double), ("exchange_ms", C.c_double)]
 
     def as_dict(self):
-        return {f: getattr(self, f) for f, _ in self._fields_ if f != "reserved"}
+        return {f: getattr(self, f) for f, _ in self._fields_}
 
 
 class CompactStats(C.Structure):

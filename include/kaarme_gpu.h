@@ -80,8 +80,10 @@ typedef struct kg_config {
     uint64_t batch_bytes;     /* raw bytes per device batch; 0 = default (128 MiB)                  */
     int32_t rank;             /* hash-sharded multi-GPU: this context's shard                       */
     int32_t world;            /* number of shards (1 = single GPU)                                  */
-    uint32_t partitions;      /* single GPU: > 1 buckets every batch by hash into this many table regions
-                                 before inserting (L2-blocked insert); 0/1 = insert directly              */
+    uint32_t partitions;      /* L2-blocked insert: every batch is bucketed by hash into this many contiguous
+                                 regions of the shard's table / filter before inserting.  0 = choose per pass
+                                 (~24 MiB regions; direct insert when the structure is small), 1 = always
+                                 insert directly, > 1 = as given (world * partitions <= 1024)              */
     uint32_t reserved;
 } kg_config;
 
@@ -94,7 +96,7 @@ typedef struct kg_pass_stats {
     uint64_t new_in_second;
     uint64_t bloom_bits;     /* m, bits per filter (main.cpp:404-410)                               */
     uint32_t bloom_hashes;   /* ceil(h)  (main.cpp:417)                                            */
-    uint32_t reserved;
+    uint32_t partitions;     /* local table/filter regions the pass bucketed its batches into (1 = direct)  */
     uint64_t raw_bytes;      /* bytes fed in the pass                                               */
     uint64_t bases;          /* valid bases packed                                                  */
     double device_ms;        /* CUDA-event time, first kernel of the pass to the last               */

@@ -27,7 +27,8 @@ def main():
     torch.cuda.set_device(local)
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     failures = 0
-    for k, use_bloom, uneven in ((51, False, False), (31, False, True), (127, False, False), (51, True, False)):
+    for k, use_bloom, uneven, npart in ((51, False, False, 1), (31, False, True, 4), (127, False, False, 16), (51, True, False, 8),
+                                       (51, False, True, 0), (21, True, True, 32)):
         rng = np.random.default_rng(1234 + k)
         data = make_fasta(rng, 200000, 600, 2000, wrap=80, err=0.01, n_rate=0.0003)
         truth = oracle.count(data, k)
@@ -40,7 +41,7 @@ def main():
         lo, hi = cuts[rank], cuts[rank + 1]
         ctx_lo, in_hdr = K.slice_context(data, lo, k)
         c = kg.Counter(k=k, min_slots=2_000_000, use_bloom=use_bloom, expected_unique=truth.n, fpr=0.01, device=local,
-                       rank=rank, world=world, batch_bytes=1 << 20)
+                       rank=rank, world=world, batch_bytes=1 << 20, partitions=npart)
         uid = [kg.comm_unique_id() if rank == 0 else None]
         dist.broadcast_object_list(uid, src=0)
         c.comm_init(uid[0], rank, world)
@@ -64,7 +65,7 @@ def main():
                   and sum(p[2] for p in parts) == truth.total_windows)
             if not use_bloom:
                 ok = ok and sum(p[3] for p in parts) == truth.total_windows
-            print(f"multigpu k={k} bloom={use_bloom} uneven={uneven} world={world}: {'OK' if ok else 'MISMATCH'} "
+            print(f"multigpu k={k} bloom={use_bloom} uneven={uneven} partitions={npart} world={world}: {'OK' if ok else 'MISMATCH'} "
                   f"(distinct {len(allc)} vs {want.n}; input {sum(p[2] for p in parts)} vs {truth.total_windows}; "
                   f"per-shard {[len(p[1]) for p in parts]})", flush=True)
             failures += 0 if ok else 1
