@@ -73,6 +73,9 @@ struct kg_ctx {
     cudaEvent_t ev_pass_begin = nullptr, ev_pass_end = nullptr;
     std::vector<cudaEvent_t> ev_pool;   // [parse_begin, parse_end(=count_begin), count_end] per batch
     size_t ev_used = 0;
+    std::vector<cudaEvent_t> ins_pool;  // [insert_begin, insert_end] pairs around the insert kernels of the pass
+    size_t ins_used = 0;
+    uint64_t ins_launches = 0, ins_keys_upper = 0;
     uint64_t raw_bytes_pass = 0, bases_pass = 0;
     uint64_t launches = 0;
     // export staging
@@ -260,6 +263,7 @@ static void free_all(kg_ctx* c) {
     cudaFree(c->d_words); cudaFree(c->d_brk); cudaFree(c->d_carry_words); cudaFree(c->d_carry_brk);
     cudaFree(c->d_stream); cudaFree(c->d_stats); cudaFree(c->table.slots); cudaFree(c->bloom.bits);
     for (auto e : c->ev_pool) cudaEventDestroy(e);
+    for (auto e : c->ins_pool) cudaEventDestroy(e);
     if (c->ev_pass_begin) cudaEventDestroy(c->ev_pass_begin);
     if (c->ev_pass_end) cudaEventDestroy(c->ev_pass_end);
     if (c->s_compute) cudaStreamDestroy(c->s_compute);
@@ -476,6 +480,8 @@ extern "C" int kg_pass_begin(kg_ctx* c, int pass) {
     c->pass = pass;
     c->stream_open = false;
     c->ev_used = 0;
+    c->ins_used = 0;
+    c->ins_launches = 0;
     c->raw_bytes_pass = 0;
     KG_CUDA(c, cudaEventRecord(c->ev_pass_begin, c->s_compute));
     KG_CUDA(c, cudaMemsetAsync(c->d_stats, 0, sizeof(KgStats), c->s_compute));
@@ -537,6 +543,15 @@ extern "C" int kg_stream_begin(kg_ctx* c, int starts_in_header) {
     return KG_OK;
 }
 
+static cudaEvent_t next_ins_event(kg_ctx* c) {
+    if (c->ins_used == c->ins_pool.size()) {
+        cudaEvent_t e;
+        if (cudaEventCreate(&e) != cudaSuccess) return nullptr;
+        c->ins_pool.push_back(e);
+    }
+    return c->ins_pool[c->ins_used++];
+}
+
 static cudaEvent_t next_event(kg_ctx* c) {
     if (c->ev_used == c->ev_pool.size()) {
         cudaEvent_t e;
@@ -580,6 +595,9 @@ static void launch_insert_keys(kg_ctx* c, cudaStream_t s, const u64* keys, u64 n
 
 static void insert_keys(kg_ctx* c, cudaStream_t s, const u64* keys, u64 n_upper, const u32* n_dev) {
     const int sink = current_sink(c);
+    cudaEvent_t ia = next_ins_event(c), ib = next_ins_event(c);
+    if (ia) cudaEventRecord(ia, s);
+    c->ins_launches++;
     switch (c->W) {
         case 1: launch_insert_keys<1>(c, s, keys, n_upper, n_dev, sink); break;
         case 2: launch_insert_keys<2>(c, s, keys, n_upper, n_dev, sink); break;
@@ -590,6 +608,7 @@ static void insert_keys(kg_ctx* c, cudaStream_t s, const u64* keys, u64 n_upper,
         case 7: launch_insert_keys<7>(c, s, keys, n_upper, n_dev, sink); break;
         case 8: launch_insert_keys<8>(c, s, keys, n_upper, n_dev, sink); break;
     }
+    if (ib) cudaEventRecord(ib, s);
 }
 
 template <int W>
@@ -745,7 +764,11 @@ static int exchange_round(kg_ctx* c, bool have_batch, bool* all_done) {
             KG_CUDA(c, cudaStreamWaitEvent(c->s_insert, c->ev_recv_full[rb], 0));
             if (n_recv) {
                 const int sink = current_sink(c);
+                cudaEvent_t ia = next_ins_event(c), ib = next_ins_event(c);
+                if (ia) cudaEventRecord(ia, c->s_insert);
+                c->ins_launches++;
                 KG_DISPATCH_W(c->W, launch_insert_segs, c, c->s_insert, c->d_recv[rb], c->d_seg[rb], nseg, n_recv, sink);
+                if (ib) cudaEventRecord(ib, c->s_insert);
             }
             KG_CUDA(c, cudaEventRecord(c->ev_recv_free[rb], c->s_insert));
             c->subround++;
@@ -825,6 +848,9 @@ static int process_batch(kg_ctx* c, const uint8_t* d_in, size_t n, uint32_t flag
             a.table = c->table; a.bloom = c->bloom;
             a.stats = c->d_stats; a.k = c->cfg.k; a.rank = (u32)c->cfg.rank; a.world = (u32)c->cfg.world;
             const int sink = current_sink(c);
+            cudaEvent_t ia = next_ins_event(c), ib = next_ins_event(c);
+            if (ia) cudaEventRecord(ia, s);
+            c->ins_launches++;
             switch (c->W) {
                 case 1: launch_count<1>(c, a, nthreads, sink); break;
                 case 2: launch_count<2>(c, a, nthreads, sink); break;
@@ -835,6 +861,7 @@ static int process_batch(kg_ctx* c, const uint8_t* d_in, size_t n, uint32_t flag
                 case 7: launch_count<7>(c, a, nthreads, sink); break;
                 case 8: launch_count<8>(c, a, nthreads, sink); break;
             }
+            if (ib) cudaEventRecord(ib, s);
         }
     }
     kg_carry_save<<<1, 32, 0, s>>>(c->d_words, c->d_brk, c->d_stream, c->d_carry_words, c->d_carry_brk, c->cfg.k, c->carry_max_words);
@@ -956,6 +983,11 @@ extern "C" int kg_pass_end(kg_ctx* c, kg_pass_stats* out) {
             if (cudaEventElapsedTime(&a, c->ev_pool[i], c->ev_pool[i + 1]) == cudaSuccess) out->parse_ms += a;
             if (cudaEventElapsedTime(&b, c->ev_pool[i + 1], c->ev_pool[i + 2]) == cudaSuccess) out->count_ms += b;
         }
+        for (size_t i = 0; i + 2 <= c->ins_used; i += 2) {
+            float a = 0;
+            if (cudaEventElapsedTime(&a, c->ins_pool[i], c->ins_pool[i + 1]) == cudaSuccess) out->insert_ms += a;
+        }
+        out->insert_launches = c->ins_launches;
         cudaGetLastError();
     }
     const int pass = c->pass;

@@ -46,7 +46,8 @@ class PassStats(C.Structure):
                 ("table_slots", C.c_uint64), ("new_in_first", C.c_uint64), ("new_in_second", C.c_uint64),
                 ("bloom_bits", C.c_uint64), ("bloom_hashes", C.c_uint32), ("partitions", C.c_uint32),
                 ("raw_bytes", C.c_uint64), ("bases", C.c_uint64), ("device_ms", C.c_double),
-                ("parse_ms", C.c_double), ("count_ms", C.c_double), ("exchange_ms", C.c_double)]
+                ("parse_ms", C.c_double), ("count_ms", C.c_double), ("exchange_ms", C.c_double),
+                ("insert_ms", C.c_double), ("insert_launches", C.c_uint64)]
 
     def as_dict(self):
         return {f: getattr(self, f) for f, _ in self._fields_}

@@ -101,6 +101,10 @@ typedef struct kg_pass_stats {
     uint64_t bases;          /* valid bases packed                                                  */
     double device_ms;        /* CUDA-event time, first kernel of the pass to the last               */
     double parse_ms, count_ms, exchange_ms; /* per-stage CUDA-event sums (0 when not measured)      */
+    double insert_ms;        /* CUDA-event time of the table/filter-updating kernel alone (kg_count_kernel on
+                                the direct path, kg_insert_keys/segs_kernel on the bucketed path), summed over
+                                its launches; count_ms additionally holds the bucketing kernels         */
+    uint64_t insert_launches;/* launches of that kernel in the pass                                         */
 } kg_pass_stats;
 
 typedef struct kg_compact_stats {
