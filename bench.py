@@ -48,6 +48,8 @@ def parse_args():
     p.add_argument("--partitions", type=int, default=int(os.environ.get("KAARME_PARTITIONS", "0")),
                    help="table regions each batch is bucketed into before inserting (0 = library default, 1 = direct insert)")
     p.add_argument("--batch-mb", type=int, default=int(os.environ.get("KAARME_BATCH_MB", "256")))
+    p.add_argument("--bloom", action="store_true", help="two-pass double-Bloom-filter mode (-b -u <genome size>)")
+    p.add_argument("--fpr", type=float, default=0.01)
     p.add_argument("--no-cpu-baseline", action="store_true")
     p.add_argument("--no-e2e", action="store_true")
     return p.parse_args()
@@ -179,6 +181,7 @@ def main():
     torch.cuda.synchronize()
     total_slots = meta["slots"] * world
     ctr = kg.Counter(k=k, table_mode=KG.TABLE_PLAIN, input_mode=KG.INPUT_FASTA, min_slots=total_slots,
+                     use_bloom=args.bloom, expected_unique=meta["G"] if args.bloom else 0, fpr=args.fpr,
                      device=local_rank, rank=rank, world=world, batch_bytes=args.batch_mb << 20,
                      partitions=args.partitions)
     if world > 1:
@@ -191,11 +194,29 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    def step_device():
-        ctr.pass_begin(KG.PASS_COUNT)
+    bloom_info = {}
+
+    def one_pass(which, feed):
+        ctr.pass_begin(which)
         ctr.stream_begin(False)
-        ctr.feed_device(fasta.data_ptr(), fasta.numel())
+        feed()
         return ctr.pass_end()
+
+    def step(feed):
+        """one step = the whole job: (Bloom pass +) count pass; device_ms etc. are summed over the passes"""
+        if not args.bloom:
+            return one_pass(KG.PASS_COUNT, feed)
+        b = one_pass(KG.PASS_BLOOM, feed)
+        st = one_pass(KG.PASS_COUNT, feed)
+        bloom_info.update(new_in_first=b["new_in_first"], new_in_second=b["new_in_second"], bloom_bits=b["bloom_bits"],
+                          bloom_hashes=b["bloom_hashes"], bloom_pass_ms=b["device_ms"], count_pass_ms=st["device_ms"],
+                          bloom_partitions=b["partitions"], table_slots=st["table_slots"])
+        for key in ("device_ms", "count_ms", "parse_ms"):
+            st[key] += b[key]
+        return st
+
+    def step_device():
+        return step(lambda: ctr.feed_device(fasta.data_ptr(), fasta.numel()))
 
     # ---- device-resident metric -------------------------------------------------------------------------------
     for _ in range(args.warmup):
@@ -235,10 +256,7 @@ def main():
         torch.cuda.synchronize()
 
         def step_host():
-            ctr.pass_begin(KG.PASS_COUNT)
-            ctr.stream_begin(False)
-            ctr.feed(host)
-            return ctr.pass_end()
+            return step(lambda: ctr.feed(host))
 
         for _ in range(min(args.warmup, 2)):
             step_host()
@@ -254,7 +272,7 @@ def main():
         assert st2["input_kmers"] == meta["input_kmers"]
         import ctypes
         e2e = {"value": total_kmers * args.steps / te.item(), "unit": UNIT,
-               "h2d_bytes_per_step": int(fasta.numel()) * world,
+               "h2d_bytes_per_step": int(fasta.numel()) * world * (2 if args.bloom else 1),
                "d2h_bytes_per_step": ctypes.sizeof(KG.PassStats) * world,
                "ms_per_step": te.item() * 1e3 / args.steps}
         del host
@@ -312,7 +330,8 @@ def main():
            "ms_per_step": dev_ms / args.steps, "wall_ms_per_step": wall_ms / args.steps, "higher_is_better": True,
            "scaling": "weak", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
            "config": {"workload": f"{args.workload}: {meta['G']} bp genome, {meta['cov']}x of {meta['L']} bp reads, "
-                                  f"k={k}, -m 0 -s {total_slots}", "scale": args.scale, "fasta_bytes_per_gpu": int(fasta.numel()),
+                                  f"k={k}, -m 0 " + (f"-b -u {meta['G']} -f {args.fpr}" if args.bloom else f"-s {total_slots}"), "scale": args.scale,
+                      "bloom": bloom_info or None, "fasta_bytes_per_gpu": int(fasta.numel()),
                       "table_bytes_per_gpu": ctr.table_info()["slots"] * ctr.table_info()["slot_bytes"],
                       "input_kmers_per_gpu": meta["input_kmers"], "distinct_rank0": distinct,
                       "l2": "inputs (2 GB/GPU) and table (4 GB/GPU) are far larger than the 126 MB L2; no flush between steps",

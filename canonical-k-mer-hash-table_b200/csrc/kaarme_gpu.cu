@@ -445,7 +445,7 @@ static int setup_pass_buckets(kg_ctx* c, size_t region_bytes) {
     c->pass_bucketed = world > 1 || pl > 1;
     if (!c->pass_bucketed) return KG_OK;
     for (int i = 0; i < 2; i++) {
-        if (!c->d_send[i] && (i == 0 || world > 1)) KG_CUDA(c, cudaMalloc(&c->d_send[i], c->send_cap * c->W * sizeof(u64)));
+        if (!c->d_send[i]) KG_CUDA(c, cudaMalloc(&c->d_send[i], c->send_cap * c->W * sizeof(u64)));
         if (c->recv_cap && !c->d_recv[i]) KG_CUDA(c, cudaMalloc(&c->d_recv[i], c->recv_cap * c->W * sizeof(u64)));
     }
     if (c->nb > c->nb_alloc) {
@@ -454,7 +454,7 @@ static int setup_pass_buckets(kg_ctx* c, size_t region_bytes) {
         c->d_blk_hist = c->d_blk_base = c->d_bucket_counts = c->d_bucket_offs = c->d_matrix = nullptr; c->h_matrix = nullptr;
         KG_CUDA(c, cudaMalloc(&c->d_blk_hist, sizeof(u32) * (size_t)c->max_blocks * c->nb));
         KG_CUDA(c, cudaMalloc(&c->d_blk_base, sizeof(u32) * (size_t)c->max_blocks * c->nb));
-        KG_CUDA(c, cudaMalloc(&c->d_bucket_counts, sizeof(u32) * (c->nb + 1)));
+        KG_CUDA(c, cudaMalloc(&c->d_bucket_counts, sizeof(u32) * (c->nb + 4)));
         KG_CUDA(c, cudaMalloc(&c->d_bucket_offs, sizeof(u32) * (c->nb + 1)));
         KG_CUDA(c, cudaMalloc(&c->d_matrix, sizeof(u32) * (size_t)(c->nb + 1) * world));
         KG_CUDA(c, cudaHostAlloc((void**)&c->h_matrix, sizeof(u32) * (size_t)(c->nb + 1) * world, cudaHostAllocDefault));
@@ -522,7 +522,7 @@ extern "C" int kg_pass_begin(kg_ctx* c, int pass) {
         KG_CUDA(c, cudaMemsetAsync(c->table.slots, 0, bytes, c->s_compute));
         { int rc = setup_pass_buckets(c, bytes); if (rc) return rc; }
     }
-    if (c->cfg.world > 1) {   // inserts run on their own stream: order them after the clears above
+    if (c->pass_bucketed) {   // inserts run on their own stream: order them after the clears above
         KG_CUDA(c, cudaEventRecord(c->ev_pass_ready, c->s_compute));
         KG_CUDA(c, cudaStreamWaitEvent(c->s_insert, c->ev_pass_ready, 0));
     }
@@ -802,9 +802,22 @@ static int bucket_batch(kg_ctx* c, u32 nthreads) {
         return exchange_round(c, true, &all_done);
     }
     // single GPU, partitioned: the send buffer is partition-major; one insert launch walks it in order, so the
-    // blocks in flight at any moment hit one or two table regions (L2-resident)
-    bucket_kernel(c, a, nthreads, true);
-    insert_keys(c, c->s_compute, c->d_send[0], (u64)nthreads * 32u, c->d_bucket_offs + c->nb);
+    // blocks in flight at any moment hit one or two table regions (L2-resident).  The insert runs on its own
+    // stream and the key buffers alternate, so the (ALU-bound) parse + bucketing of the next batch overlaps the
+    // (L2-latency-bound) insert of this one.
+    {
+        const int b = (int)(c->round & 1);
+        a.out_keys = c->d_send[b];
+        KG_CUDA(c, cudaStreamWaitEvent(c->s_compute, c->ev_send_free[b], 0));     // insert(round-2) has drained it
+        bucket_kernel(c, a, nthreads, true);
+        KG_CUDA(c, cudaMemcpyAsync(c->d_bucket_counts + c->nb + 1 + b, c->d_bucket_offs + c->nb, sizeof(u32),
+                                   cudaMemcpyDeviceToDevice, c->s_compute));     // this batch's key total, kept per buffer
+        KG_CUDA(c, cudaEventRecord(c->ev_scatter, c->s_compute));
+        KG_CUDA(c, cudaStreamWaitEvent(c->s_insert, c->ev_scatter, 0));
+        insert_keys(c, c->s_insert, c->d_send[b], (u64)nthreads * 32u, c->d_bucket_counts + c->nb + 1 + b);
+        KG_CUDA(c, cudaEventRecord(c->ev_send_free[b], c->s_insert));
+        c->round++;
+    }
     return KG_OK;
 }
 
@@ -950,9 +963,11 @@ extern "C" int kg_pass_end(kg_ctx* c, kg_pass_stats* out) {
             int rc = exchange_round(c, false, &all_done);
             if (rc) return rc;
         }
-        KG_CUDA(c, cudaEventRecord(c->ev_tail, c->s_insert));
-        KG_CUDA(c, cudaStreamWaitEvent(c->s_compute, c->ev_tail, 0));
         KG_CUDA(c, cudaEventRecord(c->ev_tail, c->s_comm));
+        KG_CUDA(c, cudaStreamWaitEvent(c->s_compute, c->ev_tail, 0));
+    }
+    if (c->pass_bucketed) {
+        KG_CUDA(c, cudaEventRecord(c->ev_tail, c->s_insert));
         KG_CUDA(c, cudaStreamWaitEvent(c->s_compute, c->ev_tail, 0));
     }
     KG_CUDA(c, cudaEventRecord(c->ev_pass_end, c->s_compute));

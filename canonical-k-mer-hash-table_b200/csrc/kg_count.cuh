@@ -35,11 +35,13 @@ __device__ __forceinline__ void kg_bloom_masks(u64 h, u32 nh, u32 (&mask)[8]) {
     for (int i = 0; i < 8; i++) mask[i] = 0;
     u64 g = kg_fmix64(h ^ 0xA24BAED4963EE407ULL);
     for (u32 i = 0; i < nh; i++) {
-        if ((i & 7u) == 7u) g = kg_fmix64(g + 0x9FB21C651E98DF25ULL);
-        u32 b = (u32)(g >> (8 * (i & 7u))) & 255u;
-        // (i&7)==7 consumed the refreshed g's low byte; fine: all bytes of g are well mixed
+        if ((i & 7u) == 7u) g = kg_fmix64(g + 0x9FB21C651E98DF25ULL);   // every 8th probe: fresh bits
+        const u32 b = (u32)(g >> (8 * (i & 7u))) & 255u;
+        const u32 bit = 1u << (b & 31u), sel = b >> 5;
+        // branch-free select (a per-lane `if` here compiles to 8 divergent regions per probe: ~1600 instructions
+        // per k-mer, which made the filter passes ALU-bound; profiles/r01_bloom2_insert_ncu.txt)
 #pragma unroll
-        for (int w = 0; w < 8; w++) if ((b >> 5) == (u32)w) mask[w] |= 1u << (b & 31u);
+        for (int w = 0; w < 8; w++) mask[w] |= (sel == (u32)w) ? bit : 0u;
     }
 }
 // block index = range partition of the in-shard hash (like the table slot), so a bucket of the partitioned path
