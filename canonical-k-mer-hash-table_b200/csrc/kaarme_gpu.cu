@@ -106,6 +106,8 @@ struct kg_ctx {
     cudaEvent_t ev_counts = nullptr, ev_scatter = nullptr, ev_matrix = nullptr, ev_pass_ready = nullptr, ev_tail = nullptr;
     cudaEvent_t ev_send_free[2] = {nullptr, nullptr}, ev_recv_free[2] = {nullptr, nullptr}, ev_recv_full[2] = {nullptr, nullptr};
     uint64_t round = 0, subround = 0;
+    u32* d_work = nullptr;              // work counter of the persistent insert kernels
+    u32 insert_grid = 148 * 8;          // resident blocks of the grid-stride insert kernels (SMs x blocks/SM)
     // Kaarme representation (after kg_compact)
     KgKaarme kaarme{nullptr, nullptr, 0, 0};
     KgCompactStats* d_cstats = nullptr;
@@ -242,7 +244,7 @@ static void free_all(kg_ctx* c) {
         if (c->ev_out[i]) cudaEventDestroy(c->ev_out[i]);
     }
     if (c->h_out_n) cudaFreeHost(c->h_out_n);
-    cudaFree(c->kaarme.slots); cudaFree(c->kaarme.roots); cudaFree(c->d_cstats);
+    cudaFree(c->kaarme.slots); cudaFree(c->kaarme.roots); cudaFree(c->d_cstats); cudaFree(c->d_work);
     if (c->s_comm) cudaStreamSynchronize(c->s_comm);
     if (c->s_insert) cudaStreamSynchronize(c->s_insert);
     if (c->comm) { kg_nccl().CommDestroy(c->comm); c->comm = nullptr; }
@@ -299,6 +301,8 @@ extern "C" int kg_create(const kg_config* cfg, kg_ctx** out) {
     }
     kg_ctx* c = new kg_ctx();
     c->cfg = *cfg;
+    c->insert_grid = (u32)prop.multiProcessorCount * 8u;
+    if (const char* e = getenv("KG_INSERT_GRID")) c->insert_grid = (u32)atoi(e) * (u32)prop.multiProcessorCount;
     c->W = (int)((cfg->k + 31) / 32);
     c->batch_bytes = cfg->batch_bytes ? cfg->batch_bytes : KG_DEFAULT_BATCH;
     if (c->batch_bytes > KG_MAX_BATCH) c->batch_bytes = KG_MAX_BATCH;
@@ -335,6 +339,7 @@ extern "C" int kg_create(const kg_config* cfg, kg_ctx** out) {
     KG_TRY(cudaMalloc(&c->d_carry_brk, sizeof(u32) * c->carry_max_words));
     KG_TRY(cudaMalloc(&c->d_stream, sizeof(KgStream)));
     KG_TRY(cudaMalloc(&c->d_stats, sizeof(KgStats)));
+    KG_TRY(cudaMalloc(&c->d_work, sizeof(u32) * 4));
     KG_TRY(cudaMemset(c->d_stream, 0, sizeof(KgStream)));
     KG_TRY(cudaMemset(c->d_stats, 0, sizeof(KgStats)));
     KG_TRY(cudaEventCreate(&c->ev_pass_begin));
@@ -582,12 +587,14 @@ static int current_sink(const kg_ctx* c) {
 template <int W>
 static void launch_insert_keys(kg_ctx* c, cudaStream_t s, const u64* keys, u64 n_upper, const u32* n_dev, int sink) {
     const u32 block = 256;
-    const u64 grid = (n_upper + KG_KEYS_PER_BLOCK - 1) / KG_KEYS_PER_BLOCK;
+    u64 grid = (n_upper + KG_CHUNK - 1) / KG_CHUNK;
+    if (grid > c->insert_grid) grid = c->insert_grid;    // persistent kernel: just enough blocks to fill the GPU
     if (grid == 0) return;
+    cudaMemsetAsync(c->d_work, 0, sizeof(u32), s);
     switch (sink) {
-        case KG_SINK_TABLE: kg_insert_keys_kernel<W, KG_SINK_TABLE><<<(u32)grid, block, 0, s>>>(keys, n_upper, n_dev, c->table, c->bloom, c->d_stats); break;
-        case KG_SINK_BLOOM1: kg_insert_keys_kernel<W, KG_SINK_BLOOM1><<<(u32)grid, block, 0, s>>>(keys, n_upper, n_dev, c->table, c->bloom, c->d_stats); break;
-        case KG_SINK_BLOOM2: kg_insert_keys_kernel<W, KG_SINK_BLOOM2><<<(u32)grid, block, 0, s>>>(keys, n_upper, n_dev, c->table, c->bloom, c->d_stats); break;
+        case KG_SINK_TABLE: kg_insert_keys_kernel<W, KG_SINK_TABLE><<<(u32)grid, block, 0, s>>>(keys, n_upper, n_dev, c->table, c->bloom, c->d_stats, c->d_work); break;
+        case KG_SINK_BLOOM1: kg_insert_keys_kernel<W, KG_SINK_BLOOM1><<<(u32)grid, block, 0, s>>>(keys, n_upper, n_dev, c->table, c->bloom, c->d_stats, c->d_work); break;
+        case KG_SINK_BLOOM2: kg_insert_keys_kernel<W, KG_SINK_BLOOM2><<<(u32)grid, block, 0, s>>>(keys, n_upper, n_dev, c->table, c->bloom, c->d_stats, c->d_work); break;
         default: break;
     }
     c->launches++;
@@ -657,14 +664,16 @@ static void bucket_kernel(kg_ctx* c, const KgBucketArgs& a, u32 grid, bool scatt
 
 template <int W>
 static void launch_insert_segs(kg_ctx* c, cudaStream_t s, const u64* keys, const u64* seg, u32 nseg, u64 n, int sink) {
-    const u64 grid = (n + KG_KEYS_PER_BLOCK - 1) / KG_KEYS_PER_BLOCK;
+    u64 grid = (n + KG_CHUNK - 1) / KG_CHUNK;
+    if (grid > c->insert_grid) grid = c->insert_grid;
     if (grid == 0) return;
+    cudaMemsetAsync(c->d_work, 0, sizeof(u32), s);
     const u64* start = seg;
     const u64* src = seg + (nseg + 1);
     switch (sink) {
-        case KG_SINK_TABLE: kg_insert_segs_kernel<W, KG_SINK_TABLE><<<(u32)grid, 256, 0, s>>>(keys, start, src, nseg, c->table, c->bloom, c->d_stats); break;
-        case KG_SINK_BLOOM1: kg_insert_segs_kernel<W, KG_SINK_BLOOM1><<<(u32)grid, 256, 0, s>>>(keys, start, src, nseg, c->table, c->bloom, c->d_stats); break;
-        case KG_SINK_BLOOM2: kg_insert_segs_kernel<W, KG_SINK_BLOOM2><<<(u32)grid, 256, 0, s>>>(keys, start, src, nseg, c->table, c->bloom, c->d_stats); break;
+        case KG_SINK_TABLE: kg_insert_segs_kernel<W, KG_SINK_TABLE><<<(u32)grid, 256, 0, s>>>(keys, start, src, nseg, c->table, c->bloom, c->d_stats, c->d_work); break;
+        case KG_SINK_BLOOM1: kg_insert_segs_kernel<W, KG_SINK_BLOOM1><<<(u32)grid, 256, 0, s>>>(keys, start, src, nseg, c->table, c->bloom, c->d_stats, c->d_work); break;
+        case KG_SINK_BLOOM2: kg_insert_segs_kernel<W, KG_SINK_BLOOM2><<<(u32)grid, 256, 0, s>>>(keys, start, src, nseg, c->table, c->bloom, c->d_stats, c->d_work); break;
         default: break;
     }
     c->launches++;

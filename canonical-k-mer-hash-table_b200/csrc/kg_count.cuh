@@ -270,6 +270,7 @@ __global__ void __launch_bounds__(256) kg_count_kernel(KgCountArgs a) {
 // insert keys from a key array (received from other shards, or this GPU's partition-major bucket buffer).
 // A block walks KG_KEYS_PER_BLOCK consecutive keys (coalesced); statistics leave the block as one atomic per
 // counter (one atomic per warp would put millions of RMWs on a single address).
+#define KG_CHUNK 1024u            // keys per work item of the persistent insert kernels
 #define KG_KEYS_PER_THREAD 16
 #define KG_KEYS_PER_BLOCK (256 * KG_KEYS_PER_THREAD)
 
@@ -287,20 +288,30 @@ __device__ __forceinline__ void kg_block_add(u32 v, u64* dst, u32* smem /*8 word
 
 template <int W, int SINK>
 __global__ void __launch_bounds__(256) kg_insert_keys_kernel(const u64* __restrict__ keys, u64 n, const u32* n_dev,
-                                                             KgTable table, KgBloom bloom, KgStats* stats) {
+                                                             KgTable table, KgBloom bloom, KgStats* stats, u32* work) {
     __shared__ u32 sm[8];
     if (n_dev) n = *n_dev;
-    const u64 base = (u64)blockIdx.x * KG_KEYS_PER_BLOCK;
     KgConsume<W, SINK> sink;
     sink.table = table;
     sink.bloom = bloom;
-    if (base < n) {
+    // Persistent blocks pull KG_CHUNK-key chunks from a global work counter, so whatever their relative speed the
+    // resident blocks always work at the FRONT of the (partition-major) key array: the keys in flight span about
+    // grid * KG_CHUNK keys and the table region they hit stays L2-resident even when a partition holds only
+    // ~1 M keys.  (A static block -> 4096-key mapping spread the in-flight window over ~5 M keys, several regions;
+    // a plain grid-stride loop lets slow blocks fall behind and is worse still.)
+    __shared__ u32 s_chunk;
+    for (;;) {
+        if (threadIdx.x == 0) s_chunk = atomicAdd(work, 1u);
+        __syncthreads();
+        const u64 first = (u64)s_chunk * KG_CHUNK;
+        __syncthreads();
+        if (first >= n) break;
 #pragma unroll 1
-        for (int j = 0; j < KG_KEYS_PER_THREAD; j++) {
-            const u64 i = base + (u64)j * 256u + threadIdx.x;
+        for (u32 j = 0; j < KG_CHUNK / 256; j++) {
+            const u64 i = first + (u64)j * 256u + threadIdx.x;
             if (i < n) {
                 u64 key[W];
-                if constexpr (W % 2 == 0) {                                        // streamed once: evict-first, 16 B loads
+                if constexpr (W % 2 == 0) {                                    // streamed once: evict-first, 16 B loads
 #pragma unroll
                     for (int q = 0; q < W; q += 2) {
                         const ulonglong2 v = __ldcs(reinterpret_cast<const ulonglong2*>(keys + i * W + q));
@@ -334,17 +345,22 @@ __global__ void __launch_bounds__(256) kg_insert_keys_kernel(const u64* __restri
 template <int W, int SINK>
 __global__ void __launch_bounds__(256) kg_insert_segs_kernel(const u64* __restrict__ keys, const u64* __restrict__ seg_start,
                                                              const u64* __restrict__ seg_src, u32 nseg,
-                                                             KgTable table, KgBloom bloom, KgStats* stats) {
+                                                             KgTable table, KgBloom bloom, KgStats* stats, u32* work) {
     __shared__ u32 sm[8];
     const u64 n = seg_start[nseg];
-    const u64 base = (u64)blockIdx.x * KG_KEYS_PER_BLOCK;
     KgConsume<W, SINK> sink;
     sink.table = table;
     sink.bloom = bloom;
-    if (base < n) {
+    __shared__ u32 s_chunk;
+    for (;;) {
+        if (threadIdx.x == 0) s_chunk = atomicAdd(work, 1u);
+        __syncthreads();
+        const u64 first = (u64)s_chunk * KG_CHUNK;
+        __syncthreads();
+        if (first >= n) break;
 #pragma unroll 1
-        for (int j = 0; j < KG_KEYS_PER_THREAD; j++) {
-            const u64 i = base + (u64)j * 256u + threadIdx.x;
+        for (u32 j = 0; j < KG_CHUNK / 256; j++) {
+            const u64 i = first + (u64)j * 256u + threadIdx.x;
             if (i < n) {
                 u32 lo = 0, hi = nseg;                       // last segment with seg_start <= i
                 while (hi - lo > 1) { const u32 mid = (lo + hi) >> 1; if (seg_start[mid] <= i) lo = mid; else hi = mid; }
