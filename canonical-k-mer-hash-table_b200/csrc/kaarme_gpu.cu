@@ -106,6 +106,7 @@ struct kg_ctx {
     cudaEvent_t ev_counts = nullptr, ev_scatter = nullptr, ev_matrix = nullptr, ev_pass_ready = nullptr, ev_tail = nullptr;
     cudaEvent_t ev_send_free[2] = {nullptr, nullptr}, ev_recv_free[2] = {nullptr, nullptr}, ev_recv_full[2] = {nullptr, nullptr};
     uint64_t round = 0, subround = 0;
+    bool scatter_configured = false;
     u32* d_work = nullptr;              // work counter of the persistent insert kernels
     u32 insert_grid = 148 * 8;          // resident blocks of the grid-stride insert kernels (SMs x blocks/SM)
     // Kaarme representation (after kg_compact)
@@ -624,10 +625,9 @@ static void launch_bucket(kg_ctx* c, const KgBucketArgs& a, u32 nwords, bool sca
     const u32 grid = (nwords + G::WPB - 1) / G::WPB;
     if (scatter) {
         const size_t smem = G::smem_bytes(a.nb);
-        static bool configured = false;
-        if (!configured) {
+        if (!c->scatter_configured) {   // per device (one context per device, possibly several in one process)
             cudaFuncSetAttribute(kg_owner_scatter<W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G::smem_bytes(KG_MAX_BUCKETS));
-            configured = true;
+            c->scatter_configured = true;
         }
         kg_owner_scatter<W><<<grid, G::TPB, smem, c->s_compute>>>(a);
     } else {

@@ -7,7 +7,7 @@
 //     -m,--hash-table-type {0,2}   -a,--min-k-abu N   -t,--threads N   -o,--output-file PATH
 //     -b,--use-bfilter  -f,--bfilter-fpr F   exactly one of  -s,--hash-tab-size N | -u,--unq-kmers N
 //   GPU-side extras (do not collide with the reference's flags):
-//     --device N   --batch-mb N   --exact-counts   --stats-json PATH
+//     --device N   --gpus N   --batch-mb N   --exact-counts   --stats-json PATH
 //
 // Exit codes follow the reference: 0 ok; CLI11's 105 (validation), 106 (required), 107 (requires),
 // 109 (unexpected argument); 1 for an ill-formed input file (main.cpp:168-171) or a full table
@@ -23,7 +23,9 @@
 #include <fcntl.h>
 #include <filesystem>
 #include <fstream>
+#include <condition_variable>
 #include <iostream>
+#include <mutex>
 #include <string>
 #include <sys/stat.h>
 #include <thread>
@@ -45,6 +47,7 @@ struct Args {
     bool has_s = false, has_u = false, has_f = false, has_t = false;
     uint64_t slots = 0, unique = 0;
     int device = 0;
+    int gpus = 1;
     uint64_t batch_mb = 0;
     bool exact_counts = false;
 };
@@ -68,7 +71,8 @@ void print_help(const char* argv0) {
                  "  -o,--output-file TEXT      Output file where the k-mer counts will be stored\n"
                  "  -b,--use-bfilter           Use bloom filters to discard unique k-mers\n"
                  "  -f,--bfilter-fpr FLOAT     Bloom filter false positive rate (def. 0.01)\n"
-                 "  --device INT               CUDA device ordinal (def. 0)\n"
+                 "  --device INT               CUDA device ordinal (def. 0; with --gpus N the first of N consecutive devices)\n"
+                 "  --gpus INT                 Hash-shard the k-mers over N GPUs of this box (NCCL exchange; def. 1)\n"
                  "  --batch-mb UINT            Raw bytes per device batch in MiB (def. 128)\n"
                  "  --exact-counts             Report true 32-bit counts instead of emulating the reference's\n"
                  "                             16-bit wrap (-m 0) / 14-bit saturation (-m 2)\n"
@@ -156,6 +160,10 @@ Args parse_args(int argc, char** argv) {
             long long v; std::string t = value("--device");
             if (!parse_i64(t, v) || v < 0) cli_fail(105, "--device: Value " + t + " not a device ordinal");
             a.device = (int)v;
+        } else if (s == "--gpus") {
+            long long v; std::string t = value("--gpus");
+            if (!parse_i64(t, v) || v < 1 || v > 64) cli_fail(105, "--gpus: Value " + t + " not in range 1 to 64");
+            a.gpus = (int)v;
         } else if (s == "--batch-mb") {
             std::string t = value("--batch-mb");
             if (!parse_u64(t, a.batch_mb) || a.batch_mb == 0 || a.batch_mb > 1024) cli_fail(105, "--batch-mb: Value " + t + " not in range 1 to 1024");
@@ -204,37 +212,91 @@ Format file_format(const std::string& path) {
 #define KG_CHECK(call)                                                                              \
     do {                                                                                            \
         int rc_ = (call);                                                                           \
-        if (rc_ == KG_ETABLE_FULL) { std::cout << "Hash table is full... Cannot handle this yet\n"; std::exit(1); } \
+        if (rc_ == KG_ETABLE_FULL) { std::cout << "Hash table is full... Cannot handle this yet" << std::endl; std::_Exit(1); } \
         if (rc_ != KG_OK) {                                                                         \
-            std::cerr << "kaarme: " #call " failed: " << kg_strerror(rc_) << " (" << kg_last_error(ctx) << ")\n"; \
-            std::exit(2);                                                                           \
+            std::cerr << "kaarme: " #call " failed: " << kg_strerror(rc_) << " (" << kg_last_error(ctx) << ")" << std::endl; \
+            std::_Exit(2);   /* worker threads may be running: no static destructors */            \
         }                                                                                           \
     } while (0)
 
-// one pass over the file: read(2) into two pinned buffers, feed the GPU while the next read proceeds
-void feed_file(kg_ctx* ctx, const std::string& path, uint8_t* buf[2], size_t buf_bytes) {
+// Host-side sharding of one input across ranks (the role of text_reader.h:141-184): a rank that owns bytes
+// [lo, hi) must also see the k-1 bases before lo (fed with KG_FEED_CONTEXT, not counted) and must know whether its
+// first byte lies inside a FASTA header.
+struct Slice { off_t ctx_lo, lo, hi; bool in_header; };
+Slice make_slice(int fd, off_t file_size, int rank, int world, uint32_t k, bool fasta) {
+    Slice s;
+    s.lo = file_size * rank / world;
+    s.hi = file_size * (rank + 1) / world;
+    s.in_header = false;
+    // walk back over k-1 non-newline bytes
+    off_t need = (off_t)k - 1, i = s.lo;
+    std::vector<char> buf(1 << 16);
+    while (i > 0 && need > 0) {
+        off_t n = std::min<off_t>((off_t)buf.size(), i);
+        if (pread(fd, buf.data(), (size_t)n, i - n) != n) break;
+        for (off_t j = n - 1; j >= 0 && need > 0; j--) { i--; if (buf[j] != '\n') need--; }
+    }
+    s.ctx_lo = i;
+    if (fasta) {   // a '>' since the last newline before ctx_lo => the context starts inside a header
+        off_t j = s.ctx_lo;
+        bool decided = false;
+        while (j > 0 && !decided) {
+            off_t n = std::min<off_t>((off_t)buf.size(), j);
+            if (pread(fd, buf.data(), (size_t)n, j - n) != n) break;
+            for (off_t q = n - 1; q >= 0; q--) {
+                if (buf[q] == '\n') { decided = true; break; }
+                if (buf[q] == '>') { s.in_header = true; decided = true; break; }
+            }
+            j -= n;
+        }
+    }
+    return s;
+}
+
+// one pass over this rank's slice: pread(2) into two pinned buffers, feed the GPU while the next read proceeds
+void feed_file(kg_ctx* ctx, const std::string& path, uint8_t* buf[2], size_t buf_bytes, const Slice& sl) {
     int fd = open(path.c_str(), O_RDONLY);
     if (fd < 0) { std::cerr << "kaarme: cannot open " << path << "\n"; std::exit(1); }
 #ifdef __linux__
-    posix_fadvise(fd, 0, 0, POSIX_FADV_SEQUENTIAL);  // parallel_parser.hpp:280
+    posix_fadvise(fd, sl.ctx_lo, sl.hi - sl.ctx_lo, POSIX_FADV_SEQUENTIAL);  // parallel_parser.hpp:280
 #endif
-    KG_CHECK(kg_stream_begin(ctx, 0));
+    KG_CHECK(kg_stream_begin(ctx, sl.in_header ? 1 : 0));
     int which = 0;
-    for (;;) {
-        size_t got = 0;
-        while (got < buf_bytes) {
-            ssize_t r = read(fd, buf[which] + got, buf_bytes - got);
+    off_t pos = sl.ctx_lo;
+    while (pos < sl.hi) {
+        // context bytes and counted bytes go in separate feeds
+        const bool context = pos < sl.lo;
+        const off_t end = context ? sl.lo : sl.hi;
+        size_t want = (size_t)std::min<off_t>((off_t)buf_bytes, end - pos), got = 0;
+        while (got < want) {
+            ssize_t r = pread(fd, buf[which] + got, want - got, pos + (off_t)got);
             if (r < 0) { std::cerr << "kaarme: read error on " << path << "\n"; std::exit(1); }
             if (r == 0) break;
             got += (size_t)r;
         }
         if (got == 0) break;
-        KG_CHECK(kg_feed(ctx, buf[which], got, 0));   // returns once the H2D copy is done; kernels keep running
+        KG_CHECK(kg_feed(ctx, buf[which], got, context ? KG_FEED_CONTEXT : 0));   // returns once the H2D copy is done
         which ^= 1;
-        if (got < buf_bytes) break;
+        pos += (off_t)got;
     }
     close(fd);
 }
+
+// reusable barrier for the per-GPU host threads
+class Barrier {
+  public:
+    explicit Barrier(int n) : n_(n) {}
+    void wait() {
+        std::unique_lock<std::mutex> lk(m_);
+        const int gen = gen_;
+        if (++count_ == n_) { gen_++; count_ = 0; cv_.notify_all(); }
+        else cv_.wait(lk, [&] { return gen != gen_; });
+    }
+  private:
+    std::mutex m_;
+    std::condition_variable cv_;
+    int n_, count_ = 0, gen_ = 0;
+};
 
 struct Writer {
     FILE* f = nullptr;
@@ -334,97 +396,158 @@ int main(int argc, char** argv) {
     if (args.mode == 1) { std::cout << "Chosen mode not recognized\n"; return 0; }       // -m 1 (superseded variant) is out of scope
     if (args.k > 256) { std::cerr << "kaarme: k > 256 is not supported by the GPU build\n"; return 1; }
 
-    kg_ctx* ctx = nullptr;
-    kg_config cfg;
-    memset(&cfg, 0, sizeof(cfg));
-    cfg.abi_version = KG_ABI_VERSION;
-    cfg.k = (uint32_t)args.k;
-    cfg.table_mode = args.mode;
-    cfg.input_mode = input_mode;
-    cfg.min_slots = args.slots;
-    cfg.use_bloom = args.bloom ? 1 : 0;
-    cfg.device = args.device;
-    cfg.fpr = args.fpr;
-    cfg.expected_unique = args.unique;
-    cfg.batch_bytes = args.batch_mb << 20;
-    cfg.rank = 0;
-    cfg.world = 1;
-    {
-        int rc = kg_create(&cfg, &ctx);
-        if (rc != KG_OK) {
-            std::cerr << "kaarme: cannot initialise the GPU path: " << kg_strerror(rc) << " (" << kg_last_error(nullptr)
-                      << "). This build has no CPU fallback.\n";
-            return 2;
-        }
-    }
+    if (args.gpus > 1 && args.mode == KG_TABLE_KAARME)
+        std::cout << "note: with --gpus > 1 the Kaarme compaction is skipped (k-mers are exported from the sharded plain tables)\n";
+
+    const int world = args.gpus;
     const size_t buf_bytes = (args.batch_mb ? args.batch_mb : 128) << 20;
-    uint8_t* bufs[2] = {nullptr, nullptr};
-    for (int i = 0; i < 2; i++) KG_CHECK(kg_host_alloc(buf_bytes, (void**)&bufs[i]));
-
-    kg_pass_stats bloom_stats, count_stats;
-    memset(&bloom_stats, 0, sizeof(bloom_stats));
-    memset(&count_stats, 0, sizeof(count_stats));
-    kg_compact_stats compact_stats;
-    memset(&compact_stats, 0, sizeof(compact_stats));
-
-    if (args.bloom) {
-        std::cout << "Starting parallel bloom filtering\n";  // parallel_parser.hpp:2689
-        auto t0 = std::chrono::high_resolution_clock::now();
-        KG_CHECK(kg_pass_begin(ctx, KG_PASS_BLOOM));
-        feed_file(ctx, args.input, bufs, buf_bytes);
-        KG_CHECK(kg_pass_end(ctx, &bloom_stats));
-        auto t1 = std::chrono::high_resolution_clock::now();
-        std::cout << "New k-mers in first bloom filter " << bloom_stats.new_in_first << "\n";   // parallel_parser.hpp:2900-2901
-        std::cout << "New k-mers in second bloom filter " << bloom_stats.new_in_second << "\n";
-        std::cout << "Time used to bloom filter k-mers: " << std::chrono::duration_cast<std::chrono::microseconds>(t1 - t0).count() << " microseconds\n";
+    struct stat fst{};
+    stat(args.input.c_str(), &fst);
+    char nccl_id[KG_UNIQUE_ID_BYTES];
+    if (world > 1) {
+        kg_ctx* ctx = nullptr;
+        KG_CHECK(kg_comm_unique_id(nccl_id));
     }
-    std::cout << (args.mode == 0 ? "Starting atomic flag basic hash table\n" : "Starting atomic variable pointer hash table\n");
-    auto t_build0 = std::chrono::high_resolution_clock::now();
-    KG_CHECK(kg_pass_begin(ctx, KG_PASS_COUNT));
-    {
-        uint64_t slots = 0;
-        kg_table_info(ctx, &slots, nullptr, nullptr);
-        std::cout << "Hash table size is: " << slots << "\n";  // functions_math.cpp:90
-    }
-    feed_file(ctx, args.input, bufs, buf_bytes);
-    KG_CHECK(kg_pass_end(ctx, &count_stats));
-    if (args.mode == KG_TABLE_KAARME) KG_CHECK(kg_compact(ctx, &compact_stats));
-    auto t_build1 = std::chrono::high_resolution_clock::now();
-
+    // shared across the per-GPU host threads
+    std::vector<kg_pass_stats> bloom_stats(world), count_stats(world);
+    std::vector<kg_compact_stats> compact_stats(world);
+    std::vector<uint64_t> table_slots(world, 0);
+    for (int r = 0; r < world; r++) { memset(&bloom_stats[r], 0, sizeof(kg_pass_stats)); memset(&count_stats[r], 0, sizeof(kg_pass_stats)); memset(&compact_stats[r], 0, sizeof(kg_compact_stats)); }
     Writer w;
-    w.k = cfg.k; w.W = (cfg.k + 31) / 32; w.threads = std::max(1, args.threads - 2);
+    w.k = (uint32_t)args.k; w.W = ((uint32_t)args.k + 31) / 32; w.threads = std::max(1, (args.threads - 2) / world);
+    std::mutex out_mutex;
     if (args.min_abundance > 0) {
         w.f = fopen(args.output.c_str(), "wb");
         if (!w.f) { std::cerr << "kaarme: cannot open output file " << args.output << "\n"; return 1; }
         setvbuf(w.f, nullptr, _IOFBF, 8 << 20);
-        KG_CHECK(kg_export(ctx, args.min_abundance, args.exact_counts ? KG_COUNT_EXACT : KG_COUNT_REFERENCE, sink, &w));
-        fclose(w.f);
     }
-    auto t_write1 = std::chrono::high_resolution_clock::now();
-    std::cout << "Time used to build hash table: " << std::chrono::duration_cast<std::chrono::microseconds>(t_build1 - t_build0).count() << " microseconds\n";
-    std::cout << "Time used to write k-mers in a file: " << std::chrono::duration_cast<std::chrono::microseconds>(t_write1 - t_build1).count() << " microseconds\n";
+    Barrier barrier(world);
+    std::chrono::high_resolution_clock::time_point t_bloom0, t_bloom1, t_build0, t_build1, t_write1;
+
+    // one host thread per GPU: its own context (= hash shard), its own byte range of the input
+    auto rank_main = [&](int rank) {
+        kg_ctx* ctx = nullptr;
+        kg_config cfg;
+        memset(&cfg, 0, sizeof(cfg));
+        cfg.abi_version = KG_ABI_VERSION;
+        cfg.k = (uint32_t)args.k;
+        cfg.table_mode = args.mode;
+        cfg.input_mode = input_mode;
+        cfg.min_slots = args.slots;
+        cfg.use_bloom = args.bloom ? 1 : 0;
+        cfg.device = args.device + rank;
+        cfg.fpr = args.fpr;
+        cfg.expected_unique = args.unique;
+        cfg.batch_bytes = args.batch_mb << 20;
+        cfg.rank = rank;
+        cfg.world = world;
+        {
+            int rc = kg_create(&cfg, &ctx);
+            if (rc != KG_OK) {
+                std::cerr << "kaarme: cannot initialise the GPU path on device " << cfg.device << ": " << kg_strerror(rc) << " ("
+                          << kg_last_error(nullptr) << "). This build has no CPU fallback.\n";
+                std::exit(2);
+            }
+        }
+        if (world > 1) KG_CHECK(kg_comm_init(ctx, nccl_id, rank, world));
+        uint8_t* bufs[2] = {nullptr, nullptr};
+        for (int i = 0; i < 2; i++) KG_CHECK(kg_host_alloc(buf_bytes, (void**)&bufs[i]));
+        int fd = open(args.input.c_str(), O_RDONLY);
+        const Slice sl = make_slice(fd, fst.st_size, rank, world, (uint32_t)args.k, input_mode == KG_INPUT_FASTA);
+        close(fd);
+
+        if (args.bloom) {
+            barrier.wait();
+            if (rank == 0) { std::cout << "Starting parallel bloom filtering\n"; t_bloom0 = std::chrono::high_resolution_clock::now(); }  // parallel_parser.hpp:2689
+            KG_CHECK(kg_pass_begin(ctx, KG_PASS_BLOOM));
+            feed_file(ctx, args.input, bufs, buf_bytes, sl);
+            KG_CHECK(kg_pass_end(ctx, &bloom_stats[rank]));
+            barrier.wait();
+            if (rank == 0) t_bloom1 = std::chrono::high_resolution_clock::now();
+        }
+        if (args.bloom && rank == 0 && world == 1) {
+            std::cout << "New k-mers in first bloom filter " << bloom_stats[0].new_in_first << "\n";   // parallel_parser.hpp:2900-2901
+            std::cout << "New k-mers in second bloom filter " << bloom_stats[0].new_in_second << "\n";
+            std::cout << "Time used to bloom filter k-mers: " << std::chrono::duration_cast<std::chrono::microseconds>(t_bloom1 - t_bloom0).count() << " microseconds\n";
+        }
+        barrier.wait();
+        if (rank == 0) t_build0 = std::chrono::high_resolution_clock::now();
+        KG_CHECK(kg_pass_begin(ctx, KG_PASS_COUNT));
+        kg_table_info(ctx, &table_slots[rank], nullptr, nullptr);
+        if (rank == 0) {
+            std::cout << (args.mode == 0 ? "Starting atomic flag basic hash table\n" : "Starting atomic variable pointer hash table\n");
+            if (world == 1) std::cout << "Hash table size is: " << table_slots[0] << "\n";  // functions_math.cpp:90
+        }
+        feed_file(ctx, args.input, bufs, buf_bytes, sl);
+        KG_CHECK(kg_pass_end(ctx, &count_stats[rank]));
+        if (args.mode == KG_TABLE_KAARME && world == 1) KG_CHECK(kg_compact(ctx, &compact_stats[rank]));
+        barrier.wait();
+        if (rank == 0) t_build1 = std::chrono::high_resolution_clock::now();
+        if (args.min_abundance > 0) {
+            // shards own disjoint k-mers and the output order is unspecified: the ranks take turns per chunk
+            struct Locked { Writer* w; std::mutex* m; } lk{&w, &out_mutex};
+            auto locked_sink = [](void* user, const uint64_t* keys, const uint32_t* counts, size_t n) -> int {
+                auto* l = static_cast<Locked*>(user);
+                std::lock_guard<std::mutex> g(*l->m);
+                return sink(l->w, keys, counts, n);
+            };
+            KG_CHECK(kg_export(ctx, args.min_abundance, args.exact_counts ? KG_COUNT_EXACT : KG_COUNT_REFERENCE, locked_sink, &lk));
+        }
+        barrier.wait();
+        if (rank == 0) t_write1 = std::chrono::high_resolution_clock::now();
+        for (int i = 0; i < 2; i++) kg_host_free(bufs[i]);
+        kg_destroy(ctx);
+    };
+    if (world == 1) rank_main(0);
+    else {
+        std::vector<std::thread> th;
+        for (int r = 0; r < world; r++) th.emplace_back(rank_main, r);
+        for (auto& t : th) t.join();
+    }
+    if (w.f) fclose(w.f);
+
+    // logs, in the reference's order (sums over the shards)
+    kg_pass_stats bsum = bloom_stats[0], csum = count_stats[0];
+    uint64_t slots_sum = table_slots[0];
+    for (int r = 1; r < world; r++) {
+        bsum.new_in_first += bloom_stats[r].new_in_first; bsum.new_in_second += bloom_stats[r].new_in_second;
+        bsum.device_ms = std::max(bsum.device_ms, bloom_stats[r].device_ms);
+        csum.input_kmers += count_stats[r].input_kmers; csum.inserted_kmers += count_stats[r].inserted_kmers;
+        csum.distinct += count_stats[r].distinct; csum.table_slots += count_stats[r].table_slots; csum.raw_bytes += count_stats[r].raw_bytes;
+        csum.device_ms = std::max(csum.device_ms, count_stats[r].device_ms);
+        slots_sum += table_slots[r];
+    }
+    using us = std::chrono::microseconds;
+    if (args.bloom && world > 1) {
+        std::cout << "New k-mers in first bloom filter " << bsum.new_in_first << "\n";   // parallel_parser.hpp:2900-2901
+        std::cout << "New k-mers in second bloom filter " << bsum.new_in_second << "\n";
+        std::cout << "Time used to bloom filter k-mers: " << std::chrono::duration_cast<us>(t_bloom1 - t_bloom0).count() << " microseconds\n";
+    }
+    if (world > 1) std::cout << "Hash table size is: " << slots_sum << " (" << world << " shards)\n";
+    std::cout << "Time used to build hash table: " << std::chrono::duration_cast<us>(t_build1 - t_build0).count() << " microseconds\n";
+    std::cout << "Time used to write k-mers in a file: " << std::chrono::duration_cast<us>(t_write1 - t_build1).count() << " microseconds\n";
+    const kg_compact_stats& cs = compact_stats[0];
     if (args.mode == KG_TABLE_KAARME) {
         std::cout << "Written k-mers: " << w.written << "\n";                         // kmer_hash_table.cpp:4522-4523
-        std::cout << "Skipped k-mers: " << (count_stats.distinct - w.written) << "\n";
-        std::cout << "Main array slots used " << count_stats.distinct << " / " << count_stats.table_slots << "\n";  // parallel_parser.hpp:1560-1561
-        std::cout << "Max secondary array slots used " << compact_stats.roots << "\n";
-        std::cout << "Kaarme bytes: " << compact_stats.bytes << " (" << (compact_stats.kmers ? (double)compact_stats.bytes / compact_stats.kmers : 0.0)
-                  << " B/k-mer; reference layout would hold " << compact_stats.reference_bytes << " B)\n";
+        std::cout << "Skipped k-mers: " << (csum.distinct - w.written) << "\n";
+        std::cout << "Main array slots used " << csum.distinct << " / " << csum.table_slots << "\n";  // parallel_parser.hpp:1560-1561
+        if (world == 1) {
+            std::cout << "Max secondary array slots used " << cs.roots << "\n";
+            std::cout << "Kaarme bytes: " << cs.bytes << " (" << (cs.kmers ? (double)cs.bytes / cs.kmers : 0.0)
+                      << " B/k-mer; reference layout would hold " << cs.reference_bytes << " B)\n";
+        }
     }
-    std::cout << "GPU: input k-mers " << count_stats.input_kmers << ", distinct " << count_stats.distinct << ", device time "
-              << count_stats.device_ms + bloom_stats.device_ms << " ms ("
-              << (count_stats.device_ms + bloom_stats.device_ms > 0 ? count_stats.input_kmers / ((count_stats.device_ms + bloom_stats.device_ms) * 1e3) : 0.0)
-              << " M k-mers/s)\n";
+    const double dev_ms = csum.device_ms + bsum.device_ms;
+    std::cout << "GPU x" << world << ": input k-mers " << csum.input_kmers << ", distinct " << csum.distinct << ", device time " << dev_ms
+              << " ms (" << (dev_ms > 0 ? csum.input_kmers / (dev_ms * 1e3) : 0.0) << " M k-mers/s)\n";
     if (!args.stats_json.empty()) {
         std::ofstream o(args.stats_json);
-        o << "{";
-        if (args.bloom) { json_pass(o, "bloom", bloom_stats); o << ", "; }
-        json_pass(o, "count", count_stats);
-        o << ", \"written\": " << w.written << ", \"kaarme\": {\"kmers\": " << compact_stats.kmers << ", \"roots\": " << compact_stats.roots
-          << ", \"bytes\": " << compact_stats.bytes << ", \"reference_bytes\": " << compact_stats.reference_bytes << ", \"max_chain\": "
-          << compact_stats.max_chain << "}}\n";
+        o << "{\"gpus\": " << world << ", ";
+        if (args.bloom) { json_pass(o, "bloom", bsum); o << ", "; }
+        json_pass(o, "count", csum);
+        o << ", \"written\": " << w.written << ", \"kaarme\": {\"kmers\": " << cs.kmers << ", \"roots\": " << cs.roots
+          << ", \"bytes\": " << cs.bytes << ", \"reference_bytes\": " << cs.reference_bytes << ", \"max_chain\": "
+          << cs.max_chain << "}}\n";
     }
-    for (int i = 0; i < 2; i++) kg_host_free(bufs[i]);
-    kg_destroy(ctx);
     return 0;
 }
