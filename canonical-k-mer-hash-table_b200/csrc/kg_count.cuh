@@ -351,23 +351,39 @@ __global__ void __launch_bounds__(256) kg_insert_segs_kernel(const u64* __restri
     KgConsume<W, SINK> sink;
     sink.table = table;
     sink.bloom = bloom;
-    __shared__ u32 s_chunk;
+    __shared__ u32 s_chunk, s_seg0;
     for (;;) {
-        if (threadIdx.x == 0) s_chunk = atomicAdd(work, 1u);
+        if (threadIdx.x == 0) {
+            const u32 ch = atomicAdd(work, 1u);
+            s_chunk = ch;
+            // segment holding the first key of the chunk (one binary search per chunk, not per key)
+            const u64 f = (u64)ch * KG_CHUNK;
+            u32 lo = 0, hi = nseg;
+            if (f < n) while (hi - lo > 1) { const u32 mid = (lo + hi) >> 1; if (seg_start[mid] <= f) lo = mid; else hi = mid; }
+            s_seg0 = lo;
+        }
         __syncthreads();
         const u64 first = (u64)s_chunk * KG_CHUNK;
+        u32 seg = s_seg0;
         __syncthreads();
         if (first >= n) break;
 #pragma unroll 1
         for (u32 j = 0; j < KG_CHUNK / 256; j++) {
             const u64 i = first + (u64)j * 256u + threadIdx.x;
             if (i < n) {
-                u32 lo = 0, hi = nseg;                       // last segment with seg_start <= i
-                while (hi - lo > 1) { const u32 mid = (lo + hi) >> 1; if (seg_start[mid] <= i) lo = mid; else hi = mid; }
-                const u64 src = seg_src[lo] + (i - seg_start[lo]);
+                while (seg + 1 < nseg && seg_start[seg + 1] <= i) seg++;     // segments are ~10^5 keys: rarely advances
+                const u64 src = seg_src[seg] + (i - seg_start[seg]);
                 u64 key[W];
+                if constexpr (W % 2 == 0) {
 #pragma unroll
-                for (int q = 0; q < W; q++) key[q] = __ldcs(keys + src * W + q);
+                    for (int q = 0; q < W; q += 2) {
+                        const ulonglong2 v = __ldcs(reinterpret_cast<const ulonglong2*>(keys + src * W + q));
+                        key[q] = v.x; key[q + 1] = v.y;
+                    }
+                } else {
+#pragma unroll
+                    for (int q = 0; q < W; q++) key[q] = __ldcs(keys + src * W + q);
+                }
                 KgOcc none; none.word = ~0ULL;
                 sink(key, kg_hash_key<W>(key), none);
             }
