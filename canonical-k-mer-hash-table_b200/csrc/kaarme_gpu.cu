@@ -107,6 +107,8 @@ struct kg_ctx {
     cudaEvent_t ev_send_free[2] = {nullptr, nullptr}, ev_recv_free[2] = {nullptr, nullptr}, ev_recv_full[2] = {nullptr, nullptr};
     uint64_t round = 0, subround = 0;
     bool scatter_configured = false;
+    u32 reserve_cap = 0;                // keys per bucket region of the one-pass (reserve) scatter
+    size_t send_alloc = 0;              // keys each d_send buffer can hold
     u32* d_work = nullptr;              // work counter of the persistent insert kernels
     u32 insert_grid = 148 * 8;          // resident blocks of the grid-stride insert kernels (SMs x blocks/SM)
     // Kaarme representation (after kg_compact)
@@ -450,8 +452,19 @@ static int setup_pass_buckets(kg_ctx* c, size_t region_bytes) {
     c->nb = world * pl;
     c->pass_bucketed = world > 1 || pl > 1;
     if (!c->pass_bucketed) return KG_OK;
+    // one-pass (reserve) scatter on a single GPU: fixed-capacity bucket regions, 25 % slack + 8192 keys
+    size_t need = c->send_cap;
+    c->reserve_cap = 0;
+    if (world == 1 && c->W <= 4 && !getenv("KG_NO_RESERVE")) {
+        c->reserve_cap = (u32)(c->send_cap / pl + c->send_cap / pl / 4 + 8192);
+        need = (size_t)c->reserve_cap * pl;
+    }
+    if (need > c->send_alloc) {
+        for (int i = 0; i < 2; i++) { cudaFree(c->d_send[i]); c->d_send[i] = nullptr; }
+        c->send_alloc = need;
+    }
     for (int i = 0; i < 2; i++) {
-        if (!c->d_send[i]) KG_CUDA(c, cudaMalloc(&c->d_send[i], c->send_cap * c->W * sizeof(u64)));
+        if (!c->d_send[i]) KG_CUDA(c, cudaMalloc(&c->d_send[i], c->send_alloc * c->W * sizeof(u64)));
         if (c->recv_cap && !c->d_recv[i]) KG_CUDA(c, cudaMalloc(&c->d_recv[i], c->recv_cap * c->W * sizeof(u64)));
     }
     if (c->nb > c->nb_alloc) {
@@ -466,7 +479,7 @@ static int setup_pass_buckets(kg_ctx* c, size_t region_bytes) {
         KG_CUDA(c, cudaHostAlloc((void**)&c->h_matrix, sizeof(u32) * (size_t)(c->nb + 1) * world, cudaHostAllocDefault));
         c->nb_alloc = c->nb;
     }
-    if (world > 1 && c->nb + 1 > c->seg_cap) {
+    if (c->nb + 1 > c->seg_cap) {
         for (int i = 0; i < 2; i++) {
             cudaFree(c->d_seg[i]); if (c->h_seg[i]) cudaFreeHost(c->h_seg[i]);
             KG_CUDA(c, cudaMalloc(&c->d_seg[i], sizeof(u64) * 2 * (c->nb + 2)));
@@ -679,6 +692,29 @@ static void launch_insert_segs(kg_ctx* c, cudaStream_t s, const u64* keys, const
     c->launches++;
 }
 
+template <int W>
+static void launch_reserve(kg_ctx* c, const KgReserveArgs& a, u32 nwords, int sink) {
+    if constexpr (W <= 4) {
+        using G = KgBucketGeom<W>;
+        const u32 grid = (nwords + G::WPB - 1) / G::WPB;
+        const size_t smem = (size_t)G::KEYS * W * 8 + (size_t)a.nb * 12 + (size_t)G::KEYS * 2 + 64;
+        const int max_smem = (int)((size_t)G::KEYS * W * 8 + (size_t)KG_MAX_BUCKETS * 12 + (size_t)G::KEYS * 2 + 64);
+        switch (sink) {
+            case KG_SINK_TABLE:
+                cudaFuncSetAttribute(kg_scatter_reserve<W, KG_SINK_TABLE>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem);
+                kg_scatter_reserve<W, KG_SINK_TABLE><<<grid, G::TPB, smem, c->s_compute>>>(a); break;
+            case KG_SINK_BLOOM1:
+                cudaFuncSetAttribute(kg_scatter_reserve<W, KG_SINK_BLOOM1>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem);
+                kg_scatter_reserve<W, KG_SINK_BLOOM1><<<grid, G::TPB, smem, c->s_compute>>>(a); break;
+            case KG_SINK_BLOOM2:
+                cudaFuncSetAttribute(kg_scatter_reserve<W, KG_SINK_BLOOM2>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem);
+                kg_scatter_reserve<W, KG_SINK_BLOOM2><<<grid, G::TPB, smem, c->s_compute>>>(a); break;
+            default: break;
+        }
+        c->launches++;
+    }
+}
+
 // One exchange round (collective when world > 1).  have_batch: this rank's send buffer (round & 1) was just
 // filled by bucket_batch; otherwise the rank contributes nothing and reports "done".  Returns via *all_done
 // whether every rank reported done in this round.
@@ -788,8 +824,33 @@ static int exchange_round(kg_ctx* c, bool have_batch, bool* all_done) {
     return KG_OK;
 }
 
-// bucket the k-mers of the batch that was just packed (hist -> scan -> scatter), then hand them on
+// bucket the k-mers of the batch that was just packed, then hand them on
+//   single GPU, W <= 4 : one-pass reserve scatter -> segment table -> insert (kg_scatter_reserve)
+//   otherwise          : hist -> scan -> scatter (exact layout, needed for the exchange) -> exchange / insert
 static int bucket_batch(kg_ctx* c, u32 nthreads) {
+    if (c->cfg.world == 1 && c->reserve_cap) {
+        const int b = (int)(c->round & 1);
+        const int sink = current_sink(c);
+        u32* cursors = c->d_bucket_counts;
+        KG_CUDA(c, cudaMemsetAsync(cursors, 0, sizeof(u32) * c->nb, c->s_compute));
+        KG_CUDA(c, cudaStreamWaitEvent(c->s_compute, c->ev_send_free[b], 0));     // insert(round-2) has drained this buffer
+        KgReserveArgs r;
+        r.words = c->d_words; r.brk = c->d_brk; r.st = c->d_stream; r.cursors = cursors; r.out_keys = c->d_send[b];
+        r.stats = c->d_stats; r.table = c->table; r.bloom = c->bloom; r.k = c->cfg.k; r.nb = c->nb; r.cap = c->reserve_cap;
+        KG_DISPATCH_W(c->W, launch_reserve, c, r, nthreads, sink);
+        kg_seg_from_cursors<<<1, 1024, 0, c->s_compute>>>(cursors, c->nb, c->reserve_cap, c->d_seg[b], c->d_seg[b] + (c->nb + 1));
+        c->launches++;
+        KG_CUDA(c, cudaEventRecord(c->ev_scatter, c->s_compute));
+        KG_CUDA(c, cudaStreamWaitEvent(c->s_insert, c->ev_scatter, 0));
+        cudaEvent_t ia = next_ins_event(c), ib = next_ins_event(c);
+        if (ia) cudaEventRecord(ia, c->s_insert);
+        c->ins_launches++;
+        KG_DISPATCH_W(c->W, launch_insert_segs, c, c->s_insert, c->d_send[b], c->d_seg[b], c->nb, (u64)nthreads * 32u, sink);
+        if (ib) cudaEventRecord(ib, c->s_insert);
+        KG_CUDA(c, cudaEventRecord(c->ev_send_free[b], c->s_insert));
+        c->round++;
+        return KG_OK;
+    }
     const u32 grid = bucket_blocks(c, nthreads);   // blocks of the hist / scatter pair
     const int sb = c->cfg.world > 1 ? (int)(c->round & 1) : 0;
     KgBucketArgs a;

@@ -576,6 +576,211 @@ __global__ void __launch_bounds__(KgBucketGeom<W>::TPB) kg_owner_scatter(KgBucke
     }
 }
 
+// ---- single-GPU one-pass bucketing: reserve, don't count ----------------------------------------------------------
+// On one GPU the bucket layout need not be exact (nothing is sent anywhere), so the histogram pass is dropped:
+// a block computes its keys ONCE (kept in registers), ranks them with shared atomics, reserves a run in every
+// bucket's fixed-capacity region with one global atomic per (block, bucket), stages the keys in shared memory
+// and writes coalesced runs.  A key that does not fit its region (pathological skew) is inserted directly.
+// One window pass instead of three (hist + two in kg_owner_scatter).
+
+// eight consecutive windows (positions 32t+j0 .. +7), fully unrolled so per-window state can live in registers
+template <int W, typename F>
+__device__ __forceinline__ u32 kg_window8(const u64* __restrict__ words, const u32* __restrict__ brk,
+                                          u32 T, u32 C, u32 k, u32 t, u32 j0, F&& f) {
+    if ((u64)t * 32u + j0 >= T) return 0;
+    const KgKGeom g = kg_geom(k);
+    const u64 myword = words[t];
+    const u32 mybrk = brk[t];
+    const u32 jend = min(j0 + 8u, T - t * 32u);
+    u32 run = 0;
+    {
+        const u32 head = j0 ? (mybrk >> (32 - j0)) : 0u;
+        if (head) {
+            run = __ffs(head);
+        } else {
+            run = j0;
+            bool found = false;
+#pragma unroll 1
+            for (int i = 1; i <= W + 1 && !found; i++) {
+                if ((int)t - i < 0) break;
+                u32 b = brk[t - i];
+                if (b) { run += __ffs(b); found = true; }
+                else run += 32;
+            }
+        }
+    }
+    KgKmerWindow<W> w;
+    if (j0 == 0) {
+#pragma unroll
+        for (int i = 0; i < W; i++) {
+            int src = (int)t - 1 - i;
+            w.f[W - 1 - i] = src >= 0 ? words[src] : 0ULL;
+        }
+    } else {
+        const u32 s = 64 - 2 * j0;
+        u64 lo = myword;
+#pragma unroll
+        for (int i = 0; i < W; i++) {
+            int src = (int)t - 1 - i;
+            const u64 hi = src >= 0 ? words[src] : 0ULL;
+            w.f[W - 1 - i] = (hi << (64 - s)) | (lo >> s);
+            lo = hi;
+        }
+    }
+    w.f[0] &= g.topmask;
+    kg_revcomp<W>(w.f, w.r, g);
+    const u32 base_pos = t * 32u;
+    u32 n_windows = 0;
+#pragma unroll
+    for (int q = 0; q < 8; q++) {
+        const u32 j = j0 + q;
+        if (j < jend) {
+            const u32 c = (u32)(myword >> (62 - 2 * j)) & 3u;
+            kg_push<W>(w, g, c);
+            run = ((mybrk >> (31 - j)) & 1u) ? 1u : run + 1u;
+            if (run >= k && base_pos + j >= C) {
+                n_windows++;
+                u64 key[W];
+                const bool fwd = kg_forward_is_canonical<W>(w);
+#pragma unroll
+                for (int i = 0; i < W; i++) key[i] = fwd ? w.f[i] : w.r[i];
+                f(q, key, kg_hash_key<W>(key));
+            }
+        }
+    }
+    return n_windows;
+}
+
+struct KgReserveArgs {
+    const u64* words;
+    const u32* brk;
+    const KgStream* st;
+    u32* cursors;       // [nb] keys reserved so far in every bucket region (may run past cap: overflow)
+    u64* out_keys;      // nb regions of cap keys
+    KgStats* stats;
+    KgTable table;      // overflow keys are inserted directly
+    KgBloom bloom;
+    u32 k;
+    u32 nb;
+    u32 cap;            // keys per bucket region
+};
+
+template <int W, int SINK>
+__global__ void __launch_bounds__(KgBucketGeom<W>::TPB) kg_scatter_reserve(KgReserveArgs a) {
+    using G = KgBucketGeom<W>;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    u64* s_keys = reinterpret_cast<u64*>(smem_raw);                                  // KEYS * W
+    u32* s_cnt = reinterpret_cast<u32*>(s_keys + (size_t)G::KEYS * W);                 // nb
+    u32* s_off = s_cnt + a.nb;                                                         // nb
+    u32* s_gbase = s_off + a.nb;                                                       // nb
+    unsigned short* s_kb = reinterpret_cast<unsigned short*>(s_gbase + a.nb);          // KEYS
+    __shared__ u32 s_warp[32];
+    __shared__ u32 s_stat[8];
+    const u32 nb = a.nb, tid = threadIdx.x;
+    for (u32 i = tid; i < nb; i += G::TPB) s_cnt[i] = 0;
+    __syncthreads();
+    const u32 T = a.st->total_bases, C = a.st->carry_bases;
+    const u32 t = blockIdx.x * G::WPB + (tid >> 2);
+    const u32 j0 = (tid & 3u) * 8u;
+    u64 kreg[8][W];
+    u32 br[8];
+#pragma unroll
+    for (int q = 0; q < 8; q++) br[q] = 0xFFFFFFFFu;
+    const u32 n_windows = kg_window8<W>(a.words, a.brk, T, C, a.k, t, j0, [&](int q, const u64 (&key)[W], u64 h) {
+        const u32 b = (u32)__umul64hi(h, (u64)nb);
+        const u32 r = atomicAdd(&s_cnt[b], 1u);
+        br[q] = (b << 16) | r;
+#pragma unroll
+        for (int i = 0; i < W; i++) kreg[q][i] = key[i];
+    });
+    KG_WARP_ADD(a.stats, n_windows, input_kmers)
+    __syncthreads();
+    {   // exclusive scan of the bucket counts + one global reservation per non-empty bucket
+        const u32 per = (nb + G::TPB - 1) / G::TPB;
+        const u32 b0 = tid * per, b1 = min(b0 + per, nb);
+        u32 mine = 0;
+        for (u32 i = b0; i < b1; i++) mine += s_cnt[i];
+        u32 incl = mine;
+        const u32 lane = tid & 31u, warp = tid >> 5;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) { u32 o = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= (u32)d) incl += o; }
+        if (lane == 31) s_warp[warp] = incl;
+        __syncthreads();
+        u32 pre = 0;
+        for (u32 w2 = 0; w2 < warp; w2++) pre += s_warp[w2];
+        u32 cur = pre + incl - mine;
+        for (u32 i = b0; i < b1; i++) {
+            const u32 c = s_cnt[i];
+            s_off[i] = cur;
+            cur += c;
+            s_gbase[i] = c ? atomicAdd(&a.cursors[i], c) : 0u;
+        }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int q = 0; q < 8; q++) {
+        if (br[q] != 0xFFFFFFFFu) {
+            const u32 b = br[q] >> 16, idx = s_off[b] + (br[q] & 0xFFFFu);
+#pragma unroll
+            for (int i = 0; i < W; i++) s_keys[(size_t)idx * W + i] = kreg[q][i];
+            s_kb[idx] = (unsigned short)b;
+        }
+    }
+    __syncthreads();
+    const u32 n = s_off[nb - 1] + s_cnt[nb - 1];
+    KgConsume<W, SINK> sink;
+    sink.table = a.table;
+    sink.bloom = a.bloom;
+    for (u32 i = tid; i < n; i += G::TPB) {
+        const u32 b = s_kb[i];
+        const u32 rel = s_gbase[b] + (i - s_off[b]);
+        if (rel < a.cap) {
+            u64* dst = a.out_keys + ((u64)b * a.cap + rel) * W;
+            if (W % 2 == 0) {
+#pragma unroll
+                for (int q = 0; q < W; q += 2)
+                    *reinterpret_cast<ulonglong2*>(dst + q) = make_ulonglong2(s_keys[(size_t)i * W + q], s_keys[(size_t)i * W + q + 1]);
+            } else {
+#pragma unroll
+                for (int q = 0; q < W; q++) dst[q] = s_keys[(size_t)i * W + q];
+            }
+        } else {                                   // region full: insert this key here and now
+            u64 key[W];
+#pragma unroll
+            for (int q = 0; q < W; q++) key[q] = s_keys[(size_t)i * W + q];
+            KgOcc none; none.word = ~0ULL;
+            sink(key, kg_hash_key<W>(key), none);
+        }
+    }
+    if (SINK == KG_SINK_TABLE || SINK == KG_SINK_BLOOM2) {
+        kg_block_add(sink.n_ins, &a.stats->inserted, s_stat);
+        kg_block_add(sink.n_new, &a.stats->distinct, s_stat);
+    }
+    if (SINK == KG_SINK_BLOOM1) {
+        kg_block_add(sink.n_b1, &a.stats->new_in_first, s_stat);
+        kg_block_add(sink.n_b2, &a.stats->new_in_second, s_stat);
+    }
+    if (SINK == KG_SINK_BLOOM2) kg_block_add(sink.n_rej, &a.stats->bloom_rejected, s_stat);
+    if (sink.full) a.stats->table_full = 1;
+}
+
+// segment table over the bucket regions: seg b = keys [b*cap, b*cap + min(cursor[b], cap))
+__global__ void __launch_bounds__(1024) kg_seg_from_cursors(const u32* __restrict__ cursors, u32 nb, u32 cap,
+                                                            u64* __restrict__ seg_start, u64* __restrict__ seg_src) {
+    __shared__ u64 sm[1024];
+    const u64 v = threadIdx.x < nb ? (u64)min(cursors[threadIdx.x], cap) : 0ULL;
+    sm[threadIdx.x] = v;
+    __syncthreads();
+    for (u32 d = 1; d < 1024; d <<= 1) {
+        u64 t = threadIdx.x >= d ? sm[threadIdx.x - d] : 0;
+        __syncthreads();
+        sm[threadIdx.x] += t;
+        __syncthreads();
+    }
+    if (threadIdx.x < nb) { seg_start[threadIdx.x] = sm[threadIdx.x] - v; seg_src[threadIdx.x] = (u64)threadIdx.x * cap; }
+    if (threadIdx.x == 1023) seg_start[nb] = sm[1023];
+}
+
 // ---- K5 export: stream-compact slots whose reported count >= min_abundance -------------------------------
 // (replaces the table scan of write_kmers, kmer_hash_table.cpp:2013-2050)
 __device__ __forceinline__ u32 kg_reported_count(u32 n, int count_mode, int table_mode) {

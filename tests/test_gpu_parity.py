@@ -385,3 +385,17 @@ def test_kaarme_count_saturation(oracle):
     keys, counts, st, cs, _ = gpu_kaarme(data, 21, a=2)
     assert_same(keys, counts, oracle.count(data, 21).filtered(2, oracle.TABLE_KAARME))
     assert int(counts.max()) == 16383
+
+
+def test_partition_overflow_falls_back_to_direct_insert(oracle):
+    """pathological skew: one k-mer repeated 10^5 times overflows its fixed-capacity bucket region of the one-pass
+    scatter; the overflowing keys are inserted directly and nothing is lost"""
+    data = _read("g4_polya.fasta")
+    want = oracle.count(data, 21)
+    for parts in (8, 64):
+        keys, counts, st = gpu_count(data, 21, batch_bytes=65536, partitions=parts)
+        assert st["input_kmers"] == want.total_windows == st["inserted_kmers"]
+        assert_same(keys, counts, want)
+    want51 = oracle.count(data, 51)
+    keys, counts, st = gpu_count(data, 51, batch_bytes=65536, partitions=16)
+    assert_same(keys, counts, want51)
