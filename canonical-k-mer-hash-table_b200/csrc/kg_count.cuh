@@ -485,104 +485,6 @@ __global__ void __launch_bounds__(1024) kg_bucket_offsets(const u32* __restrict_
     if (threadIdx.x == 1023) offs_out[nb] = sm[1023];
 }
 
-// Geometry shared by hist and scatter: a block owns KgBucketGeom<W>::WPB packed words (32*WPB k-mer end positions).
-// hist runs one thread per word; scatter runs four threads per word (8 positions each) and stages the block's
-// keys in shared memory so that every bucket leaves the block as ONE contiguous, coalesced run.  (Writing each key
-// straight from its thread costs two 8-byte partial-sector stores per k-mer and runs at ~25 G keys/s; see
-// profiles/r01_partitioned_scatter_insert_ncu.txt and profiles/scatter_probe.sh.)
-template <int W>
-struct KgBucketGeom {
-    static constexpr int WPB = W <= 2 ? 128 : (W <= 4 ? 64 : 32);   // words per block: <= 64 KiB of staged keys
-    static constexpr int TPB = 4 * WPB;                             // scatter threads per block
-    static constexpr int KEYS = 32 * WPB;                           // staged keys per block (upper bound)
-    static constexpr size_t smem_bytes(u32 nb) {
-        return (size_t)KEYS * W * 8 + (size_t)KEYS * 2 /*bucket of a staged key*/ + (size_t)TPB * 8 * 4 /*ranks*/ +
-               (size_t)nb * 4 * 3 /*count, offset, global base*/ + 64;
-    }
-};
-
-template <int W>
-__global__ void __launch_bounds__(KgBucketGeom<W>::TPB) kg_owner_scatter(KgBucketArgs a) {
-    using G = KgBucketGeom<W>;
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    u64* s_keys = reinterpret_cast<u64*>(smem_raw);                                  // KEYS * W
-    u32* s_rank = reinterpret_cast<u32*>(s_keys + (size_t)G::KEYS * W);                // TPB * 8
-    u32* s_cnt = s_rank + G::TPB * 8;                                                  // nb
-    u32* s_off = s_cnt + a.nb;                                                         // nb
-    u32* s_gbase = s_off + a.nb;                                                       // nb
-    unsigned short* s_kb = reinterpret_cast<unsigned short*>(s_gbase + a.nb);          // KEYS
-    __shared__ u32 s_warp[32];
-    const u32 nb = a.nb, tid = threadIdx.x;
-    for (u32 i = tid; i < nb; i += G::TPB) s_cnt[i] = 0;
-    __syncthreads();
-    const u32 T = a.st->total_bases, C = a.st->carry_bases;
-    const u32 t = blockIdx.x * G::WPB + (tid >> 2);
-    const u32 j0 = (tid & 3u) * 8u;
-    // pass 1: bucket and rank-in-bucket of each of my (<= 8) windows
-#pragma unroll
-    for (int q = 0; q < 8; q++) s_rank[q * G::TPB + tid] = 0xFFFFFFFFu;
-    kg_for_each_window<W>(a.words, a.brk, T, C, a.k, t, 0, [&](const u64 (&key)[W], u64 h, KgOcc, u32 j) {
-        (void)key;
-        const u32 b = kg_bucket_of(h, a.world, nb);
-        const u32 r = atomicAdd(&s_cnt[b], 1u);
-        s_rank[(j - j0) * G::TPB + tid] = (b << 16) | r;
-    }, j0, j0 + 8);
-    __syncthreads();
-    // exclusive scan of the bucket counts (nb <= 1024), and the global base of every bucket run
-    {
-        const u32 per = (nb + G::TPB - 1) / G::TPB;
-        const u32 b0 = tid * per, b1 = min(b0 + per, nb);
-        u32 mine = 0;
-        for (u32 i = b0; i < b1; i++) mine += s_cnt[i];
-        u32 incl = mine;
-        const u32 lane = tid & 31u, warp = tid >> 5;
-#pragma unroll
-        for (int d = 1; d < 32; d <<= 1) { u32 o = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= (u32)d) incl += o; }
-        if (lane == 31) s_warp[warp] = incl;
-        __syncthreads();
-        u32 pre = 0;
-        for (u32 w2 = 0; w2 < warp; w2++) pre += s_warp[w2];
-        u32 cur = pre + incl - mine;
-        for (u32 i = b0; i < b1; i++) {
-            s_off[i] = cur;
-            cur += s_cnt[i];
-            s_gbase[i] = a.bucket_offs[i] + a.blk_base[(u64)blockIdx.x * nb + i];
-        }
-    }
-    __syncthreads();
-    // pass 2: recompute the windows and drop each key at its staged position (keys grouped by bucket)
-    kg_for_each_window<W>(a.words, a.brk, T, C, a.k, t, 0, [&](const u64 (&key)[W], u64, KgOcc, u32 j) {
-        const u32 br = s_rank[(j - j0) * G::TPB + tid];
-        const u32 b = br >> 16, idx = s_off[b] + (br & 0xFFFFu);
-#pragma unroll
-        for (int i = 0; i < W; i++) s_keys[(size_t)idx * W + i] = key[i];
-        s_kb[idx] = (unsigned short)b;
-    }, j0, j0 + 8);
-    __syncthreads();
-    // coalesced write-out: consecutive staged keys of one bucket go to consecutive global addresses
-    const u32 n = s_off[nb - 1] + s_cnt[nb - 1];
-    if (a.dbg == 1) return;
-    for (u32 i = tid; i < n; i += G::TPB) {
-        const u32 b = s_kb[i];
-        u64* dst = a.out_keys + (u64)(s_gbase[b] + (i - s_off[b])) * W;
-        if (W % 2 == 0) {
-#pragma unroll
-            for (int q = 0; q < W; q += 2)
-                *reinterpret_cast<ulonglong2*>(dst + q) = make_ulonglong2(s_keys[(size_t)i * W + q], s_keys[(size_t)i * W + q + 1]);
-        } else {
-#pragma unroll
-            for (int q = 0; q < W; q++) dst[q] = s_keys[(size_t)i * W + q];
-        }
-    }
-}
-
-// ---- single-GPU one-pass bucketing: reserve, don't count ----------------------------------------------------------
-// On one GPU the bucket layout need not be exact (nothing is sent anywhere), so the histogram pass is dropped:
-// a block computes its keys ONCE (kept in registers), ranks them with shared atomics, reserves a run in every
-// bucket's fixed-capacity region with one global atomic per (block, bucket), stages the keys in shared memory
-// and writes coalesced runs.  A key that does not fit its region (pathological skew) is inserted directly.
-// One window pass instead of three (hist + two in kg_owner_scatter).
-
 // eight consecutive windows (positions 32t+j0 .. +7), fully unrolled so per-window state can live in registers
 template <int W, typename F>
 __device__ __forceinline__ u32 kg_window8(const u64* __restrict__ words, const u32* __restrict__ brk,
@@ -650,6 +552,132 @@ __device__ __forceinline__ u32 kg_window8(const u64* __restrict__ words, const u
     }
     return n_windows;
 }
+
+// Geometry shared by hist and scatter: a block owns KgBucketGeom<W>::WPB packed words (32*WPB k-mer end positions).
+// hist runs one thread per word; scatter runs four threads per word (8 positions each) and stages the block's
+// keys in shared memory so that every bucket leaves the block as ONE contiguous, coalesced run.  (Writing each key
+// straight from its thread costs two 8-byte partial-sector stores per k-mer and runs at ~25 G keys/s; see
+// profiles/r01_partitioned_scatter_insert_ncu.txt and profiles/scatter_probe.sh.)
+template <int W>
+struct KgBucketGeom {
+    static constexpr int WPB = W <= 2 ? 128 : (W <= 4 ? 64 : 32);   // words per block: <= 64 KiB of staged keys
+    static constexpr int TPB = 4 * WPB;                             // scatter threads per block
+    static constexpr int KEYS = 32 * WPB;                           // staged keys per block (upper bound)
+    static constexpr size_t smem_bytes(u32 nb) {
+        return (size_t)KEYS * W * 8 + (size_t)KEYS * 2 /*bucket of a staged key*/ + (size_t)TPB * 8 * 4 /*ranks*/ +
+               (size_t)nb * 4 * 3 /*count, offset, global base*/ + 64;
+    }
+};
+
+template <int W>
+__global__ void __launch_bounds__(KgBucketGeom<W>::TPB) kg_owner_scatter(KgBucketArgs a) {
+    using G = KgBucketGeom<W>;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    u64* s_keys = reinterpret_cast<u64*>(smem_raw);                                  // KEYS * W
+    u32* s_rank = reinterpret_cast<u32*>(s_keys + (size_t)G::KEYS * W);                // TPB * 8
+    u32* s_cnt = s_rank + G::TPB * 8;                                                  // nb
+    u32* s_off = s_cnt + a.nb;                                                         // nb
+    u32* s_gbase = s_off + a.nb;                                                       // nb
+    unsigned short* s_kb = reinterpret_cast<unsigned short*>(s_gbase + a.nb);          // KEYS
+    __shared__ u32 s_warp[32];
+    const u32 nb = a.nb, tid = threadIdx.x;
+    for (u32 i = tid; i < nb; i += G::TPB) s_cnt[i] = 0;
+    __syncthreads();
+    const u32 T = a.st->total_bases, C = a.st->carry_bases;
+    const u32 t = blockIdx.x * G::WPB + (tid >> 2);
+    const u32 j0 = (tid & 3u) * 8u;
+    // pass 1: bucket and rank-in-bucket of each of my (<= 8) windows.  W <= 4: the keys stay in registers and
+    // the windows are computed once; wider keys recompute them in pass 2 (register budget).
+    constexpr bool kInRegs = W <= 4;
+    u64 kreg[kInRegs ? 8 : 1][W];
+    u32 br[8];
+#pragma unroll
+    for (int q = 0; q < 8; q++) br[q] = 0xFFFFFFFFu;
+    if constexpr (kInRegs) {
+        kg_window8<W>(a.words, a.brk, T, C, a.k, t, j0, [&](int q, const u64 (&key)[W], u64 h) {
+            const u32 b = kg_bucket_of(h, a.world, nb);
+            const u32 r = atomicAdd(&s_cnt[b], 1u);
+            br[q] = (b << 16) | r;
+#pragma unroll
+            for (int i = 0; i < W; i++) kreg[q][i] = key[i];
+        });
+    } else {
+#pragma unroll
+        for (int q = 0; q < 8; q++) s_rank[q * G::TPB + tid] = 0xFFFFFFFFu;
+        kg_for_each_window<W>(a.words, a.brk, T, C, a.k, t, 0, [&](const u64 (&key)[W], u64 h, KgOcc, u32 j) {
+            (void)key;
+            const u32 b = kg_bucket_of(h, a.world, nb);
+            const u32 r = atomicAdd(&s_cnt[b], 1u);
+            s_rank[(j - j0) * G::TPB + tid] = (b << 16) | r;
+        }, j0, j0 + 8);
+    }
+    __syncthreads();
+    // exclusive scan of the bucket counts (nb <= 1024), and the global base of every bucket run
+    {
+        const u32 per = (nb + G::TPB - 1) / G::TPB;
+        const u32 b0 = tid * per, b1 = min(b0 + per, nb);
+        u32 mine = 0;
+        for (u32 i = b0; i < b1; i++) mine += s_cnt[i];
+        u32 incl = mine;
+        const u32 lane = tid & 31u, warp = tid >> 5;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) { u32 o = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= (u32)d) incl += o; }
+        if (lane == 31) s_warp[warp] = incl;
+        __syncthreads();
+        u32 pre = 0;
+        for (u32 w2 = 0; w2 < warp; w2++) pre += s_warp[w2];
+        u32 cur = pre + incl - mine;
+        for (u32 i = b0; i < b1; i++) {
+            s_off[i] = cur;
+            cur += s_cnt[i];
+            s_gbase[i] = a.bucket_offs[i] + a.blk_base[(u64)blockIdx.x * nb + i];
+        }
+    }
+    __syncthreads();
+    // pass 2: drop each key at its staged position (keys grouped by bucket)
+    if constexpr (kInRegs) {
+#pragma unroll
+        for (int q = 0; q < 8; q++) {
+            if (br[q] != 0xFFFFFFFFu) {
+                const u32 b = br[q] >> 16, idx = s_off[b] + (br[q] & 0xFFFFu);
+#pragma unroll
+                for (int i = 0; i < W; i++) s_keys[(size_t)idx * W + i] = kreg[q][i];
+                s_kb[idx] = (unsigned short)b;
+            }
+        }
+    } else {
+        kg_for_each_window<W>(a.words, a.brk, T, C, a.k, t, 0, [&](const u64 (&key)[W], u64, KgOcc, u32 j) {
+            const u32 brj = s_rank[(j - j0) * G::TPB + tid];
+            const u32 b = brj >> 16, idx = s_off[b] + (brj & 0xFFFFu);
+#pragma unroll
+            for (int i = 0; i < W; i++) s_keys[(size_t)idx * W + i] = key[i];
+            s_kb[idx] = (unsigned short)b;
+        }, j0, j0 + 8);
+    }
+    __syncthreads();
+    // coalesced write-out: consecutive staged keys of one bucket go to consecutive global addresses
+    const u32 n = s_off[nb - 1] + s_cnt[nb - 1];
+    if (a.dbg == 1) return;
+    for (u32 i = tid; i < n; i += G::TPB) {
+        const u32 b = s_kb[i];
+        u64* dst = a.out_keys + (u64)(s_gbase[b] + (i - s_off[b])) * W;
+        if (W % 2 == 0) {
+#pragma unroll
+            for (int q = 0; q < W; q += 2)
+                *reinterpret_cast<ulonglong2*>(dst + q) = make_ulonglong2(s_keys[(size_t)i * W + q], s_keys[(size_t)i * W + q + 1]);
+        } else {
+#pragma unroll
+            for (int q = 0; q < W; q++) dst[q] = s_keys[(size_t)i * W + q];
+        }
+    }
+}
+
+// ---- single-GPU one-pass bucketing: reserve, don't count ----------------------------------------------------------
+// On one GPU the bucket layout need not be exact (nothing is sent anywhere), so the histogram pass is dropped:
+// a block computes its keys ONCE (kept in registers), ranks them with shared atomics, reserves a run in every
+// bucket's fixed-capacity region with one global atomic per (block, bucket), stages the keys in shared memory
+// and writes coalesced runs.  A key that does not fit its region (pathological skew) is inserted directly.
+// One window pass instead of three (hist + two in kg_owner_scatter).
 
 struct KgReserveArgs {
     const u64* words;
