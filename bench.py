@@ -295,7 +295,9 @@ def main():
     rec = meta["record_bytes"]
     bytes_per_kmer = rec / (meta["L"] - k + 1) + 2 * 32 * S      # fused parse->insert figure
     bucketed = st["partitions"] > 1 or world > 1
-    kernel = (f"kg_insert_segs_kernel<{W},TABLE>" if world > 1 else f"kg_insert_keys_kernel<{W},TABLE>") if bucketed \
+    # (the segment-table variant serves the exchange and the one-pass scatter of W <= 4; wider keys on one GPU use
+    # the exact hist/scatter layout and kg_insert_keys_kernel)
+    kernel = (f"kg_insert_segs_kernel<{W},TABLE>" if (world > 1 or W <= 4) else f"kg_insert_keys_kernel<{W},TABLE>") if bucketed \
         else f"kg_count_kernel<{W},TABLE>"
     kmers_in_kernel = inserted_rank * args.steps                   # k-mers this rank's kernel launches processed
     achieved = kmers_in_kernel * bytes_per_kmer / (insert_ms * 1e-3) / 1e9

@@ -857,7 +857,6 @@ static int bucket_batch(kg_ctx* c, u32 nthreads) {
     a.words = c->d_words; a.brk = c->d_brk; a.st = c->d_stream;
     a.blk_hist = c->d_blk_hist; a.blk_base = c->d_blk_base; a.bucket_offs = c->d_bucket_offs; a.out_keys = c->d_send[sb];
     a.stats = c->d_stats; a.k = c->cfg.k; a.nb = c->nb; a.world = (u32)c->cfg.world;
-    { const char* e = getenv("KG_SCATTER_DBG"); a.dbg = e ? (u32)atoi(e) : 0; }
     bucket_kernel(c, a, nthreads, false);
     kg_bucket_colscan<<<c->nb, 1024, 0, c->s_compute>>>(c->d_blk_hist, c->d_blk_base, grid, c->nb, c->d_bucket_counts);
     kg_bucket_offsets<<<1, 1024, 0, c->s_compute>>>(c->d_bucket_counts, c->nb, c->d_bucket_offs);

@@ -420,7 +420,6 @@ struct KgBucketArgs {
     u32 k;
     u32 nb;             // number of buckets: world (multi-GPU) or partitions (single GPU)
     u32 world;          // > 1: bucket = owner shard; 1: bucket = partition of the local hash
-    u32 dbg;            // experiments: 1 = skip the global stores, 2 = skip the shared atomics
 };
 
 // bucket = floor(h * nb / 2^64) with nb = world * local_partitions: the high part is the owner shard
@@ -557,7 +556,7 @@ __device__ __forceinline__ u32 kg_window8(const u64* __restrict__ words, const u
 // hist runs one thread per word; scatter runs four threads per word (8 positions each) and stages the block's
 // keys in shared memory so that every bucket leaves the block as ONE contiguous, coalesced run.  (Writing each key
 // straight from its thread costs two 8-byte partial-sector stores per k-mer and runs at ~25 G keys/s; see
-// profiles/r01_partitioned_scatter_insert_ncu.txt and profiles/scatter_probe.sh.)
+// profiles/r01_partitioned_scatter_insert_ncu.txt and profiles/r01_scatter_probe_result.txt.)
 template <int W>
 struct KgBucketGeom {
     static constexpr int WPB = W <= 2 ? 128 : (W <= 4 ? 64 : 32);   // words per block: <= 64 KiB of staged keys
@@ -657,7 +656,6 @@ __global__ void __launch_bounds__(KgBucketGeom<W>::TPB) kg_owner_scatter(KgBucke
     __syncthreads();
     // coalesced write-out: consecutive staged keys of one bucket go to consecutive global addresses
     const u32 n = s_off[nb - 1] + s_cnt[nb - 1];
-    if (a.dbg == 1) return;
     for (u32 i = tid; i < n; i += G::TPB) {
         const u32 b = s_kb[i];
         u64* dst = a.out_keys + (u64)(s_gbase[b] + (i - s_off[b])) * W;

@@ -1,6 +1,6 @@
 #!/usr/bin/env python3
 """Turn the ncu outputs brought back in gpurun_out/ into the tracked summaries under profiles/:
-   r01_launches_summary.txt, r01_insert_keys_ncu.txt, r01_count_direct_ncu.txt, traffic.json"""
+   r01_launches_summary.txt, r01_insert_segs_ncu.txt, r01_count_direct_ncu.txt, traffic.json"""
 import collections
 import csv
 import json
@@ -69,8 +69,8 @@ if __name__ == "__main__":
     launches()
     kpl = 497_500_000 / 2  # k-mers per launch at --scale 0.25 with 256 MiB batches (2 batches)
     t = {}
-    t["kg_insert_keys_kernel"] = raw("r01_insert_keys.ncu-rep", "r01_insert_keys_ncu.txt",
-                                     "# ncu --set full --clock-control none --import-source on -k regex:kg_insert_keys_kernel -s 2 -c 2 ; python bench.py --scale 0.25 --steps 1 --warmup 1 --no-cpu-baseline --no-e2e\n"
+    t["kg_insert_segs_kernel"] = raw("r01_insert_segs.ncu-rep", "r01_insert_segs_ncu.txt",
+                                     "# ncu --set full --clock-control none --import-source on -k regex:kg_insert_segs_kernel -s 2 -c 2 ; python bench.py --scale 0.25 --steps 1 --warmup 1 --no-cpu-baseline --no-e2e\n"
                                      "# L2-blocked insert (partitions auto = 64, table 1 GB packed 16-byte slots), 248.75 M k-mers per launch\n", kpl)
     t["kg_count_kernel"] = raw("r01_count_direct.ncu-rep", "r01_count_direct_ncu.txt",
                                "# ncu --set full ... -k regex:kg_count_kernel -s 2 -c 2 ; python bench.py --scale 0.25 ... --partitions 1   (direct, DRAM-random insert)\n", kpl)
