@@ -108,18 +108,44 @@ __device__ __forceinline__ u32 kg_block_sum_exclusive(u32 mine, u32* smem, u32* 
     return pre + incl - mine;
 }
 
-// header effect of 16 bytes: '>' => SET (from this byte on), '\n' => CLEAR (from the next byte on)
-__device__ __forceinline__ u32 kg_hdr_effect16(const uint4& v, int nvalid) {
-    u32 eff = KG_EFF_NONE;
+// ---- SWAR classification of 16 bytes ----------------------------------------------------------------------
+// Per-byte compares run four at a time (__vcmpeq4); the results are folded into 16-bit position masks
+// (bit i = byte i) and the 2-bit codes into one 32-bit word (bits 2i+1:2i = code of byte i), so the per-byte
+// state machine of the reference's scanner (parallel_parser.hpp:597-638) becomes a handful of bit operations
+// per EVENT (header, newline, invalid byte) instead of a branchy loop per byte.
+struct KgMasks16 {
+    u32 base;   // A C G T a c g t
+    u32 nl;     // '\n'
+    u32 gt;     // '>'
+    u32 codes;  // 2-bit code of every byte (garbage where base is 0)
+};
+__device__ __forceinline__ u32 kg_movemask4(u32 m) {          // 0xFF/0x00 per byte -> 4 bits, bit i = byte i
+    return ((m & 0x01010101u) * 0x01020408u) >> 24;
+}
+__device__ __forceinline__ KgMasks16 kg_masks16(const uint4& v, int nvalid) {
+    const u32 w[4] = {v.x, v.y, v.z, v.w};
+    KgMasks16 m;
+    m.base = m.nl = m.gt = m.codes = 0;
 #pragma unroll
-    for (int i = 0; i < 16; i++) {
-        if (i < nvalid) {
-            u32 b = kg_byte_of(v, i);
-            if (b == '>') eff = KG_EFF_SET;
-            else if (b == '\n') eff = KG_EFF_CLEAR;
-        }
+    for (int i = 0; i < 4; i++) {
+        const u32 x = w[i], t = x & 0xDFDFDFDFu;                 // fold case
+        const u32 b4 = __vcmpeq4(t, 0x41414141u) | __vcmpeq4(t, 0x43434343u) | __vcmpeq4(t, 0x47474747u) | __vcmpeq4(t, 0x54545454u);
+        u32 c2 = (t >> 1) & 0x03030303u;                         // A0 C1 G3 T2
+        c2 ^= (c2 >> 1) & 0x01010101u;                           // A0 C1 G2 T3
+        m.base |= kg_movemask4(b4) << (4 * i);
+        m.nl |= kg_movemask4(__vcmpeq4(x, 0x0A0A0A0Au)) << (4 * i);
+        m.gt |= kg_movemask4(__vcmpeq4(x, 0x3E3E3E3Eu)) << (4 * i);
+        m.codes |= ((c2 * 0x01041040u) >> 24) << (8 * i);
     }
-    return eff;
+    const u32 live = nvalid >= 16 ? 0xFFFFu : ((1u << nvalid) - 1u);
+    m.base &= live; m.nl &= live; m.gt &= live;
+    return m;
+}
+
+// header effect of 16 bytes: '>' => SET (from this byte on), '\n' => CLEAR (from the next byte on); last one wins
+__device__ __forceinline__ u32 kg_hdr_effect16(const KgMasks16& m) {
+    if ((m.gt | m.nl) == 0) return KG_EFF_NONE;
+    return m.gt > m.nl ? KG_EFF_SET : KG_EFF_CLEAR;              // the higher top bit is the later byte
 }
 
 // ---- pass A (FASTA only): per-tile header effect ------------------------------------------------------
@@ -129,8 +155,9 @@ __global__ void __launch_bounds__(KG_PT) kg_hdr_summary(const uint8_t* __restric
     const size_t off = (size_t)blockIdx.x * KG_TILE + (size_t)threadIdx.x * KG_BPT;
     int nvalid = off >= n ? 0 : (n - off >= 16 ? 16 : (int)(n - off));
     uint4 v = kg_load_tile16(in, n, off);
+    const KgMasks16 m = kg_masks16(v, nvalid);
     u32 tot;
-    kg_block_lww_exclusive(kg_hdr_effect16(v, nvalid), sm, &tot);
+    kg_block_lww_exclusive(kg_hdr_effect16(m), sm, &tot);
     if (threadIdx.x == 0) tile_hdr_eff[blockIdx.x] = tot;
 }
 
@@ -166,37 +193,74 @@ struct KgThreadParse {
     u32 pend_eff;   // effect on "pending break" after these bytes
 };
 
+__device__ __forceinline__ u32 kg_bits_from(u32 lo) { return ~((1u << lo) - 1u); }          // bits lo..31
+__device__ __forceinline__ u32 kg_bits_upto(u32 hi) { return hi >= 31 ? ~0u : ((2u << hi) - 1u); }   // bits 0..hi
+
 template <bool FASTA>
-__device__ __forceinline__ KgThreadParse kg_parse16(const uint4& v, int nvalid, u32 in_header) {
+__device__ __forceinline__ KgThreadParse kg_parse16(const KgMasks16& m, int nvalid, u32 in_header) {
     KgThreadParse r;
-    r.nbases = 0; r.bits = 0; r.brk = 0; r.first_needs_pending = 1; r.pend_eff = KG_EFF_NONE;
-    u32 hdr = in_header;
-    u32 pend = 0;  // break seen since the last base inside this thread
-#pragma unroll
-    for (int i = 0; i < 16; i++) {
-        if (i < nvalid) {
-            u32 b = kg_byte_of(v, i);
-            u32 c = kg_classify(b);
-            if (FASTA) {
-                if (c == KG_C_GT) hdr = 1;
-                if (hdr) {
-                    pend = 1;                       // header bytes reset the window
-                    if (c == KG_C_NL) hdr = 0;      // the newline ends the header
-                    continue;
-                }
-                if (c == KG_C_NL) continue;         // newline inside a record is skipped
-            }
-            if (c > 3u) { pend = 1; continue; }     // non-ACGT (PLAIN: newline too) resets the window
-            // a base
-            if (r.nbases == 0) { if (pend) { r.brk |= 1u << 15; r.first_needs_pending = 0; } }
-            else if (pend) r.brk |= 1u << (15 - r.nbases);
-            r.bits |= c << (30 - 2 * r.nbases);
-            r.nbases++;
-            pend = 0;
+    const u32 live = nvalid >= 16 ? 0xFFFFu : ((1u << nvalid) - 1u);
+    u32 B = m.base;                    // bytes that are bases
+    u32 E;                             // break events (bit = position of the byte that breaks the window)
+    if (FASTA) {
+        // header regions: from a '>' (or from byte 0 when we start inside a header) through the next '\n'
+        u32 hdrmask = 0, starts = 0, pos = 0, hdr = in_header;
+        if (hdr) {
+            const u32 nlb = m.nl;
+            starts = 1u;
+            if (nlb) { const u32 e = __ffs(nlb) - 1; hdrmask = kg_bits_upto(e); pos = e + 1; hdr = 0; }
+            else { hdrmask = live; pos = 16; }
         }
+        while (pos < 16) {
+            const u32 g = m.gt & kg_bits_from(pos);
+            if (!g) break;
+            const u32 sb = __ffs(g) - 1;
+            starts |= 1u << sb;
+            const u32 nlb = m.nl & kg_bits_from(sb);
+            if (nlb) { const u32 e = __ffs(nlb) - 1; hdrmask |= kg_bits_from(sb) & kg_bits_upto(e); pos = e + 1; }
+            else { hdrmask |= kg_bits_from(sb) & live; pos = 16; }
+        }
+        B &= ~hdrmask;
+        // a header resets the window (event at its first byte); other non-base bytes outside headers are events,
+        // except '\n', which is skipped inside a record
+        E = (starts | (live & ~(m.base | m.nl) & ~hdrmask)) & live;
+    } else {
+        E = live & ~m.base;           // PLAIN: every non-ACGT byte, newline included, ends the string
     }
-    if (r.nbases > 0) r.pend_eff = pend ? KG_EFF_SET : KG_EFF_CLEAR;
-    else r.pend_eff = pend ? KG_EFF_SET : KG_EFF_NONE;
+    r.nbases = __popc(B);
+    // break flag of a base = an event since the previous base; only the FIRST base after each event gets one
+    u32 brk = 0, ev = E;
+    while (ev) {
+        const u32 e = __ffs(ev) - 1;
+        const u32 after = B & kg_bits_from(e);      // (an event byte is never a base)
+        if (!after) break;
+        const u32 fb = __ffs(after) - 1;
+        brk |= 1u << fb;
+        ev &= kg_bits_from(fb);                     // events up to that base are spent
+    }
+    const u32 lowB = B ? (u32)__ffs(B) - 1 : 32u;
+    r.first_needs_pending = (B && (E & kg_bits_upto(lowB)) == 0) ? 1u : 0u;   // no event before the first base
+    if (B) {
+        const u32 top = 31u - __clz(B);
+        r.pend_eff = (E & kg_bits_from(top)) ? KG_EFF_SET : KG_EFF_CLEAR;      // events after the last base
+    } else {
+        r.pend_eff = E ? KG_EFF_SET : KG_EFF_NONE;
+    }
+    // compact codes and break bits of the base positions (drop every non-base position below the top base)
+    u32 codes = m.codes, holes = B ? (~B & kg_bits_upto(31u - __clz(B))) : 0u;
+    while (holes) {
+        const u32 h = 31u - __clz(holes);           // highest hole first: lower indices stay valid
+        const u32 lowc = (1u << (2 * h)) - 1u, lowb = (1u << h) - 1u;
+        codes = (codes & lowc) | ((codes >> 2) & ~lowc);
+        brk = (brk & lowb) | ((brk >> 1) & ~lowb);
+        holes &= ~(1u << h);
+    }
+    // to the output convention: first base in the TOP bits
+    u32 rev = __brev(codes);
+    rev = ((rev >> 1) & 0x55555555u) | ((rev & 0x55555555u) << 1);
+    r.bits = r.nbases ? (rev & ~((r.nbases >= 16) ? 0u : ((1u << (32 - 2 * r.nbases)) - 1u))) : 0u;
+    r.brk = (__brev(brk) >> 16) & 0xFFFFu;
+    if (r.first_needs_pending == 0 && r.nbases) { /* first base's flag already set by its event */ }
     return r;
 }
 
@@ -209,13 +273,14 @@ __global__ void __launch_bounds__(KG_PT) kg_tile_count(const uint8_t* __restrict
     const size_t off = (size_t)blockIdx.x * KG_TILE + (size_t)threadIdx.x * KG_BPT;
     int nvalid = off >= n ? 0 : (n - off >= 16 ? 16 : (int)(n - off));
     uint4 v = kg_load_tile16(in, n, off);
+    const KgMasks16 m = kg_masks16(v, nvalid);
     u32 hdr_in = 0, tot;
     if (FASTA) {
-        u32 pre = kg_block_lww_exclusive(kg_hdr_effect16(v, nvalid), sm, &tot);
+        u32 pre = kg_block_lww_exclusive(kg_hdr_effect16(m), sm, &tot);
         u32 tile_in = tile_hdr_in[blockIdx.x] ? KG_EFF_SET : KG_EFF_CLEAR;
         hdr_in = kg_lww(tile_in, pre) == KG_EFF_SET;
     }
-    KgThreadParse p = kg_parse16<FASTA>(v, nvalid, hdr_in);
+    KgThreadParse p = kg_parse16<FASTA>(m, nvalid, hdr_in);
     u32 total_bases, pend_tot;
     kg_block_sum_exclusive(p.nbases, sm, &total_bases);
     kg_block_lww_exclusive(p.pend_eff, sm, &pend_tot);
@@ -254,16 +319,17 @@ __global__ void __launch_bounds__(KG_PT) kg_tile_pack(const uint8_t* __restrict_
     const size_t off = (size_t)blockIdx.x * KG_TILE + (size_t)threadIdx.x * KG_BPT;
     int nvalid = off >= n ? 0 : (n - off >= 16 ? 16 : (int)(n - off));
     uint4 v = kg_load_tile16(in, n, off);
+    const KgMasks16 m = kg_masks16(v, nvalid);
     for (u32 i = threadIdx.x; i < KG_TILE / 32 + 2; i += KG_PT) { sw[i] = 0; sb[i] = 0; }
     u32 hdr_in = 0, tot;
     if (FASTA) {
-        u32 pre = kg_block_lww_exclusive(kg_hdr_effect16(v, nvalid), sm, &tot);
+        u32 pre = kg_block_lww_exclusive(kg_hdr_effect16(m), sm, &tot);
         u32 tile_in = tile_hdr_in[blockIdx.x] ? KG_EFF_SET : KG_EFF_CLEAR;
         hdr_in = kg_lww(tile_in, pre) == KG_EFF_SET;
     } else {
         __syncthreads();
     }
-    KgThreadParse p = kg_parse16<FASTA>(v, nvalid, hdr_in);
+    KgThreadParse p = kg_parse16<FASTA>(m, nvalid, hdr_in);
     u32 total_bases, pend_tot;
     u32 base_pre = kg_block_sum_exclusive(p.nbases, sm, &total_bases);
     u32 pend_pre = kg_block_lww_exclusive(p.pend_eff, sm, &pend_tot);
