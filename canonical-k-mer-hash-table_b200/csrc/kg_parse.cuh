@@ -165,16 +165,29 @@ __global__ void __launch_bounds__(KG_PT) kg_hdr_summary(const uint8_t* __restric
 // in_eff[t] -> out_state[t] = state (0/1) at the start of tile t; *state_io: initial state in, final out.
 __global__ void __launch_bounds__(1024) kg_lww_scan(const u32* __restrict__ in_eff, u32* __restrict__ out_state,
                                                     u32 ntiles, u32* state_io) {
-    __shared__ u32 sm[1024];
+    __shared__ u32 sw[32];
     const u32 per = (ntiles + 1023) / 1024;
     const u32 b = threadIdx.x * per, e = min(b + per, ntiles);
+    const u32 lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
     u32 mine = KG_EFF_NONE;
     for (u32 t = b; t < e; t++) mine = kg_lww(mine, in_eff[t]);
-    sm[threadIdx.x] = mine;
+    // inclusive last-writer-wins scan across the 1024 threads: shuffles inside a warp, then across the 32 warps
+    u32 incl = mine;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) { u32 o = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= (u32)d) incl = kg_lww(o, incl); }
+    if (lane == 31) sw[warp] = incl;
     __syncthreads();
-    u32 init = *state_io ? KG_EFF_SET : KG_EFF_CLEAR;
-    u32 pre = init;
-    for (u32 i = 0; i < threadIdx.x; i++) pre = kg_lww(pre, sm[i]);
+    if (warp == 0) {
+        u32 v = sw[lane];
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) { u32 o = __shfl_up_sync(0xffffffffu, v, d); if (lane >= (u32)d) v = kg_lww(o, v); }
+        sw[lane] = v;
+    }
+    __syncthreads();
+    const u32 init = *state_io ? KG_EFF_SET : KG_EFF_CLEAR;
+    u32 excl = __shfl_up_sync(0xffffffffu, incl, 1);
+    if (lane == 0) excl = KG_EFF_NONE;
+    const u32 pre = kg_lww(kg_lww(init, warp ? sw[warp - 1] : KG_EFF_NONE), excl);
     u32 cur = pre;
     for (u32 t = b; t < e; t++) {
         out_state[t] = cur == KG_EFF_SET ? 1u : 0u;
@@ -290,15 +303,25 @@ __global__ void __launch_bounds__(KG_PT) kg_tile_count(const uint8_t* __restrict
 // ---- single-block exclusive sum over tiles; also finalises the stream state ------------------------------
 __global__ void __launch_bounds__(1024) kg_tile_scan(const u32* __restrict__ tile_nbases, u32* __restrict__ tile_off,
                                                      u32 ntiles, KgStream* st) {
-    __shared__ u32 sm[1024];
+    __shared__ u32 sw[32];
     const u32 per = (ntiles + 1023) / 1024;
     const u32 b = threadIdx.x * per, e = min(b + per, ntiles);
+    const u32 lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
     u32 mine = 0;
     for (u32 t = b; t < e; t++) mine += tile_nbases[t];
-    sm[threadIdx.x] = mine;
+    u32 incl = mine;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) { u32 o = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= (u32)d) incl += o; }
+    if (lane == 31) sw[warp] = incl;
     __syncthreads();
-    u32 pre = st->carry_bases;
-    for (u32 i = 0; i < threadIdx.x; i++) pre += sm[i];
+    if (warp == 0) {
+        u32 v = sw[lane];
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) { u32 o = __shfl_up_sync(0xffffffffu, v, d); if (lane >= (u32)d) v += o; }
+        sw[lane] = v;
+    }
+    __syncthreads();
+    const u32 pre = st->carry_bases + (warp ? sw[warp - 1] : 0u) + incl - mine;
     u32 cur = pre;
     for (u32 t = b; t < e; t++) { tile_off[t] = cur; cur += tile_nbases[t]; }
     __syncthreads();
