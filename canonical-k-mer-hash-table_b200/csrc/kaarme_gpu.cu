@@ -352,15 +352,15 @@ extern "C" int kg_create(const kg_config* cfg, kg_ctx** out) {
         bloom_params(cfg->expected_unique, cfg->fpr, &m, &nh);
         if (nh < 1) nh = 1;
         if (nh > 16) nh = 16;
-        // every shard holds m/world bits per filter (rounded up to whole 256-bit blocks, at least one)
+        // every shard holds m/world bits per filter (rounded up to whole 64-bit words, at least one)
         uint64_t m_local = (m + (uint64_t)cfg->world - 1) / (uint64_t)cfg->world;
-        uint64_t nblocks = (m_local + 255) / 256;
-        if (nblocks == 0) nblocks = 1;
+        uint64_t nwords = (m_local + 63) / 64;
+        if (nwords == 0) nwords = 1;
         c->bloom_m = m;
-        c->bloom.nblocks = nblocks;
+        c->bloom.nblocks = nwords;
         c->bloom.nh = nh;
         c->bloom.world = (u32)cfg->world;
-        c->bloom_bytes = nblocks * 64;
+        c->bloom_bytes = nwords * 16;                 // [F1 word][F2 word] pairs: 2m bits, as the reference's interleaved array
         KG_TRY(cudaMalloc(&c->bloom.bits, c->bloom_bytes));
     }
     // partitions: 0 = choose per pass from the table / filter size, 1 = never bucket on one GPU, > 1 = as given
@@ -528,10 +528,12 @@ extern "C" int kg_pass_begin(kg_ctx* c, int pass) {
             stride = 2;
         }
         size_t bytes = (size_t)nslots * stride * sizeof(u64);
-        if (!c->table.slots || bytes != c->table_bytes) {
+        // keep the allocation when the new table fits and is not much smaller (Bloom mode sizes the table from
+        // new_in_second, which moves a little from run to run: do not pay cudaFree + cudaMalloc of GBs for that)
+        if (!c->table.slots || bytes > c->table_bytes || bytes < c->table_bytes / 2) {
             if (c->table.slots) { KG_CUDA(c, cudaFree(c->table.slots)); c->table.slots = nullptr; }
-            KG_CUDA(c, cudaMalloc(&c->table.slots, bytes ? bytes : 16));
-            c->table_bytes = bytes;
+            c->table_bytes = bytes + bytes / 64;
+            KG_CUDA(c, cudaMalloc(&c->table.slots, c->table_bytes ? c->table_bytes : 16));
         }
         c->table.nslots = nslots;
         c->table.stride = stride;

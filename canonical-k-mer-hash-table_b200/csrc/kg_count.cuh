@@ -19,101 +19,59 @@ enum KgSink : int {
     KG_SINK_BLOOM2 = 2   // Bloom pass 2: insert only if F2 admits
 };
 
-// blocked double Bloom filter: block = 64 B = [F1: 256 bits][F2: 256 bits]; all nh bits of a k-mer fall in
-// one block, so a test touches one 32-byte sector per filter (double_bloomfilter.hpp:303-413 touches nh
-// random bytes per filter).  m = bits per filter (main.cpp:404-410), nblocks = m / 256.
+// Word-blocked double Bloom filter.  Filter bit h of the reference (double_bloomfilter.hpp:303-368: bit 2h = filter
+// 1, bit 2h+1 = filter 2 of one interleaved array) becomes: all nh bit positions of a k-mer fall into ONE 64-bit word
+// per filter, the two words sit side by side [F1 word][F2 word] (16 B, one sector).  m = bits per filter
+// (main.cpp:404-410), nwords = m / 64.
+// Why one word: a single atomicOr then is an exact, atomic test-and-set of the whole k-mer.  Of any number of
+// concurrent occurrences of a k-mer exactly one sees "not all bits were set" -- no false negative is possible and
+// new_in_first / new_in_second are exact without the reference's race heuristic ("a bit was set by someone else
+// meanwhile => also put it into filter 2", :401-411), which with ~300k threads working on one L2-resident filter
+// region fired for unrelated k-mers and inflated the false-positive rate to 2.6 % (a 256-bit-block version of this
+// filter; profiles/r01_fullsize_reference_parity.txt shows the admitted singletons).
 struct KgBloom {
-    u32* bits;     // nblocks * 16 words
-    u64 nblocks;
+    u64* bits;     // nwords * 2 words: [F1][F2] pairs
+    u64 nblocks;   // nwords
     u32 nh;        // ceil(h) (main.cpp:417)
-    u32 world;     // shards (the block index uses the in-shard part of the hash)
+    u32 world;     // shards (the word index uses the in-shard part of the hash)
 };
 
-// the nh bit positions of a k-mer inside its 256-bit block, as 8 x 32-bit masks
-__device__ __forceinline__ void kg_bloom_masks(u64 h, u32 nh, u32 (&mask)[8]) {
-#pragma unroll
-    for (int i = 0; i < 8; i++) mask[i] = 0;
+// the nh bit positions of a k-mer inside its 64-bit word (6 hash bits each)
+__device__ __forceinline__ u64 kg_bloom_mask(u64 h, u32 nh) {
     u64 g = kg_fmix64(h ^ 0xA24BAED4963EE407ULL);
+    u64 mask = 0;
     for (u32 i = 0; i < nh; i++) {
-        if ((i & 7u) == 7u) g = kg_fmix64(g + 0x9FB21C651E98DF25ULL);   // every 8th probe: fresh bits
-        const u32 b = (u32)(g >> (8 * (i & 7u))) & 255u;
-        const u32 bit = 1u << (b & 31u), sel = b >> 5;
-        // branch-free select (a per-lane `if` here compiles to 8 divergent regions per probe: ~1600 instructions
-        // per k-mer, which made the filter passes ALU-bound; profiles/r01_bloom2_insert_ncu.txt)
-#pragma unroll
-        for (int w = 0; w < 8; w++) mask[w] |= (sel == (u32)w) ? bit : 0u;
+        if (i == 10) g = kg_fmix64(g + 0x9FB21C651E98DF25ULL);   // 10 probes per 64-bit draw
+        mask |= 1ULL << ((g >> (6 * (i % 10))) & 63ULL);
     }
+    return mask;
 }
-// block index = range partition of the in-shard hash (like the table slot), so a bucket of the partitioned path
-// touches one contiguous region of the filter; the bit positions inside the block come from an independent mix
-__device__ __forceinline__ u64 kg_bloom_block(u64 h, u64 nblocks, u32 world) {
-    return __umul64hi(kg_local_hash(h, world), nblocks);
+// word index = range partition of the in-shard hash (like the table slot), so a bucket of the partitioned path
+// touches one contiguous region of the filter; the bit positions inside the word come from an independent mix
+__device__ __forceinline__ u64 kg_bloom_block(u64 h, u64 nwords, u32 world) {
+    return __umul64hi(kg_local_hash(h, world), nwords);
 }
 
-// pass 1 (insertion_process, double_bloomfilter.hpp:371-413) on the blocked layout.
+// pass 1 (insertion_process, double_bloomfilter.hpp:371-413): in F2 -> done; in F1 -> into F2; else into F1
 __device__ __forceinline__ void kg_bloom_insert(const KgBloom& bf, u64 h, u32& new1, u32& new2) {
-    u32 mask[8];
-    kg_bloom_masks(h, bf.nh, mask);
-    u32* blk = bf.bits + kg_bloom_block(h, bf.nblocks, bf.world) * 16;
-    // F2 first: "in second? done"
-    bool in2 = true;
-    u32 miss2[8];
-    {
-        uint4 a = __ldcg(reinterpret_cast<const uint4*>(blk + 8));
-        uint4 b = __ldcg(reinterpret_cast<const uint4*>(blk + 12));
-        u32 cur[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
-#pragma unroll
-        for (int w = 0; w < 8; w++) { miss2[w] = mask[w] & ~cur[w]; in2 = in2 && (miss2[w] == 0); }
+    const u64 mask = kg_bloom_mask(h, bf.nh);
+    u64* w = bf.bits + kg_bloom_block(h, bf.nblocks, bf.world) * 2;
+    u64 f1, f2;
+    kg_ld_v2(w, f1, f2);
+    if ((f2 & mask) == mask) return;                              // already in the second filter
+    if ((f1 & mask) != mask) {
+        const u64 old1 = atomicOr(w, mask);                       // exact test-and-set of the whole k-mer
+        if ((old1 & mask) != mask) { new1++; return; }            // I am its first occurrence
     }
-    if (in2) return;
-    bool in1 = true;
-    u32 miss1[8];
-    {
-        uint4 a = __ldcg(reinterpret_cast<const uint4*>(blk));
-        uint4 b = __ldcg(reinterpret_cast<const uint4*>(blk + 4));
-        u32 cur[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
-#pragma unroll
-        for (int w = 0; w < 8; w++) { miss1[w] = mask[w] & ~cur[w]; in1 = in1 && (miss1[w] == 0); }
-    }
-    bool to_second = in1;
-    if (!in1) {
-        // set F1; "all_mine" = I flipped every bit that was missing when I looked
-        bool all_mine = true, any_mine = false;
-#pragma unroll
-        for (int w = 0; w < 8; w++)
-            if (miss1[w]) {
-                u32 old = atomicOr(blk + w, miss1[w]);
-                all_mine = all_mine && ((old & miss1[w]) == 0);
-                any_mine = any_mine || ((old & miss1[w]) != miss1[w]);
-            }
-        if (any_mine) new1++;
-        if (!all_mine) to_second = true;  // somebody raced me on a bit: the k-mer was seen twice concurrently (:401-411)
-    }
-    if (to_second) {
-        // The reference counts a k-mer only when ONE thread flipped all of its missing bits (:353-368), which
-        // under-counts when occurrences race (it reports run-to-run variation itself).
-        // With ~300k threads in flight that would under-size the table (main.cpp:454), so count every thread
-        // that flipped at least one bit: exact without races, a slight over-count with them.
-        bool any_mine = false;
-#pragma unroll
-        for (int w = 0; w < 8; w++)
-            if (miss2[w]) { u32 old = atomicOr(blk + 8 + w, miss2[w]); any_mine = any_mine || ((old & miss2[w]) != miss2[w]); }
-        if (any_mine) new2++;
-    }
+    const u64 old2 = atomicOr(w + 1, mask);
+    if ((old2 & mask) != mask) new2++;                            // first to complete it in filter 2
 }
 
 // pass 2 admission (second_contains, double_bloomfilter.hpp:319-337; parallel_parser.hpp:2021-2026)
 __device__ __forceinline__ bool kg_bloom_admits(const KgBloom& bf, u64 h) {
-    u32 mask[8];
-    kg_bloom_masks(h, bf.nh, mask);
-    const u32* blk = bf.bits + kg_bloom_block(h, bf.nblocks, bf.world) * 16 + 8;
-    uint4 a = __ldg(reinterpret_cast<const uint4*>(blk));
-    uint4 b = __ldg(reinterpret_cast<const uint4*>(blk + 4));
-    u32 cur[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
-    bool ok = true;
-#pragma unroll
-    for (int w = 0; w < 8; w++) ok = ok && ((mask[w] & ~cur[w]) == 0);
-    return ok;
+    const u64 mask = kg_bloom_mask(h, bf.nh);
+    const u64 f2 = __ldg(bf.bits + kg_bloom_block(h, bf.nblocks, bf.world) * 2 + 1);
+    return (f2 & mask) == mask;
 }
 
 struct KgCountArgs {
