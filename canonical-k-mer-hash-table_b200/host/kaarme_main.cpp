@@ -50,6 +50,7 @@ struct Args {
     int gpus = 1;
     uint64_t batch_mb = 0;
     bool exact_counts = false;
+    bool print_slices = false;    // --print-slices: show how --gpus N would shard the input, then exit (no GPU needed)
 };
 
 [[noreturn]] void cli_fail(int code, const std::string& msg) {
@@ -168,6 +169,7 @@ Args parse_args(int argc, char** argv) {
             std::string t = value("--batch-mb");
             if (!parse_u64(t, a.batch_mb) || a.batch_mb == 0 || a.batch_mb > 1024) cli_fail(105, "--batch-mb: Value " + t + " not in range 1 to 1024");
         } else if (s == "--exact-counts") a.exact_counts = true;
+        else if (s == "--print-slices") a.print_slices = true;
         else if (s == "--stats-json") a.stats_json = value("--stats-json");
         else if (s.size() > 1 && s[0] == '-' && !(s[1] >= '0' && s[1] <= '9')) cli_fail(109, "The following argument was not expected: " + s);
         else pos.push_back(s);
@@ -396,6 +398,17 @@ int main(int argc, char** argv) {
     if (args.mode == 1) { std::cout << "Chosen mode not recognized\n"; return 0; }       // -m 1 (superseded variant) is out of scope
     if (args.k > 256) { std::cerr << "kaarme: k > 256 is not supported by the GPU build\n"; return 1; }
 
+    if (args.print_slices) {   // host-side sharding only: byte range, context start and header state of every rank
+        int fd = open(args.input.c_str(), O_RDONLY);
+        struct stat st{};
+        fstat(fd, &st);
+        for (int r = 0; r < args.gpus; r++) {
+            const Slice sl = make_slice(fd, st.st_size, r, args.gpus, (uint32_t)args.k, input_mode == KG_INPUT_FASTA);
+            std::cout << "slice " << r << " " << sl.ctx_lo << " " << sl.lo << " " << sl.hi << " " << (sl.in_header ? 1 : 0) << "\n";
+        }
+        close(fd);
+        return 0;
+    }
     if (args.gpus > 1 && args.mode == KG_TABLE_KAARME)
         std::cout << "note: with --gpus > 1 the Kaarme compaction is skipped (k-mers are exported from the sharded plain tables)\n";
 

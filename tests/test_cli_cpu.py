@@ -65,3 +65,35 @@ def test_no_gpu_fails_loudly():
         pytest.skip("GPU present")
     p = run(FA, 21, "-s", 1000)
     assert p.returncode == 2 and "no CPU fallback" in p.stderr
+
+
+@pytest.mark.parametrize("world", [2, 3, 8])
+@pytest.mark.parametrize("name,k", [("g1_multiline.fasta", 21), ("g5_long.fasta", 51), ("g2_reads.fa", 31), ("g3_plain.txt", 21)])
+def test_cli_sharding_matches_python_and_oracle(oracle, name, k, world):
+    """--gpus N host logic of the C++ CLI (make_slice): same slices as kaarme_gpu.slice_context, and counting every
+    rank's slice (context fed but not counted) with the oracle reproduces the whole-file count"""
+    import importlib
+    import numpy as np
+    K = importlib.import_module("canonical-k-mer-hash-table_b200").kaarme_gpu
+    path = os.path.join(GOLDEN, name)
+    data = open(path, "rb").read()
+    mode = oracle.PLAIN if name.endswith(".txt") else oracle.FASTA
+    p = run(path, k, "-s", 1000, "--gpus", world, "--print-slices")
+    assert p.returncode == 0, p.stderr
+    rows = [list(map(int, ln.split()[1:])) for ln in p.stdout.splitlines() if ln.startswith("slice ")]
+    assert len(rows) == world
+    total = {}
+    windows = 0
+    for r, (rank, ctx_lo, lo, hi, hdr) in enumerate(rows):
+        assert rank == r and (lo, hi) == K.shard_ranges(len(data), world)[r]
+        assert (ctx_lo, bool(hdr)) == K.slice_context(data, lo, k, K.INPUT_PLAIN if mode == oracle.PLAIN else K.INPUT_FASTA)
+        a = oracle.count(data[ctx_lo:hi], k, mode, bool(hdr))
+        b = oracle.count(data[ctx_lo:lo], k, mode, bool(hdr))
+        windows += a.total_windows - b.total_windows
+        for c, sign in ((a, 1), (b, -1)):
+            for kk, cc in zip(map(bytes, c.keys.view(np.uint8).reshape(c.n, c.W * 8)), c.counts.tolist()):
+                total[kk] = total.get(kk, 0) + sign * cc
+    whole = oracle.count(data, k, mode)
+    assert windows == whole.total_windows
+    want = dict(zip(map(bytes, whole.keys.view(np.uint8).reshape(whole.n, whole.W * 8)), whole.counts.tolist()))
+    assert {kk: cc for kk, cc in total.items() if cc} == want
