@@ -305,7 +305,7 @@ def main():
     tp = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(tp):
         tj = json.load(open(tp)).get(kernel.split("<")[0], {})
-        if tj.get("dram_bytes_per_kmer") is not None:
+        if tj.get("dram_bytes_per_kmer") is not None and tj.get("W") == W:   # the capture was taken at k=51 (W=2)
             traffic = tj["dram_bytes_per_kmer"] * kmers_in_kernel / max(1, insert_launches)
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": traffic, "kernel": kernel, "peak_source": peak_src,

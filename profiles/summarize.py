@@ -61,7 +61,7 @@ def raw(rep, out, header, kmers):
         return v * {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "Tbyte": 1e12}[unit]
     rd = sum(to_bytes(v, u) for v, u in res["dram__bytes_read.sum"]) / len(res["dram__bytes_read.sum"])
     wr = sum(to_bytes(v, u) for v, u in res["dram__bytes_write.sum"]) / len(res["dram__bytes_write.sum"])
-    return {"dram_bytes_per_launch": rd + wr, "dram_bytes_per_kmer": (rd + wr) / kmers, "kmers_per_launch": kmers,
+    return {"W": 2, "k": 51, "dram_bytes_per_launch": rd + wr, "dram_bytes_per_kmer": (rd + wr) / kmers, "kmers_per_launch": kmers,
             "launch_ms": [float(v) for v, _ in res["gpu__time_duration.sum"]]}
 
 
@@ -71,7 +71,7 @@ if __name__ == "__main__":
     t = {}
     t["kg_insert_segs_kernel"] = raw("r01_insert_segs.ncu-rep", "r01_insert_segs_ncu.txt",
                                      "# ncu --set full --clock-control none --import-source on -k regex:kg_insert_segs_kernel -s 2 -c 2 ; python bench.py --scale 0.25 --steps 1 --warmup 1 --no-cpu-baseline --no-e2e\n"
-                                     "# L2-blocked insert (partitions auto = 64, table 1 GB packed 16-byte slots), 248.75 M k-mers per launch\n", kpl)
+                                     "# L2-blocked insert through the segment table (partitions auto = 64, table 1 GB of packed 16-byte slots), 248.75 M k-mers per launch\n", kpl)
     t["kg_count_kernel"] = raw("r01_count_direct.ncu-rep", "r01_count_direct_ncu.txt",
                                "# ncu --set full ... -k regex:kg_count_kernel -s 2 -c 2 ; python bench.py --scale 0.25 ... --partitions 1   (direct, DRAM-random insert)\n", kpl)
     json.dump(t, open(os.path.join(P, "traffic.json"), "w"), indent=1)
