@@ -226,11 +226,9 @@ __global__ void __launch_bounds__(256) kg_count_kernel(KgCountArgs a) {
 }
 
 // insert keys from a key array (received from other shards, or this GPU's partition-major bucket buffer).
-// A block walks KG_KEYS_PER_BLOCK consecutive keys (coalesced); statistics leave the block as one atomic per
+// Blocks walk KG_CHUNK-key chunks (coalesced loads); statistics leave the block as one atomic per
 // counter (one atomic per warp would put millions of RMWs on a single address).
 #define KG_CHUNK 1024u            // keys per work item of the persistent insert kernels
-#define KG_KEYS_PER_THREAD 16
-#define KG_KEYS_PER_BLOCK (256 * KG_KEYS_PER_THREAD)
 
 __device__ __forceinline__ void kg_block_add(u32 v, u64* dst, u32* smem /*8 words*/) {
     for (int d = 16; d; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);

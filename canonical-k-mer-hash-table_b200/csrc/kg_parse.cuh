@@ -11,7 +11,8 @@
 // Both "am I inside a header" and "did a reset happen since the previous base" are last-writer-wins
 // scans, so the batch is processed in 4 KiB tiles with two tiny single-block scans in between:
 //   kg_hdr_summary -> kg_hdr_scan -> kg_tile_count -> kg_tile_scan -> kg_tile_pack
-// All kernels are HBM-streaming: 3 reads of the raw bytes + 0.375 B/base written.
+// All kernels are HBM-streaming: 3 reads of the raw bytes + 0.375 B/base written; the per-byte work is SWAR
+// (kg_masks16 / kg_parse16 below).
 #pragma once
 #include "kg_device.cuh"
 
@@ -23,22 +24,6 @@
 #define KG_EFF_NONE 0u
 #define KG_EFF_SET 1u    // header: enter header   | pending: a break happened after the last base
 #define KG_EFF_CLEAR 2u  // header: leave header   | pending: a base was emitted after the last break
-
-// byte classes
-#define KG_C_NL 4u
-#define KG_C_GT 5u
-#define KG_C_INV 6u
-
-__device__ __forceinline__ u32 kg_classify(u32 b) {
-    u32 u = b & 0xDFu;  // fold case
-    if (u == 0x41u || u == 0x43u || u == 0x47u || u == 0x54u) {
-        u32 c = (u >> 1) & 3u;  // A0 C1 G3 T2
-        return c ^ (c >> 1);    // A0 C1 G2 T3
-    }
-    if (b == '\n') return KG_C_NL;
-    if (b == '>') return KG_C_GT;
-    return KG_C_INV;
-}
 
 __device__ __forceinline__ uint4 kg_load_tile16(const uint8_t* in, size_t n, size_t off) {
     // 16 bytes at `off` (16-byte aligned base pointer + multiple-of-16 offset); bytes past n read as '\n'
@@ -54,11 +39,6 @@ __device__ __forceinline__ uint4 kg_load_tile16(const uint8_t* in, size_t n, siz
     }
     return v;
 }
-__device__ __forceinline__ u32 kg_byte_of(const uint4& v, int i) {
-    u32 w = i < 4 ? v.x : i < 8 ? v.y : i < 12 ? v.z : v.w;
-    return (w >> (8 * (i & 3))) & 0xFFu;
-}
-
 // combine for last-writer-wins: later non-NONE effect overrides
 __device__ __forceinline__ u32 kg_lww(u32 earlier, u32 later) { return later != KG_EFF_NONE ? later : earlier; }
 
