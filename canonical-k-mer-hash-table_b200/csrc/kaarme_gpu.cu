@@ -95,8 +95,10 @@ struct kg_ctx {
     u32 nb_alloc = 0;                   // buckets the scratch below was sized for
     u64 *d_seg[2] = {nullptr, nullptr}, *h_seg[2] = {nullptr, nullptr};   // segment tables (start[nseg+1], src[nseg])
     u32 seg_cap = 0;
-    ncclComm_t comm = nullptr;
-    cudaStream_t s_comm = nullptr, s_insert = nullptr;
+    ncclComm_t comm = nullptr;       // key slices (ncclSend/ncclRecv) on s_comm
+    ncclComm_t ctl_comm = nullptr;   // per-round count all-gather on s_ctl: its own communicator and stream, so the
+                                     // tiny control exchange of round i+1 never queues behind the key transfer of round i
+    cudaStream_t s_comm = nullptr, s_insert = nullptr, s_ctl = nullptr;
     u64* d_send[2] = {nullptr, nullptr};
     u64* d_recv[2] = {nullptr, nullptr};
     size_t send_cap = 0, recv_cap = 0;  // in keys
@@ -250,7 +252,9 @@ static void free_all(kg_ctx* c) {
     cudaFree(c->kaarme.slots); cudaFree(c->kaarme.roots); cudaFree(c->d_cstats); cudaFree(c->d_work);
     if (c->s_comm) cudaStreamSynchronize(c->s_comm);
     if (c->s_insert) cudaStreamSynchronize(c->s_insert);
+    if (c->s_ctl) cudaStreamSynchronize(c->s_ctl);
     if (c->comm) { kg_nccl().CommDestroy(c->comm); c->comm = nullptr; }
+    if (c->ctl_comm) { kg_nccl().CommDestroy(c->ctl_comm); c->ctl_comm = nullptr; }
     for (int i = 0; i < 2; i++) {
         cudaFree(c->d_send[i]); cudaFree(c->d_recv[i]);
         if (c->ev_send_free[i]) cudaEventDestroy(c->ev_send_free[i]);
@@ -263,6 +267,7 @@ static void free_all(kg_ctx* c) {
     for (cudaEvent_t e : {c->ev_counts, c->ev_scatter, c->ev_matrix, c->ev_pass_ready, c->ev_tail}) if (e) cudaEventDestroy(e);
     if (c->s_comm) cudaStreamDestroy(c->s_comm);
     if (c->s_insert) cudaStreamDestroy(c->s_insert);
+    if (c->s_ctl) cudaStreamDestroy(c->s_ctl);
     cudaFree(c->d_tile_hdr_eff); cudaFree(c->d_tile_hdr_in); cudaFree(c->d_tile_nbases);
     cudaFree(c->d_tile_pend_eff); cudaFree(c->d_tile_pend_in); cudaFree(c->d_tile_off);
     cudaFree(c->d_words); cudaFree(c->d_brk); cudaFree(c->d_carry_words); cudaFree(c->d_carry_brk);
@@ -372,6 +377,7 @@ extern "C" int kg_create(const kg_config* cfg, kg_ctx** out) {
         c->recv_cap = cfg->world > 1 ? 2 * c->send_cap : 0;      // single GPU inserts straight from the send buffer
         KG_TRY(cudaStreamCreateWithFlags(&c->s_comm, cudaStreamNonBlocking));
         KG_TRY(cudaStreamCreateWithFlags(&c->s_insert, cudaStreamNonBlocking));
+        KG_TRY(cudaStreamCreateWithFlags(&c->s_ctl, cudaStreamNonBlocking));
         for (int i = 0; i < 2; i++) {
             KG_TRY(cudaEventCreateWithFlags(&c->ev_send_free[i], cudaEventDisableTiming));
             KG_TRY(cudaEventCreateWithFlags(&c->ev_recv_free[i], cudaEventDisableTiming));
@@ -409,13 +415,14 @@ extern "C" int kg_destroy(kg_ctx* c) {
 
 extern "C" int kg_comm_unique_id(void* id_out) {
     if (!id_out) return KG_EBADARG;
-    static_assert(sizeof(ncclUniqueId) <= KG_UNIQUE_ID_BYTES, "unique id size");
-    ncclUniqueId id;
+    static_assert(2 * sizeof(ncclUniqueId) <= KG_UNIQUE_ID_BYTES, "unique id size");
+    ncclUniqueId id[2];
     kg_ctx* none = nullptr;
     if (!kg_nccl().ok) { g_err = "libnccl.so.2 could not be loaded"; return KG_ENCCL; }
-    KG_NCCL(none, kg_nccl().GetUniqueId(&id));
+    KG_NCCL(none, kg_nccl().GetUniqueId(&id[0]));     // key transfers
+    KG_NCCL(none, kg_nccl().GetUniqueId(&id[1]));     // control (count all-gather)
     memset(id_out, 0, KG_UNIQUE_ID_BYTES);
-    memcpy(id_out, &id, sizeof(id));
+    memcpy(id_out, id, sizeof(id));
     return KG_OK;
 }
 
@@ -423,14 +430,14 @@ extern "C" int kg_comm_init(kg_ctx* c, const void* id, int rank, int world) {
     if (!c || !id) return KG_EBADARG;
     if (rank != c->cfg.rank || world != c->cfg.world || world < 2) { c->err = "kg_comm_init: rank/world differ from kg_config"; return KG_EBADARG; }
     KG_CUDA(c, cudaSetDevice(c->cfg.device));
-    ncclUniqueId uid;
-    memcpy(&uid, id, sizeof(uid));
+    ncclUniqueId uid[2];
+    memcpy(uid, id, sizeof(uid));
     if (!kg_nccl().ok) { c->err = "libnccl.so.2 could not be loaded"; return KG_ENCCL; }
-    KG_NCCL(c, kg_nccl().CommInitRank(&c->comm, world, uid, rank));
+    KG_NCCL(c, kg_nccl().CommInitRank(&c->comm, world, uid[0], rank));
+    KG_NCCL(c, kg_nccl().CommInitRank(&c->ctl_comm, world, uid[1], rank));
     return KG_OK;
 }
 
-// -----------------------------------------------------------------------------------------------------------
 // Decide how the coming pass buckets its batches and size the scratch for it.  region_bytes = what the inserts
 // of this pass hit at random (count table, or the Bloom filter): local partitions are chosen so that one
 // partition's region is ~16-32 MiB, comfortably L2-resident next to the streaming keys.
@@ -733,10 +740,10 @@ static int exchange_round(kg_ctx* c, bool have_batch, bool* all_done) {
         KG_CUDA(c, cudaMemsetAsync(c->d_bucket_counts + nb, 1, sizeof(u32), c->s_compute));   // non-zero = done
         KG_CUDA(c, cudaEventRecord(c->ev_counts, c->s_compute));
     }
-    KG_CUDA(c, cudaStreamWaitEvent(c->s_comm, c->ev_counts, 0));
-    KG_NCCL(c, kg_nccl().AllGather(c->d_bucket_counts, c->d_matrix, row, ncclUint32, c->comm, c->s_comm));
-    KG_CUDA(c, cudaMemcpyAsync(c->h_matrix, c->d_matrix, sizeof(u32) * row * world, cudaMemcpyDeviceToHost, c->s_comm));
-    KG_CUDA(c, cudaEventRecord(c->ev_matrix, c->s_comm));
+    KG_CUDA(c, cudaStreamWaitEvent(c->s_ctl, c->ev_counts, 0));
+    KG_NCCL(c, kg_nccl().AllGather(c->d_bucket_counts, c->d_matrix, row, ncclUint32, c->ctl_comm, c->s_ctl));
+    KG_CUDA(c, cudaMemcpyAsync(c->h_matrix, c->d_matrix, sizeof(u32) * row * world, cudaMemcpyDeviceToHost, c->s_ctl));
+    KG_CUDA(c, cudaEventRecord(c->ev_matrix, c->s_ctl));
     KG_CUDA(c, cudaEventSynchronize(c->ev_matrix));
     const u32* M = c->h_matrix;   // M[r*row + b] = keys rank r holds for bucket b; M[r*row + nb] = done flag
     auto to_owner = [&](u32 r, u32 d) { u64 t = 0; for (u32 p = 0; p < pl; p++) t += M[r * row + d * pl + p]; return t; };
@@ -759,7 +766,7 @@ static int exchange_round(kg_ctx* c, bool have_batch, bool* all_done) {
         for (u64 sr = 0; sr < S; sr++) {
             const int rb = (int)(c->subround & 1);
             KG_CUDA(c, cudaStreamWaitEvent(c->s_comm, c->ev_recv_free[rb], 0));
-            if (sr >= 2) KG_CUDA(c, cudaEventSynchronize(c->ev_recv_full[rb]));   // h_seg[rb] was uploaded
+            KG_CUDA(c, cudaEventSynchronize(c->ev_recv_full[rb]));   // the previous upload of h_seg[rb] has been consumed
             std::vector<u64> recv_off(world + 1, 0), rlo_of(world), rhi_of(world);
             KG_NCCL(c, kg_nccl().GroupStart());
             for (u32 peer = 0; peer < world; peer++) {

@@ -105,8 +105,8 @@ def lib():
 
 
 def comm_unique_id() -> bytes:
-    """rank 0 calls this and broadcasts the 128 bytes (e.g. torch.distributed.broadcast_object_list)."""
-    buf = C.create_string_buffer(128)
+    """rank 0 calls this and broadcasts the 256 bytes (e.g. torch.distributed.broadcast_object_list)."""
+    buf = C.create_string_buffer(256)
     rc = lib().kg_comm_unique_id(buf)
     if rc:
         raise KaarmeError(rc, "kg_comm_unique_id", lib().kg_last_error(None).decode())
@@ -179,7 +179,7 @@ class Counter:
 
     # -- the ABI ------------------------------------------------------------------------------------------
     def comm_init(self, unique_id: bytes, rank: int, world: int):
-        buf = C.create_string_buffer(unique_id, 128)
+        buf = C.create_string_buffer(unique_id, 256)
         self._check(lib().kg_comm_init(self._h, buf, rank, world), "kg_comm_init")
 
     def pass_begin(self, which):

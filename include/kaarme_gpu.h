@@ -138,7 +138,7 @@ int kg_host_alloc(size_t bytes, void** out);
 int kg_host_free(void* p);
 
 /* ---- multi-GPU (one context per GPU; shards own disjoint hash ranges) --------------------------- */
-#define KG_UNIQUE_ID_BYTES 128
+#define KG_UNIQUE_ID_BYTES 256 /* two NCCL unique ids: key transfers and the control all-gather */
 int kg_comm_unique_id(void* id_out);                                   /* rank 0, then broadcast    */
 int kg_comm_init(kg_ctx* ctx, const void* id, int rank, int world);    /* collective                */
 
