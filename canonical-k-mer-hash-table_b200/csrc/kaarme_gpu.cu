@@ -548,7 +548,16 @@ extern "C" int kg_pass_begin(kg_ctx* c, int pass) {
         c->table.world = (u32)c->cfg.world;
         c->table.packed_tb = packed_tb;
         KG_CUDA(c, cudaMemsetAsync(c->table.slots, 0, bytes, c->s_compute));
-        { int rc = setup_pass_buckets(c, bytes); if (rc) return rc; }
+        {
+            // the partition count must be identical on every rank (it fixes the bucket layout of the exchange):
+            // derive it from configuration only.  After a Bloom pass the shard tables differ a little in size
+            // (2 x the LOCAL new_in_second), so use the configured estimate there.
+            size_t region = bytes;
+            if (c->cfg.world > 1 && c->cfg.use_bloom)
+                region = (size_t)(2 * c->cfg.expected_unique / (uint64_t)c->cfg.world) * stride * sizeof(u64);
+            int rc = setup_pass_buckets(c, region);
+            if (rc) return rc;
+        }
     }
     if (c->pass_bucketed) {   // inserts run on their own stream: order them after the clears above
         KG_CUDA(c, cudaEventRecord(c->ev_pass_ready, c->s_compute));
