@@ -737,7 +737,8 @@ static void launch_reserve(kg_ctx* c, const KgReserveArgs& a, u32 nwords, int si
 // filled by bucket_batch; otherwise the rank contributes nothing and reports "done".  Returns via *all_done
 // whether every rank reported done in this round.
 //   buckets are owner-major: owner d holds buckets [d*pl, (d+1)*pl) = its local partitions, in table order
-//   s_comm:   all-gather of the per-bucket counts -> host; grouped ncclSend/ncclRecv of the key slices
+//   s_ctl:    all-gather of the per-bucket counts -> host (own communicator, never behind a key transfer)
+//   s_comm:   grouped ncclSend/ncclRecv of the key slices
 //   s_insert: insert kernel over what arrived (partition-major across senders through a segment table),
 //             overlapping the next batch's parse + bucketing on s_compute
 static int exchange_round(kg_ctx* c, bool have_batch, bool* all_done) {
