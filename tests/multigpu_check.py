@@ -28,7 +28,7 @@ def main():
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     failures = 0
     for k, use_bloom, uneven, npart in ((51, False, False, 1), (31, False, True, 4), (127, False, False, 16), (51, True, False, 8),
-                                       (51, False, True, 0), (21, True, True, 32)):
+                                       (51, False, True, 0), (21, True, True, 32), (31, True, False, 0)):
         rng = np.random.default_rng(1234 + k)
         data = make_fasta(rng, 200000, 600, 2000, wrap=80, err=0.01, n_rate=0.0003)
         truth = oracle.count(data, k)
