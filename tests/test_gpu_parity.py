@@ -399,3 +399,23 @@ def test_partition_overflow_falls_back_to_direct_insert(oracle):
     want51 = oracle.count(data, 51)
     keys, counts, st = gpu_count(data, 51, batch_bytes=65536, partitions=16)
     assert_same(keys, counts, want51)
+
+
+# ---- file-level mirrors of the reference functors (parallel_parser.hpp:229,1181,1577,2255) ---------------------------
+@pytest.mark.parametrize("fn,mode,bloom", [("parse_input_atomic_flag", 0, False), ("parse_input_pointer_atomic_variable", 2, False),
+                                           ("parse_input_atomic_flag_BF", 0, True), ("parse_input_pointer_atomic_variable_BF", 2, True)])
+def test_functor_mirrors(tmp_path, fn, mode, bloom):
+    # (the reference's sorted -m 0 and -m 2 outputs are identical while counts stay below 16 384, SURVEY section 8;
+    #  the golden set holds the no-Bloom g5 run for -m 0 only)
+    case = [c for c in CASES if c["input"] == "g5_long.fasta" and c["k"] == 51 and c["a"] == 2
+            and bool(c["unique"]) == bloom and (c["mode"] == mode or not bloom)][0]
+    out = tmp_path / "out.txt"
+    f = getattr(kg, fn)
+    src = os.path.join(GOLDEN, "g5_long.fasta")
+    if bloom:
+        f(src, str(out), 51, case["unique"], case["fpr"], 2)
+    else:
+        f(src, str(out), 51, case["slots"], 2)
+    lines = sorted(out.read_bytes().splitlines(keepends=True))
+    assert len(lines) == case["n_lines"]
+    assert hashlib.sha256(b"".join(lines)).hexdigest() == case["sha256"]

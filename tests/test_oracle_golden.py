@@ -112,3 +112,14 @@ def test_live_reference(oracle, tmp_path, k, mode):
     path.write_text("".join(recs))
     ref, _ = oracle.run_ref(str(path), k, mode=mode, slots=300000, min_abundance=2)
     assert oracle.count(path.read_bytes(), k).text(2, mode) == ref
+
+
+def test_binding_text_formatter_matches_oracle_writer(oracle):
+    """kaarme_gpu.keys_to_text (used by tests and the file-level mirrors) == the oracle's restatement of the
+    reference writer, for every key width"""
+    import importlib
+    kg = importlib.import_module("canonical-k-mer-hash-table_b200")
+    data = _read("g1_multiline.fasta")
+    for k in (5, 21, 32, 33, 51, 64, 127, 255):
+        c = oracle.count(data, k)
+        assert kg.keys_to_text(c.keys, c.counts, k) == c.text(1)
