@@ -18,6 +18,7 @@
 #include "kg_device.cuh"
 #include "kg_kaarme.cuh"
 #include "kg_parse.cuh"
+#include "kg_text.cuh"
 
 #define KG_MAX_W 8
 #define KG_DISPATCH_W(W_, fn, ...)                     \
@@ -87,6 +88,13 @@ struct kg_ctx {
     u32* h_out_n = nullptr;
     size_t out_chunk = 0;
     cudaEvent_t ev_out[2] = {nullptr, nullptr};
+    // GPU-side text dump (kg_export_text): formatted lines, double-buffered
+    char* d_text[2] = {nullptr, nullptr};
+    char* h_text[2] = {nullptr, nullptr};
+    u64* d_text_cur[2] = {nullptr, nullptr};   // bytes written into d_text[i] by the format kernel
+    u64* h_text_cur = nullptr;                 // pinned, 2 words
+    size_t text_cap = 0;                       // bytes per text buffer
+    bool text_configured = false;
     // bucketed path (multi-GPU exchange, or partitions > 1 on one GPU)
     bool bucketed = false;              // this context may bucket (streams/events exist)
     bool pass_bucketed = false;         // the current pass buckets its batches
@@ -247,8 +255,11 @@ static void free_all(kg_ctx* c) {
         if (c->h_out_keys[i]) cudaFreeHost(c->h_out_keys[i]);
         if (c->h_out_counts[i]) cudaFreeHost(c->h_out_counts[i]);
         if (c->ev_out[i]) cudaEventDestroy(c->ev_out[i]);
+        cudaFree(c->d_text[i]); cudaFree(c->d_text_cur[i]);
+        if (c->h_text[i]) cudaFreeHost(c->h_text[i]);
     }
     if (c->h_out_n) cudaFreeHost(c->h_out_n);
+    if (c->h_text_cur) cudaFreeHost(c->h_text_cur);
     cudaFree(c->kaarme.slots); cudaFree(c->kaarme.roots); cudaFree(c->d_cstats); cudaFree(c->d_work);
     if (c->s_comm) cudaStreamSynchronize(c->s_comm);
     if (c->s_insert) cudaStreamSynchronize(c->s_insert);
@@ -1201,11 +1212,17 @@ static void launch_export(kg_ctx* c, u64 b, u64 e, uint64_t min_ab, int count_mo
     c->launches++;
 }
 
-extern "C" int kg_export(kg_ctx* c, uint64_t min_abundance, int count_mode, kg_sink_fn sink, void* user) {
-    if (!c || !sink || (!c->table.slots && !c->compacted)) return KG_EBADARG;
+#define KG_TEXT_BUFFER_BYTES (64ull << 20)
+
+// Shared driver of kg_export (records) and kg_export_text (formatted lines).  The table (or the compact structure)
+// is scanned in chunks; chunk i is compacted (and formatted) on the compute stream while the host hands chunk i-1
+// to the sink.
+static int export_impl(kg_ctx* c, uint64_t min_abundance, int count_mode, kg_sink_fn sink, kg_text_sink_fn tsink, void* user) {
+    if (!c || (!sink && !tsink) || (!c->table.slots && !c->compacted)) return KG_EBADARG;
     if (min_abundance == 0) return KG_OK;  // parallel_parser.hpp:860-861
     KG_CUDA(c, cudaSetDevice(c->cfg.device));
     const int W = c->W;
+    const bool text = tsink != nullptr;
     if (!c->out_chunk) {
         c->out_chunk = (16u << 20) / (size_t)W;
         for (int i = 0; i < 2; i++) {
@@ -1217,13 +1234,41 @@ extern "C" int kg_export(kg_ctx* c, uint64_t min_abundance, int count_mode, kg_s
         }
         KG_CUDA(c, cudaHostAlloc((void**)&c->h_out_n, 2 * sizeof(u32), cudaHostAllocDefault));
     }
+    size_t chunk = c->out_chunk;           // table slots (= upper bound on records) per chunk
+    const u32 line_bound = kg_line_bound(c->cfg.k);
+    const size_t text_smem = 16 + (size_t)KG_TEXT_TPB * line_bound;
+    if (text) {
+        if (!c->text_cap) {
+            for (int i = 0; i < 2; i++) {
+                KG_CUDA(c, cudaMalloc(&c->d_text[i], KG_TEXT_BUFFER_BYTES));
+                KG_CUDA(c, cudaMalloc(&c->d_text_cur[i], sizeof(u64)));
+                KG_CUDA(c, cudaHostAlloc((void**)&c->h_text[i], KG_TEXT_BUFFER_BYTES, cudaHostAllocDefault));
+            }
+            KG_CUDA(c, cudaHostAlloc((void**)&c->h_text_cur, 2 * sizeof(u64), cudaHostAllocDefault));
+            c->text_cap = KG_TEXT_BUFFER_BYTES;
+        }
+        if (!c->text_configured) {
+            KG_CUDA(c, cudaFuncSetAttribute(kg_format_text, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                            (int)(16 + (size_t)KG_TEXT_TPB * kg_line_bound(KG_MAX_K))));
+            c->text_configured = true;
+        }
+        const size_t fit = c->text_cap / line_bound;      // records whose lines always fit one text buffer
+        if (fit < chunk) chunk = fit;
+    }
     const u64 nslots = c->compacted ? c->kaarme.n_kmers : c->table.nslots;
-    const u64 nchunks = (nslots + c->out_chunk - 1) / c->out_chunk;
+    const u64 nchunks = (nslots + chunk - 1) / chunk;
     auto finish = [&](u64 i) -> int {
         const int b = (int)(i & 1);
         KG_CUDA(c, cudaEventSynchronize(c->ev_out[b]));
         const u32 n = c->h_out_n[b];
-        if (n) {
+        if (!n) return KG_OK;
+        if (text) {
+            const u64 bytes = c->h_text_cur[b];
+            if (bytes > c->text_cap) { c->err = "kg_export_text: text buffer overrun"; return KG_ECUDA; }
+            KG_CUDA(c, cudaMemcpyAsync(c->h_text[b], c->d_text[b], (size_t)bytes, cudaMemcpyDeviceToHost, c->s_copy));
+            KG_CUDA(c, cudaStreamSynchronize(c->s_copy));
+            if (tsink(user, c->h_text[b], (size_t)bytes, n) != 0) return KG_ESINK;
+        } else {
             KG_CUDA(c, cudaMemcpyAsync(c->h_out_keys[b], c->d_out_keys[b], (size_t)n * W * sizeof(u64), cudaMemcpyDeviceToHost, c->s_copy));
             KG_CUDA(c, cudaMemcpyAsync(c->h_out_counts[b], c->d_out_counts[b], (size_t)n * sizeof(u32), cudaMemcpyDeviceToHost, c->s_copy));
             KG_CUDA(c, cudaStreamSynchronize(c->s_copy));
@@ -1233,7 +1278,7 @@ extern "C" int kg_export(kg_ctx* c, uint64_t min_abundance, int count_mode, kg_s
     };
     for (u64 i = 0; i < nchunks; i++) {
         const int b = (int)(i & 1);
-        const u64 sb = i * c->out_chunk, se = sb + c->out_chunk < nslots ? sb + c->out_chunk : nslots;
+        const u64 sb = i * chunk, se = sb + chunk < nslots ? sb + chunk : nslots;
         KG_CUDA(c, cudaMemsetAsync(c->d_out_n[b], 0, sizeof(u32), c->s_compute));
         switch (W) {
             case 1: launch_export<1>(c, sb, se, min_abundance, count_mode, b); break;
@@ -1244,6 +1289,14 @@ extern "C" int kg_export(kg_ctx* c, uint64_t min_abundance, int count_mode, kg_s
             case 6: launch_export<6>(c, sb, se, min_abundance, count_mode, b); break;
             case 7: launch_export<7>(c, sb, se, min_abundance, count_mode, b); break;
             case 8: launch_export<8>(c, sb, se, min_abundance, count_mode, b); break;
+        }
+        if (text) {
+            KG_CUDA(c, cudaMemsetAsync(c->d_text_cur[b], 0, sizeof(u64), c->s_compute));
+            const u32 grid = (u32)((se - sb + KG_TEXT_TPB - 1) / KG_TEXT_TPB);   // upper bound; blocks past *n exit
+            kg_format_text<<<grid, KG_TEXT_TPB, text_smem, c->s_compute>>>(c->d_out_keys[b], c->d_out_counts[b], c->d_out_n[b],
+                                                                        (u32)W, c->cfg.k, c->d_text[b], c->d_text_cur[b]);
+            c->launches++;
+            KG_CUDA(c, cudaMemcpyAsync(&c->h_text_cur[b], c->d_text_cur[b], sizeof(u64), cudaMemcpyDeviceToHost, c->s_compute));
         }
         KG_CUDA(c, cudaMemcpyAsync(&c->h_out_n[b], c->d_out_n[b], sizeof(u32), cudaMemcpyDeviceToHost, c->s_compute));
         KG_CUDA(c, cudaEventRecord(c->ev_out[b], c->s_compute));
@@ -1259,11 +1312,48 @@ extern "C" int kg_export(kg_ctx* c, uint64_t min_abundance, int count_mode, kg_s
     return KG_OK;
 }
 
+extern "C" int kg_export(kg_ctx* c, uint64_t min_abundance, int count_mode, kg_sink_fn sink, void* user) {
+    if (!sink) return KG_EBADARG;
+    return export_impl(c, min_abundance, count_mode, sink, nullptr, user);
+}
+
+extern "C" int kg_export_text(kg_ctx* c, uint64_t min_abundance, int count_mode, kg_text_sink_fn sink, void* user) {
+    if (!sink) return KG_EBADARG;
+    return export_impl(c, min_abundance, count_mode, nullptr, sink, user);
+}
+
 extern "C" int kg_kaarme_download(kg_ctx* c, uint64_t* slots, uint64_t* roots) {
     if (!c || !c->compacted) return KG_EBADARG;
     KG_CUDA(c, cudaSetDevice(c->cfg.device));
     if (slots && c->kaarme.n_kmers) KG_CUDA(c, cudaMemcpy(slots, c->kaarme.slots, sizeof(u64) * c->kaarme.n_kmers, cudaMemcpyDeviceToHost));
     if (roots && c->kaarme.n_roots) KG_CUDA(c, cudaMemcpy(roots, c->kaarme.roots, sizeof(u64) * c->kaarme.n_roots * c->W, cudaMemcpyDeviceToHost));
+    return KG_OK;
+}
+
+extern "C" int kg_kaarme_upload(kg_ctx* c, const uint64_t* slots, uint64_t n_kmers, const uint64_t* roots, uint64_t n_roots) {
+    if (!c) return KG_EBADARG;
+    if (c->cfg.table_mode != KG_TABLE_KAARME || c->cfg.world != 1) { c->err = "kg_kaarme_upload needs a single-GPU KG_TABLE_KAARME context"; return KG_EBADARG; }
+    if (c->pass) { c->err = "kg_kaarme_upload inside a pass"; return KG_EBADARG; }
+    if ((n_kmers && !slots) || (n_roots && !roots)) return KG_EBADARG;
+    if (n_kmers >> 38 || n_roots >> 38) { c->err = "kg_kaarme_upload: indices are 38 bits (kmer.hpp:108)"; return KG_EBADARG; }
+    KG_CUDA(c, cudaSetDevice(c->cfg.device));
+    KG_CUDA(c, cudaStreamSynchronize(c->s_compute));
+    cudaFree(c->kaarme.slots); cudaFree(c->kaarme.roots);
+    c->kaarme = KgKaarme{nullptr, nullptr, 0, 0};
+    c->compacted = false;
+    if (c->table.slots) { cudaFree(c->table.slots); c->table.slots = nullptr; c->table_bytes = 0; }
+    KgKaarme ks{nullptr, nullptr, n_kmers, n_roots};
+    KG_CUDA(c, cudaMalloc(&ks.slots, sizeof(u64) * (n_kmers ? n_kmers : 1)));
+    if (cudaMalloc(&ks.roots, sizeof(u64) * (n_roots ? n_roots : 1) * c->W) != cudaSuccess) {
+        cudaFree(ks.slots); cudaGetLastError(); c->err = "kg_kaarme_upload: out of device memory"; return KG_ENOMEM;
+    }
+    c->kaarme = ks;
+    if (n_kmers) KG_CUDA(c, cudaMemcpy(ks.slots, slots, sizeof(u64) * n_kmers, cudaMemcpyHostToDevice));
+    if (n_roots) KG_CUDA(c, cudaMemcpy(ks.roots, roots, sizeof(u64) * n_roots * c->W, cudaMemcpyHostToDevice));
+    if (!c->d_cstats) KG_CUDA(c, cudaMalloc(&c->d_cstats, sizeof(KgCompactStats)));
+    KG_CUDA(c, cudaMemset(c->d_cstats, 0, sizeof(KgCompactStats)));
+    c->compacted = true;
+    c->counted = true;
     return KG_OK;
 }
 

@@ -7,7 +7,8 @@
 //     -m,--hash-table-type {0,2}   -a,--min-k-abu N   -t,--threads N   -o,--output-file PATH
 //     -b,--use-bfilter  -f,--bfilter-fpr F   exactly one of  -s,--hash-tab-size N | -u,--unq-kmers N
 //   GPU-side extras (do not collide with the reference's flags):
-//     --device N   --gpus N   --batch-mb N   --exact-counts   --stats-json PATH
+//     --device N   --gpus N   --batch-mb N   --exact-counts   --stats-json PATH   --host-format
+//     --dump-kaarme PATH   (-m 2: save the compact structure)      --from-kaarme   (INPUT is such a file: decode it)
 //
 // Exit codes follow the reference: 0 ok; CLI11's 105 (validation), 106 (required), 107 (requires),
 // 109 (unexpected argument); 1 for an ill-formed input file (main.cpp:168-171) or a full table
@@ -33,6 +34,7 @@
 #include <vector>
 
 #include "kaarme_gpu.h"
+#include "kg_reader.hpp"
 
 namespace {
 
@@ -51,6 +53,9 @@ struct Args {
     uint64_t batch_mb = 0;
     bool exact_counts = false;
     bool print_slices = false;    // --print-slices: show how --gpus N would shard the input, then exit (no GPU needed)
+    bool host_format = false;     // --host-format: export (key, count) records and format the lines on host threads
+    std::string dump_kaarme;      // --dump-kaarme PATH: write the compact structure (-m 2, one GPU) as a binary file
+    bool from_kaarme = false;     // --from-kaarme: INPUT is a file written by --dump-kaarme; decode it on the GPU
 };
 
 [[noreturn]] void cli_fail(int code, const std::string& msg) {
@@ -77,7 +82,11 @@ void print_help(const char* argv0) {
                  "  --batch-mb UINT            Raw bytes per device batch in MiB (def. 128)\n"
                  "  --exact-counts             Report true 32-bit counts instead of emulating the reference's\n"
                  "                             16-bit wrap (-m 0) / 14-bit saturation (-m 2)\n"
-                 "  --stats-json TEXT          Write pass statistics and device timings as JSON\n\n"
+                 "  --stats-json TEXT          Write pass statistics and device timings as JSON\n"
+                 "  --host-format              Format the output lines on host threads instead of on the GPU\n"
+                 "  --dump-kaarme TEXT         -m 2, one GPU: also save the compact Kaarme structure (8-byte slots + roots)\n"
+                 "  --from-kaarme              INPUT is a file saved with --dump-kaarme: decode it on the GPU and write\n"
+                 "                             its k-mers with count >= -a (no -s/-u needed)\n\n"
                  "[Exactly 1 of the following options is required]\n"
                  "Mandatory params:\n"
                  "  -s,--hash-tab-size UINT    Hash table size\n"
@@ -170,6 +179,9 @@ Args parse_args(int argc, char** argv) {
             if (!parse_u64(t, a.batch_mb) || a.batch_mb == 0 || a.batch_mb > 1024) cli_fail(105, "--batch-mb: Value " + t + " not in range 1 to 1024");
         } else if (s == "--exact-counts") a.exact_counts = true;
         else if (s == "--print-slices") a.print_slices = true;
+        else if (s == "--host-format") a.host_format = true;
+        else if (s == "--from-kaarme") a.from_kaarme = true;
+        else if (s == "--dump-kaarme") a.dump_kaarme = value("--dump-kaarme");
         else if (s == "--stats-json") a.stats_json = value("--stats-json");
         else if (s.size() > 1 && s[0] == '-' && !(s[1] >= '0' && s[1] <= '9')) cli_fail(109, "The following argument was not expected: " + s);
         else pos.push_back(s);
@@ -185,6 +197,7 @@ Args parse_args(int argc, char** argv) {
     if (pos.size() < 2) cli_fail(106, "KLEN is required");
     if (!parse_i64(pos[1], a.k) || a.k <= 0) cli_fail(105, "KLEN: Value " + pos[1] + " not in range 0 to inf (positive number required)");
     int given = (a.has_s ? 1 : 0) + (a.has_u ? 1 : 0);
+    if (a.from_kaarme && given == 0 && !a.bloom && !a.has_f) return a;   // decoding a saved structure sizes nothing
     if (given == 0) cli_fail(106, "Exactly 1 option from [-s,--hash-tab-size,-u,--unq-kmers] is required");
     if (given == 2) cli_fail(106, "Exactly 1 option from [-s,--hash-tab-size,-u,--unq-kmers] is required and 2 were given");
     if (a.has_u && !a.bloom) cli_fail(107, "--unq-kmers requires --use-bfilter");
@@ -255,33 +268,18 @@ Slice make_slice(int fd, off_t file_size, int rank, int world, uint32_t k, bool 
     return s;
 }
 
-// one pass over this rank's slice: pread(2) into two pinned buffers, feed the GPU while the next read proceeds
-void feed_file(kg_ctx* ctx, const std::string& path, uint8_t* buf[2], size_t buf_bytes, const Slice& sl) {
-    int fd = open(path.c_str(), O_RDONLY);
-    if (fd < 0) { std::cerr << "kaarme: cannot open " << path << "\n"; std::exit(1); }
-#ifdef __linux__
-    posix_fadvise(fd, sl.ctx_lo, sl.hi - sl.ctx_lo, POSIX_FADV_SEQUENTIAL);  // parallel_parser.hpp:280
-#endif
+// one pass over this rank's slice: the reader ring (kg_reader.hpp) fills pinned buffers with concurrent pread(2)s
+// while this thread feeds the GPU; a buffer returns to the ring as soon as kg_feed has copied it to the device
+void feed_file(kg_ctx* ctx, const std::string& path, uint8_t* const* bufs, int nbufs, size_t buf_bytes, const Slice& sl,
+               int io_threads) {
     KG_CHECK(kg_stream_begin(ctx, sl.in_header ? 1 : 0));
-    int which = 0;
-    off_t pos = sl.ctx_lo;
-    while (pos < sl.hi) {
-        // context bytes and counted bytes go in separate feeds
-        const bool context = pos < sl.lo;
-        const off_t end = context ? sl.lo : sl.hi;
-        size_t want = (size_t)std::min<off_t>((off_t)buf_bytes, end - pos), got = 0;
-        while (got < want) {
-            ssize_t r = pread(fd, buf[which] + got, want - got, pos + (off_t)got);
-            if (r < 0) { std::cerr << "kaarme: read error on " << path << "\n"; std::exit(1); }
-            if (r == 0) break;
-            got += (size_t)r;
-        }
-        if (got == 0) break;
-        KG_CHECK(kg_feed(ctx, buf[which], got, context ? KG_FEED_CONTEXT : 0));   // returns once the H2D copy is done
-        which ^= 1;
-        pos += (off_t)got;
+    kg::SliceReader reader(path, sl.ctx_lo, sl.lo, sl.hi, bufs, nbufs, buf_bytes, io_threads);
+    kg::ReadChunk c;
+    while (reader.next(c)) {
+        KG_CHECK(kg_feed(ctx, c.data, c.len, c.context ? KG_FEED_CONTEXT : 0));   // returns once the H2D copy is done
+        reader.release(c.buf);
     }
-    close(fd);
+    if (reader.failed()) { std::cerr << "kaarme: " << reader.error() << "\n"; std::_Exit(1); }
 }
 
 // reusable barrier for the per-GPU host threads
@@ -301,14 +299,24 @@ class Barrier {
 };
 
 struct Writer {
-    FILE* f = nullptr;
+    int fd = -1;
     uint32_t k = 0, W = 0;
     int threads = 1;
     uint64_t written = 0;
     std::vector<std::vector<char>> bufs;
 };
 
-// kmer_hash_table.cpp:2022-2043: k characters, a space, the decimal count, newline
+bool write_all(int fd, const char* p, size_t n) {
+    while (n) {
+        const ssize_t r = write(fd, p, n);
+        if (r < 0) { if (errno == EINTR) continue; return false; }
+        p += r; n -= (size_t)r;
+    }
+    return true;
+}
+
+// kmer_hash_table.cpp:2022-2043: k characters, a space, the decimal count, newline  (--host-format path; the default
+// path receives these lines ready-made from the GPU, csrc/kg_text.cuh)
 size_t format_range(const Writer& w, const uint64_t* keys, const uint32_t* counts, size_t b, size_t e, std::vector<char>& out) {
     const uint32_t k = w.k, W = w.W;
     out.resize((e - b) * (k + 12));
@@ -342,9 +350,55 @@ int sink(void* user, const uint64_t* keys, const uint32_t* counts, size_t n) {
     }
     for (auto& x : th) x.join();
     for (int t = 0; t < T; t++)
-        if (lens[t] && fwrite(w.bufs[t].data(), 1, lens[t], w.f) != lens[t]) return 1;
+        if (lens[t] && !write_all(w.fd, w.bufs[t].data(), lens[t])) return 1;
     w.written += n;
     return 0;
+}
+
+// default: the lines were formatted by kg_format_text on the GPU; the host only writes them
+int text_sink(void* user, const char* text, size_t bytes, size_t records) {
+    Writer& w = *(Writer*)user;
+    if (!write_all(w.fd, text, bytes)) return 1;
+    w.written += records;
+    return 0;
+}
+
+// ---- saved Kaarme structure (--dump-kaarme / --from-kaarme) ----------------------------------------------------
+// little-endian: magic "KAARMEG1", u32 version, u32 k, u32 key words W, u32 flags, u64 n_kmers, u64 n_roots,
+// u64 reserved[3]  (64 bytes), then n_kmers slot words in the bit layout of kmer.hpp:108-123 (pointers are indices
+// into this same array / into the roots), then n_roots * W root words (secondary array, kmer_hash_table.cpp:2144-2145)
+struct KaarmeFileHeader {
+    char magic[8];
+    uint32_t version, k, W, flags;
+    uint64_t n_kmers, n_roots, reserved[3];
+};
+static_assert(sizeof(KaarmeFileHeader) == 64, "header is 64 bytes");
+const char KAARME_MAGIC[8] = {'K', 'A', 'A', 'R', 'M', 'E', 'G', '1'};
+
+bool save_kaarme(const std::string& path, uint32_t k, uint32_t W, const std::vector<uint64_t>& slots, const std::vector<uint64_t>& roots,
+                 uint64_t n_kmers, uint64_t n_roots) {
+    int fd = open(path.c_str(), O_WRONLY | O_CREAT | O_TRUNC, 0644);
+    if (fd < 0) return false;
+    KaarmeFileHeader h;
+    memset(&h, 0, sizeof(h));
+    memcpy(h.magic, KAARME_MAGIC, 8);
+    h.version = 1; h.k = k; h.W = W; h.n_kmers = n_kmers; h.n_roots = n_roots;
+    bool ok = write_all(fd, (const char*)&h, sizeof(h)) && write_all(fd, (const char*)slots.data(), n_kmers * 8) &&
+              write_all(fd, (const char*)roots.data(), n_roots * W * 8);
+    return close(fd) == 0 && ok;
+}
+
+bool load_kaarme(const std::string& path, KaarmeFileHeader& h, std::vector<uint64_t>& slots, std::vector<uint64_t>& roots, std::string& why) {
+    std::ifstream f(path, std::ios::binary);
+    if (!f.read((char*)&h, sizeof(h)) || memcmp(h.magic, KAARME_MAGIC, 8) != 0 || h.version != 1) { why = "not a Kaarme structure file"; return false; }
+    if (h.k < 1 || h.k > KG_MAX_K || h.W != (h.k + 31) / 32 || (h.n_kmers >> 38) || (h.n_roots >> 38)) { why = "bad header"; return false; }
+    struct stat st{};
+    if (stat(path.c_str(), &st) != 0 || (uint64_t)st.st_size != sizeof(h) + 8 * h.n_kmers + 8 * (uint64_t)h.W * h.n_roots) { why = "file size does not match its header"; return false; }
+    slots.resize(h.n_kmers);
+    roots.resize(h.n_roots * h.W);
+    if ((h.n_kmers && !f.read((char*)slots.data(), (std::streamsize)(8 * h.n_kmers))) ||
+        (!roots.empty() && !f.read((char*)roots.data(), (std::streamsize)(8 * roots.size())))) { why = "short read"; return false; }
+    return true;
 }
 
 void json_pass(std::ostream& o, const char* name, const kg_pass_stats& s) {
@@ -355,10 +409,60 @@ void json_pass(std::ostream& o, const char* name, const kg_pass_stats& s) {
       << ", \"count_ms\": " << s.count_ms << "}";
 }
 
+// the product path needs `need` usable sm_100 devices; say so before any file is created
+void require_devices(int need) {
+    int have = 0;
+    const int rc = kg_device_count(&have);
+    if (rc != KG_OK || have < need) {
+        std::cerr << "kaarme: cannot initialise the GPU path: " << (rc != KG_OK ? kg_strerror(rc) : "not enough compute capability 10.x devices")
+                  << " (" << have << " usable, " << need << " needed). This build has no CPU fallback.\n";
+        std::exit(2);
+    }
+}
+
+// --from-kaarme: INPUT is a saved compact structure; the GPU walks the predecessor chains (reconstruct_kmer_in_slot,
+// kmer_hash_table.cpp:3848-4058) and formats every k-mer with count >= -a
+int decode_kaarme_file(const Args& args) {
+    KaarmeFileHeader h;
+    std::vector<uint64_t> slots, roots;
+    std::string why;
+    if (!load_kaarme(args.input, h, slots, roots, why)) { std::cerr << "Input file " << args.input << " is ill-formed (" << why << ")" << std::endl; return 1; }
+    if ((long long)h.k != args.k) { std::cerr << "kaarme: " << args.input << " holds " << h.k << "-mers, KLEN says " << args.k << "\n"; return 1; }
+    require_devices(args.device + 1);
+    std::string output = args.output.empty() ? std::filesystem::path(args.input).replace_extension().filename().string() + ".kaarme_counts" : args.output;
+    kg_ctx* ctx = nullptr;
+    kg_config cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.abi_version = KG_ABI_VERSION; cfg.k = h.k; cfg.table_mode = KG_TABLE_KAARME; cfg.input_mode = KG_INPUT_FASTA;
+    cfg.min_slots = 1; cfg.device = args.device; cfg.world = 1; cfg.partitions = 1; cfg.batch_bytes = 1 << 20;
+    if (kg_create(&cfg, &ctx) != KG_OK) { std::cerr << "kaarme: cannot initialise the GPU path (" << kg_last_error(nullptr) << "). This build has no CPU fallback.\n"; return 2; }
+    KG_CHECK(kg_kaarme_upload(ctx, slots.data(), h.n_kmers, roots.data(), h.n_roots));
+    Writer w;
+    const unsigned hc = std::thread::hardware_concurrency();
+    w.k = h.k; w.W = h.W; w.threads = std::max(1, (args.has_t ? args.threads : (int)std::min(64u, hc ? hc : 3u)) - 2);
+    const auto t0 = std::chrono::high_resolution_clock::now();
+    if (args.min_abundance > 0) {
+        w.fd = open(output.c_str(), O_WRONLY | O_CREAT | O_TRUNC, 0644);
+        if (w.fd < 0) { std::cerr << "kaarme: cannot open output file " << output << "\n"; return 1; }
+        // counts in the structure are already 14-bit saturated (kmer.cpp:699-714): nothing left to emulate
+        if (args.host_format) KG_CHECK(kg_export(ctx, args.min_abundance, KG_COUNT_EXACT, sink, &w));
+        else KG_CHECK(kg_export_text(ctx, args.min_abundance, KG_COUNT_EXACT, text_sink, &w));
+        if (close(w.fd) != 0) { std::cerr << "kaarme: error closing " << output << "\n"; return 1; }
+    }
+    const auto t1 = std::chrono::high_resolution_clock::now();
+    kg_destroy(ctx);
+    std::cout << "Kaarme structure: " << h.n_kmers << " k-mers, " << h.n_roots << " roots, k = " << h.k << "\n";
+    std::cout << "Time used to write k-mers in a file: " << std::chrono::duration_cast<std::chrono::microseconds>(t1 - t0).count() << " microseconds\n";
+    std::cout << "Written k-mers: " << w.written << "\n";                        // kmer_hash_table.cpp:4522-4523
+    std::cout << "Skipped k-mers: " << (h.n_kmers - w.written) << "\n";
+    return 0;
+}
+
 }  // namespace
 
 int main(int argc, char** argv) {
     Args args = parse_args(argc, argv);
+    if (args.from_kaarme) return decode_kaarme_file(args);
     Format fmt = file_format(args.input);
     if (fmt.ill_formed) {
         std::cerr << "Input file " << args.input << " is ill-formed" << std::endl;
@@ -413,9 +517,16 @@ int main(int argc, char** argv) {
         std::cout << "note: with --gpus > 1 the Kaarme compaction is skipped (k-mers are exported from the sharded plain tables)\n";
 
     const int world = args.gpus;
-    const size_t buf_bytes = (args.batch_mb ? args.batch_mb : 128) << 20;
     struct stat fst{};
     stat(args.input.c_str(), &fst);
+    // batch = ring buffer = device batch: --batch-mb (def. 128 MiB), but no larger than a rank's share of the file
+    // (small inputs should not pay for pinning and allocating hundreds of MiB)
+    size_t buf_bytes = (args.batch_mb ? args.batch_mb : 128) << 20;
+    {
+        const size_t share = (size_t)fst.st_size / (size_t)world + (size_t)args.k + 4096;
+        const size_t rounded = std::max<size_t>(1u << 20, (share + (1u << 20) - 1) >> 20 << 20);
+        if (!args.batch_mb && rounded < buf_bytes) buf_bytes = rounded;
+    }
     char nccl_id[KG_UNIQUE_ID_BYTES];
     if (world > 1) {
         kg_ctx* ctx = nullptr;
@@ -426,14 +537,20 @@ int main(int argc, char** argv) {
     std::vector<kg_compact_stats> compact_stats(world);
     std::vector<uint64_t> table_slots(world, 0);
     for (int r = 0; r < world; r++) { memset(&bloom_stats[r], 0, sizeof(kg_pass_stats)); memset(&count_stats[r], 0, sizeof(kg_pass_stats)); memset(&compact_stats[r], 0, sizeof(kg_compact_stats)); }
+    require_devices(args.device + world);   // before anything is created on disk
+    if (!args.dump_kaarme.empty() && (args.mode != KG_TABLE_KAARME || world != 1)) {
+        std::cerr << "kaarme: --dump-kaarme needs -m 2 on one GPU\n";
+        return 1;
+    }
     Writer w;
     w.k = (uint32_t)args.k; w.W = ((uint32_t)args.k + 31) / 32; w.threads = std::max(1, (args.threads - 2) / world);
     std::mutex out_mutex;
     if (args.min_abundance > 0) {
-        w.f = fopen(args.output.c_str(), "wb");
-        if (!w.f) { std::cerr << "kaarme: cannot open output file " << args.output << "\n"; return 1; }
-        setvbuf(w.f, nullptr, _IOFBF, 8 << 20);
+        w.fd = open(args.output.c_str(), O_WRONLY | O_CREAT | O_TRUNC, 0644);
+        if (w.fd < 0) { std::cerr << "kaarme: cannot open output file " << args.output << "\n"; return 1; }
     }
+    const int io_threads = std::max(1, std::min(8, (args.threads - 2) / world));
+    const int nbufs = 3;
     Barrier barrier(world);
     std::chrono::high_resolution_clock::time_point t_bloom0, t_bloom1, t_build0, t_build1, t_write1;
 
@@ -451,7 +568,7 @@ int main(int argc, char** argv) {
         cfg.device = args.device + rank;
         cfg.fpr = args.fpr;
         cfg.expected_unique = args.unique;
-        cfg.batch_bytes = args.batch_mb << 20;
+        cfg.batch_bytes = buf_bytes;
         cfg.rank = rank;
         cfg.world = world;
         {
@@ -463,8 +580,8 @@ int main(int argc, char** argv) {
             }
         }
         if (world > 1) KG_CHECK(kg_comm_init(ctx, nccl_id, rank, world));
-        uint8_t* bufs[2] = {nullptr, nullptr};
-        for (int i = 0; i < 2; i++) KG_CHECK(kg_host_alloc(buf_bytes, (void**)&bufs[i]));
+        uint8_t* bufs[nbufs] = {nullptr, nullptr, nullptr};
+        for (int i = 0; i < nbufs; i++) KG_CHECK(kg_host_alloc(buf_bytes, (void**)&bufs[i]));
         int fd = open(args.input.c_str(), O_RDONLY);
         const Slice sl = make_slice(fd, fst.st_size, rank, world, (uint32_t)args.k, input_mode == KG_INPUT_FASTA);
         close(fd);
@@ -473,7 +590,7 @@ int main(int argc, char** argv) {
             barrier.wait();
             if (rank == 0) { std::cout << "Starting parallel bloom filtering\n"; t_bloom0 = std::chrono::high_resolution_clock::now(); }  // parallel_parser.hpp:2689
             KG_CHECK(kg_pass_begin(ctx, KG_PASS_BLOOM));
-            feed_file(ctx, args.input, bufs, buf_bytes, sl);
+            feed_file(ctx, args.input, bufs, nbufs, buf_bytes, sl, io_threads);
             KG_CHECK(kg_pass_end(ctx, &bloom_stats[rank]));
             barrier.wait();
             if (rank == 0) t_bloom1 = std::chrono::high_resolution_clock::now();
@@ -491,24 +608,45 @@ int main(int argc, char** argv) {
             std::cout << (args.mode == 0 ? "Starting atomic flag basic hash table\n" : "Starting atomic variable pointer hash table\n");
             if (world == 1) std::cout << "Hash table size is: " << table_slots[0] << "\n";  // functions_math.cpp:90
         }
-        feed_file(ctx, args.input, bufs, buf_bytes, sl);
+        feed_file(ctx, args.input, bufs, nbufs, buf_bytes, sl, io_threads);
         KG_CHECK(kg_pass_end(ctx, &count_stats[rank]));
-        if (args.mode == KG_TABLE_KAARME && world == 1) KG_CHECK(kg_compact(ctx, &compact_stats[rank]));
+        if (args.mode == KG_TABLE_KAARME && world == 1) {
+            KG_CHECK(kg_compact(ctx, &compact_stats[rank]));
+            if (!args.dump_kaarme.empty()) {
+                const kg_compact_stats& cs = compact_stats[rank];
+                std::vector<uint64_t> slots(cs.kmers), roots(cs.roots * w.W);
+                KG_CHECK(kg_kaarme_download(ctx, slots.data(), roots.data()));
+                if (!save_kaarme(args.dump_kaarme, w.k, w.W, slots, roots, cs.kmers, cs.roots)) {
+                    std::cerr << "kaarme: cannot write " << args.dump_kaarme << "\n";
+                    std::_Exit(1);
+                }
+            }
+        }
         barrier.wait();
         if (rank == 0) t_build1 = std::chrono::high_resolution_clock::now();
         if (args.min_abundance > 0) {
             // shards own disjoint k-mers and the output order is unspecified: the ranks take turns per chunk
             struct Locked { Writer* w; std::mutex* m; } lk{&w, &out_mutex};
-            auto locked_sink = [](void* user, const uint64_t* keys, const uint32_t* counts, size_t n) -> int {
-                auto* l = static_cast<Locked*>(user);
-                std::lock_guard<std::mutex> g(*l->m);
-                return sink(l->w, keys, counts, n);
-            };
-            KG_CHECK(kg_export(ctx, args.min_abundance, args.exact_counts ? KG_COUNT_EXACT : KG_COUNT_REFERENCE, locked_sink, &lk));
+            const int count_mode = args.exact_counts ? KG_COUNT_EXACT : KG_COUNT_REFERENCE;
+            if (args.host_format) {
+                auto locked_sink = [](void* user, const uint64_t* keys, const uint32_t* counts, size_t n) -> int {
+                    auto* l = static_cast<Locked*>(user);
+                    std::lock_guard<std::mutex> g(*l->m);
+                    return sink(l->w, keys, counts, n);
+                };
+                KG_CHECK(kg_export(ctx, args.min_abundance, count_mode, locked_sink, &lk));
+            } else {
+                auto locked_text = [](void* user, const char* text, size_t bytes, size_t records) -> int {
+                    auto* l = static_cast<Locked*>(user);
+                    std::lock_guard<std::mutex> g(*l->m);
+                    return text_sink(l->w, text, bytes, records);
+                };
+                KG_CHECK(kg_export_text(ctx, args.min_abundance, count_mode, locked_text, &lk));
+            }
         }
         barrier.wait();
         if (rank == 0) t_write1 = std::chrono::high_resolution_clock::now();
-        for (int i = 0; i < 2; i++) kg_host_free(bufs[i]);
+        for (int i = 0; i < nbufs; i++) kg_host_free(bufs[i]);
         kg_destroy(ctx);
     };
     if (world == 1) rank_main(0);
@@ -517,7 +655,7 @@ int main(int argc, char** argv) {
         for (int r = 0; r < world; r++) th.emplace_back(rank_main, r);
         for (auto& t : th) t.join();
     }
-    if (w.f) fclose(w.f);
+    if (w.fd >= 0 && close(w.fd) != 0) { std::cerr << "kaarme: error closing " << args.output << "\n"; return 1; }
 
     // logs, in the reference's order (sums over the shards)
     kg_pass_stats bsum = bloom_stats[0], csum = count_stats[0];

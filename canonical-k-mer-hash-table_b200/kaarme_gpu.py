@@ -62,11 +62,13 @@ class CompactStats(C.Structure):
 
 
 SINK_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.POINTER(C.c_uint64), C.POINTER(C.c_uint32), C.c_size_t)
+TEXT_SINK_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.POINTER(C.c_char), C.c_size_t, C.c_size_t)
 
 EXPORTS = ["kg_abi_version", "kg_strerror", "kg_last_error", "kg_device_count", "kg_create", "kg_destroy",
            "kg_host_alloc", "kg_host_free", "kg_comm_unique_id", "kg_comm_init", "kg_pass_begin",
            "kg_stream_begin", "kg_feed", "kg_feed_device", "kg_pass_end", "kg_compact", "kg_export",
-           "kg_table_info", "kg_atomic_ceiling", "kg_launch_count", "kg_kaarme_download"]
+           "kg_table_info", "kg_atomic_ceiling", "kg_launch_count", "kg_kaarme_download", "kg_export_text",
+           "kg_kaarme_upload"]
 
 _lib = None
 
@@ -100,6 +102,8 @@ def lib():
         L.kg_atomic_ceiling.argtypes = [C.c_int, C.c_uint64, C.c_uint64, C.c_int, C.POINTER(C.c_double)]
         L.kg_launch_count.argtypes = [C.c_void_p, C.POINTER(C.c_uint64)]
         L.kg_kaarme_download.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+        L.kg_export_text.argtypes = [C.c_void_p, C.c_uint64, C.c_int, TEXT_SINK_FN, C.c_void_p]
+        L.kg_kaarme_upload.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64]
         _lib = L
     return _lib
 
@@ -216,6 +220,30 @@ class Counter:
         roots = np.zeros(max(1, st["roots"]) * self.W, np.uint64)
         self._check(lib().kg_kaarme_download(self._h, slots.ctypes.data, roots.ctypes.data), "kg_kaarme_download")
         return slots[:st["kmers"]], roots[:st["roots"] * self.W].reshape(-1, self.W)
+
+    def kaarme_upload(self, slots, roots):
+        """Load a compact structure (as returned by kaarme_download) into this (-m 2, not yet counted) context;
+        export() / export_text() then decode it on the GPU."""
+        slots = np.ascontiguousarray(slots, dtype=np.uint64).reshape(-1)
+        roots = np.ascontiguousarray(roots, dtype=np.uint64).reshape(-1)
+        assert roots.size % self.W == 0
+        self._check(lib().kg_kaarme_upload(self._h, slots.ctypes.data, slots.size, roots.ctypes.data,
+                                           roots.size // self.W), "kg_kaarme_upload")
+        self._compact = {"kmers": int(slots.size), "roots": int(roots.size // self.W)}
+
+    def export_text(self, min_abundance=1, count_mode=COUNT_EXACT):
+        """-> (text bytes, records): the output lines '<KMER> <COUNT>\\n' formatted on the GPU (kg_format_text),
+        in the unspecified order the device produced them."""
+        parts, total = [], [0]
+
+        def sink(user, text, nbytes, records):
+            parts.append(C.string_at(text, nbytes))
+            total[0] += records
+            return 0
+
+        cb = TEXT_SINK_FN(sink)
+        self._check(lib().kg_export_text(self._h, min_abundance, count_mode, cb, None), "kg_export_text")
+        return b"".join(parts), total[0]
 
     def export(self, min_abundance=1, count_mode=COUNT_EXACT, sort=True):
         """-> (keys [n, W] uint64, counts [n] uint32), sorted by key when sort=True."""
@@ -336,9 +364,9 @@ def _run_file(input_file, output_file, k, table_mode, min_abundance, min_slots=0
         stats["count"] = c.run_pass(PASS_COUNT, data)
         if table_mode == TABLE_KAARME:
             stats["compact"] = c.compact()
-        keys, counts = c.export(min_abundance, COUNT_REFERENCE, sort=False)
+        text, stats["written"] = c.export_text(min_abundance, COUNT_REFERENCE)
     with open(output_file, "wb") as f:
-        f.write(keys_to_text(keys, counts, k))
+        f.write(text)
     return stats
 
 

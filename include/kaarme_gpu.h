@@ -121,6 +121,11 @@ typedef struct kg_compact_stats {
  * Return non-zero to abort (kg_export then returns KG_ESINK). Buffers are valid only during the call. */
 typedef int (*kg_sink_fn)(void* user, const uint64_t* keys, const uint32_t* counts, size_t n);
 
+/* Text sink: `bytes` bytes holding `records` complete output lines "<k chars ACGT> <count>\n" -- the writer format
+ * of kmer_hash_table.cpp:2022-2043 -- formatted on the GPU; the host only has to write(2) them.  Line order is
+ * unspecified (as in the reference).  Return non-zero to abort.  The buffer is valid only during the call. */
+typedef int (*kg_text_sink_fn)(void* user, const char* text, size_t bytes, size_t records);
+
 /* ---- lifecycle -------------------------------------------------------------------------------- */
 int kg_abi_version(void);
 const char* kg_strerror(int status);
@@ -165,10 +170,18 @@ int kg_compact(kg_ctx* ctx, kg_compact_stats* stats);
  * parallel_parser.hpp:860-861).  In KG_TABLE_KAARME mode after kg_compact the k-mers are DECODED from
  * the compact structure (chain walk, kmer_hash_table.cpp:3848-4058), not read from the plain table. */
 int kg_export(kg_ctx* ctx, uint64_t min_abundance, int count_mode, kg_sink_fn sink, void* user);
+/* Same selection, but the records reach the sink as finished text lines (replaces the char-by-char ofstream loops of
+ * write_kmers, kmer_hash_table.cpp:2013-2050, and write_kmers_on_disk_separately_even_faster, :4318-4524).     */
+int kg_export_text(kg_ctx* ctx, uint64_t min_abundance, int count_mode, kg_text_sink_fn sink, void* user);
 /* Copy the compact structure to host memory after kg_compact: slots = kmers words (kmer.hpp:108-123 layout,
  * pointers are indices into this same array), roots = roots*W words (the secondary array,
  * kmer_hash_table.cpp:2144-2145).  Either pointer may be NULL.  Sizes come from kg_compact_stats.           */
 int kg_kaarme_download(kg_ctx* ctx, uint64_t* slots, uint64_t* roots);
+/* The inverse: load a compact structure (e.g. one saved with kg_kaarme_download) into a KG_TABLE_KAARME context that
+ * has not counted anything; kg_export / kg_export_text then decode it on the GPU (reconstruct_kmer_in_slot,
+ * kmer_hash_table.cpp:3848-4058).  Malformed chains are detected while decoding (KG_ECUDA from the export), never
+ * followed out of bounds.  Single GPU (world == 1).                                                            */
+int kg_kaarme_upload(kg_ctx* ctx, const uint64_t* slots, uint64_t n_kmers, const uint64_t* roots, uint64_t n_roots);
 /* Table geometry for reports: bytes per slot and slots. */
 int kg_table_info(const kg_ctx* ctx, uint64_t* slots, uint32_t* slot_bytes, uint32_t* key_words);
 
