@@ -86,7 +86,7 @@ struct kg_ctx {
     u64* h_out_keys[2] = {nullptr, nullptr};
     u32* h_out_counts[2] = {nullptr, nullptr};
     u32* h_out_n = nullptr;
-    size_t out_chunk = 0;
+    size_t out_cap_dev = 0, out_cap_host = 0;  // records the device / pinned export buffers can hold
     cudaEvent_t ev_out[2] = {nullptr, nullptr};
     // GPU-side text dump (kg_export_text): formatted lines, double-buffered
     char* d_text[2] = {nullptr, nullptr};
@@ -1223,39 +1223,70 @@ static int export_impl(kg_ctx* c, uint64_t min_abundance, int count_mode, kg_sin
     KG_CUDA(c, cudaSetDevice(c->cfg.device));
     const int W = c->W;
     const bool text = tsink != nullptr;
-    if (!c->out_chunk) {
-        c->out_chunk = (16u << 20) / (size_t)W;
-        for (int i = 0; i < 2; i++) {
-            KG_CUDA(c, cudaMalloc(&c->d_out_keys[i], c->out_chunk * W * sizeof(u64)));
-            KG_CUDA(c, cudaMalloc(&c->d_out_counts[i], c->out_chunk * sizeof(u32)));
-            KG_CUDA(c, cudaMalloc(&c->d_out_n[i], sizeof(u32)));
-            KG_CUDA(c, cudaHostAlloc((void**)&c->h_out_keys[i], c->out_chunk * W * sizeof(u64), cudaHostAllocDefault));
-            KG_CUDA(c, cudaHostAlloc((void**)&c->h_out_counts[i], c->out_chunk * sizeof(u32), cudaHostAllocDefault));
-        }
-        KG_CUDA(c, cudaHostAlloc((void**)&c->h_out_n, 2 * sizeof(u32), cudaHostAllocDefault));
-    }
-    size_t chunk = c->out_chunk;           // table slots (= upper bound on records) per chunk
+    // Slots (= upper bound on records) per chunk: 16 M key words, but never more than the structure holds (a small
+    // input must not pay for pinning hundreds of MiB: cudaHostAlloc costs ~1 ms per MiB) and, for text, never more
+    // than one text buffer can hold.  Buffers grow on demand and are kept for the next export.
+    const u64 nslots = c->compacted ? c->kaarme.n_kmers : c->table.nslots;
     const u32 line_bound = kg_line_bound(c->cfg.k);
     const size_t text_smem = 16 + (size_t)KG_TEXT_TPB * line_bound;
+    size_t chunk = (16u << 20) / (size_t)W;
+    if (text && KG_TEXT_BUFFER_BYTES / line_bound < chunk) chunk = KG_TEXT_BUFFER_BYTES / line_bound;
+    if (nslots < chunk) chunk = (size_t)((nslots + 4095) / 4096 * 4096);
+    if (chunk == 0) chunk = 4096;
+    if (!c->h_out_n) {
+        for (int i = 0; i < 2; i++) KG_CUDA(c, cudaMalloc(&c->d_out_n[i], sizeof(u32)));
+        KG_CUDA(c, cudaHostAlloc((void**)&c->h_out_n, 2 * sizeof(u32), cudaHostAllocDefault));
+    }
+    if (chunk > c->out_cap_dev) {
+        for (int i = 0; i < 2; i++) {
+            cudaFree(c->d_out_keys[i]); cudaFree(c->d_out_counts[i]);
+            c->d_out_keys[i] = nullptr; c->d_out_counts[i] = nullptr;
+        }
+        c->out_cap_dev = 0;
+        for (int i = 0; i < 2; i++) {
+            KG_CUDA(c, cudaMalloc(&c->d_out_keys[i], chunk * W * sizeof(u64)));
+            KG_CUDA(c, cudaMalloc(&c->d_out_counts[i], chunk * sizeof(u32)));
+        }
+        c->out_cap_dev = chunk;
+    }
+    if (!text && chunk > c->out_cap_host) {
+        for (int i = 0; i < 2; i++) {
+            if (c->h_out_keys[i]) cudaFreeHost(c->h_out_keys[i]);
+            if (c->h_out_counts[i]) cudaFreeHost(c->h_out_counts[i]);
+            c->h_out_keys[i] = nullptr; c->h_out_counts[i] = nullptr;
+        }
+        c->out_cap_host = 0;
+        for (int i = 0; i < 2; i++) {
+            KG_CUDA(c, cudaHostAlloc((void**)&c->h_out_keys[i], chunk * W * sizeof(u64), cudaHostAllocDefault));
+            KG_CUDA(c, cudaHostAlloc((void**)&c->h_out_counts[i], chunk * sizeof(u32), cudaHostAllocDefault));
+        }
+        c->out_cap_host = chunk;
+    }
     if (text) {
-        if (!c->text_cap) {
-            for (int i = 0; i < 2; i++) {
-                KG_CUDA(c, cudaMalloc(&c->d_text[i], KG_TEXT_BUFFER_BYTES));
-                KG_CUDA(c, cudaMalloc(&c->d_text_cur[i], sizeof(u64)));
-                KG_CUDA(c, cudaHostAlloc((void**)&c->h_text[i], KG_TEXT_BUFFER_BYTES, cudaHostAllocDefault));
-            }
+        const size_t need = ((chunk * (size_t)line_bound) + 4095) / 4096 * 4096;   // every line of a chunk always fits
+        if (!c->h_text_cur) {
+            for (int i = 0; i < 2; i++) KG_CUDA(c, cudaMalloc(&c->d_text_cur[i], sizeof(u64)));
             KG_CUDA(c, cudaHostAlloc((void**)&c->h_text_cur, 2 * sizeof(u64), cudaHostAllocDefault));
-            c->text_cap = KG_TEXT_BUFFER_BYTES;
+        }
+        if (need > c->text_cap) {
+            for (int i = 0; i < 2; i++) {
+                cudaFree(c->d_text[i]);
+                if (c->h_text[i]) cudaFreeHost(c->h_text[i]);
+                c->d_text[i] = nullptr; c->h_text[i] = nullptr;
+            }
+            c->text_cap = 0;
+            for (int i = 0; i < 2; i++) {
+                KG_CUDA(c, cudaMalloc(&c->d_text[i], need));
+                KG_CUDA(c, cudaHostAlloc((void**)&c->h_text[i], need, cudaHostAllocDefault));
+            }
+            c->text_cap = need;
         }
         if (!c->text_configured) {
             KG_CUDA(c, cudaFuncSetAttribute(kg_format_text, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                             (int)(16 + (size_t)KG_TEXT_TPB * kg_line_bound(KG_MAX_K))));
             c->text_configured = true;
         }
-        const size_t fit = c->text_cap / line_bound;      // records whose lines always fit one text buffer
-        if (fit < chunk) chunk = fit;
     }
-    const u64 nslots = c->compacted ? c->kaarme.n_kmers : c->table.nslots;
     const u64 nchunks = (nslots + chunk - 1) / chunk;
     auto finish = [&](u64 i) -> int {
         const int b = (int)(i & 1);

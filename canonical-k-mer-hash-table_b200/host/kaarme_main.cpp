@@ -35,6 +35,7 @@
 
 #include "kaarme_gpu.h"
 #include "kg_reader.hpp"
+#include "kg_writer.hpp"
 
 namespace {
 
@@ -300,6 +301,7 @@ class Barrier {
 
 struct Writer {
     int fd = -1;
+    kg::ParallelWriter out;       // appends whole buffers with concurrent pwrite(2)s (host/kg_writer.hpp)
     uint32_t k = 0, W = 0;
     int threads = 1;
     uint64_t written = 0;
@@ -350,7 +352,7 @@ int sink(void* user, const uint64_t* keys, const uint32_t* counts, size_t n) {
     }
     for (auto& x : th) x.join();
     for (int t = 0; t < T; t++)
-        if (lens[t] && !write_all(w.fd, w.bufs[t].data(), lens[t])) return 1;
+        if (lens[t] && !w.out.append(w.bufs[t].data(), lens[t])) return 1;
     w.written += n;
     return 0;
 }
@@ -358,7 +360,7 @@ int sink(void* user, const uint64_t* keys, const uint32_t* counts, size_t n) {
 // default: the lines were formatted by kg_format_text on the GPU; the host only writes them
 int text_sink(void* user, const char* text, size_t bytes, size_t records) {
     Writer& w = *(Writer*)user;
-    if (!write_all(w.fd, text, bytes)) return 1;
+    if (!w.out.append(text, bytes)) return 1;
     w.written += records;
     return 0;
 }
@@ -444,6 +446,7 @@ int decode_kaarme_file(const Args& args) {
     if (args.min_abundance > 0) {
         w.fd = open(output.c_str(), O_WRONLY | O_CREAT | O_TRUNC, 0644);
         if (w.fd < 0) { std::cerr << "kaarme: cannot open output file " << output << "\n"; return 1; }
+        w.out.reset(w.fd, std::max(1, std::min(8, w.threads)));
         // counts in the structure are already 14-bit saturated (kmer.cpp:699-714): nothing left to emulate
         if (args.host_format) KG_CHECK(kg_export(ctx, args.min_abundance, KG_COUNT_EXACT, sink, &w));
         else KG_CHECK(kg_export_text(ctx, args.min_abundance, KG_COUNT_EXACT, text_sink, &w));
@@ -548,6 +551,7 @@ int main(int argc, char** argv) {
     if (args.min_abundance > 0) {
         w.fd = open(args.output.c_str(), O_WRONLY | O_CREAT | O_TRUNC, 0644);
         if (w.fd < 0) { std::cerr << "kaarme: cannot open output file " << args.output << "\n"; return 1; }
+        w.out.reset(w.fd, std::max(1, std::min(8, args.threads - 2)));
     }
     const int io_threads = std::max(1, std::min(8, (args.threads - 2) / world));
     const int nbufs = 3;

@@ -2,6 +2,8 @@
   * csrc/kg_text.cuh   kg_format_line / kg_ndigits -- the per-record formatter the GPU text dump runs per thread
                        (__host__ __device__, so the same code runs here) vs the oracle's restatement of the reference
                        writer (kmer_hash_table.cpp:2022-2043) and the binding's keys_to_text;
+  * host/kg_writer.hpp ParallelWriter -- the CLI's output side: whole text buffers appended with concurrent pwrite(2)s
+                       (replaces the ofstream loop of kmer_hash_table.cpp:2013-2050) vs the bytes handed to it;
   * host/kg_reader.hpp SliceReader -- the CLI's threaded reader ring (replaces text_reader.h:91-226 + io_worker,
                        parallel_parser.hpp:275-338) vs the bytes of the file.
 The harnesses live in tests/native/ and are compiled here (nvcc host compilation / g++); no GPU is touched."""
@@ -24,7 +26,8 @@ def _build(name, cmd):
     exe = os.path.join(BUILD, name)
     srcs = [a for a in cmd if a.endswith((".cu", ".cpp"))]
     deps = srcs + [os.path.join(ROOT, "canonical-k-mer-hash-table_b200", "csrc", "kg_text.cuh"),
-                   os.path.join(ROOT, "canonical-k-mer-hash-table_b200", "host", "kg_reader.hpp")]
+                   os.path.join(ROOT, "canonical-k-mer-hash-table_b200", "host", "kg_reader.hpp"),
+                   os.path.join(ROOT, "canonical-k-mer-hash-table_b200", "host", "kg_writer.hpp")]
     if not os.path.exists(exe) or any(os.path.getmtime(d) > os.path.getmtime(exe) for d in deps):
         subprocess.run(cmd + ["-o", exe], check=True, stdout=subprocess.PIPE, stderr=subprocess.PIPE)
     return exe
@@ -138,3 +141,41 @@ def test_reader_matches_cli_slices(reader_exe):
     for _, ctx_lo, lo, hi, _hdr in rows:
         ctx, body, _ = _read_slice(reader_exe, fa, ctx_lo, lo, hi, 8192, 3, 2)
         assert ctx == blob[ctx_lo:lo] and body == blob[lo:hi]
+
+
+@pytest.fixture(scope="module")
+def writer_exe():
+    return _build("writer_host", ["g++", "-O2", "-std=c++17", "-Wall", "-pthread", os.path.join(NATIVE, "writer_host.cpp")])
+
+
+def test_writer_appends_buffers_back_to_back(writer_exe, tmp_path):
+    rng = np.random.default_rng(3)
+    blob = rng.integers(0, 256, 70_000_003, dtype=np.uint8).tobytes()
+    src = tmp_path / "src.bin"
+    src.write_bytes(blob)
+    for threads, chunk in [(1, 64 << 20), (8, 64 << 20), (4, 9_999_999), (16, 1 << 20), (3, 70_000_003), (8, 4096)]:
+        out = tmp_path / f"out_{threads}_{chunk}.bin"
+        p = subprocess.run([writer_exe, str(src), str(out), str(threads), str(chunk)])
+        assert p.returncode == 0
+        assert out.read_bytes() == blob, (threads, chunk)
+        out.unlink()
+    # continues at the current offset of the descriptor
+    out = tmp_path / "prefixed.bin"
+    assert subprocess.run([writer_exe, str(src), str(out), "8", str(32 << 20), "HEADER\n"]).returncode == 0
+    assert out.read_bytes() == b"HEADER\n" + blob
+
+
+def test_writer_on_a_pipe_falls_back_to_sequential_writes(writer_exe, tmp_path):
+    blob = np.random.default_rng(4).integers(0, 256, 20_000_001, dtype=np.uint8).tobytes()
+    src = tmp_path / "src.bin"
+    src.write_bytes(blob)
+    p = subprocess.run([writer_exe, str(src), "-", "8", str(16 << 20)], stdout=subprocess.PIPE)
+    assert p.returncode == 0 and p.stdout == blob
+
+
+def test_writer_reports_errors(writer_exe, tmp_path):
+    src = tmp_path / "src.bin"
+    src.write_bytes(b"x" * 100)
+    with open("/dev/full", "wb") as full:
+        p = subprocess.run([writer_exe, str(src), "-", "2", "50"], stdout=full)
+    assert p.returncode == 5

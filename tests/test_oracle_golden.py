@@ -123,3 +123,36 @@ def test_binding_text_formatter_matches_oracle_writer(oracle):
     for k in (5, 21, 32, 33, 51, 64, 127, 255):
         c = oracle.count(data, k)
         assert kg.keys_to_text(c.keys, c.counts, k) == c.text(1)
+
+
+def test_kaarme_file_fixture_decodes_to_the_reference_output(oracle):
+    """tests/golden/g2_reads_k21.kaarme was written on a B200 by `kaarme g2_reads.fa 21 -s 200000 -a 2 --dump-kaarme`
+    (profiles/io_rows_probe.sh).  The oracle's restatement of reconstruct_kmer_in_slot (kmer_hash_table.cpp:3848-4058)
+    walks every chain of that file on the CPU; the lines it yields are the reference binary's own -m 2 output
+    (golden.json).  Pins the file layout (header + kmer.hpp:108-123 slot words + roots) across rounds."""
+    import hashlib
+    import struct
+    blob = _read("g2_reads_k21.kaarme")
+    magic, ver, k, W, flags, n_kmers, n_roots = struct.unpack_from("<8sIIIIQQ", blob, 0)
+    assert (magic, ver, k, W, flags) == (b"KAARMEG1", 1, 21, 1, 0)
+    assert len(blob) == 64 + 8 * n_kmers + 8 * W * n_roots
+    slots = np.frombuffer(blob, np.uint64, n_kmers, 64)
+    roots = np.frombuffer(blob, np.uint64, n_roots * W, 64 + 8 * n_kmers)
+    lines = []
+    for i in range(n_kmers):
+        d = int(slots[i])
+        assert d & 1                                         # dense: every slot is occupied
+        count = (d >> 12) & 16383
+        hops, codes = oracle.kaarme_decode(slots, roots, k, i)
+        assert hops >= 0
+        kmer = "".join("ACGT"[x] for x in codes)
+        assert (int(codes[0]), int(codes[-1])) == ((d >> 10) & 3, (d >> 8) & 3)      # stored end characters
+        if count >= 2:
+            lines.append(f"{kmer} {count}\n".encode())
+    case = [c for c in json.load(open(os.path.join(GOLDEN, "golden.json")))
+            if c["input"] == "g2_reads.fa" and c["k"] == 21 and c["mode"] == 2 and c["a"] == 2 and c["unique"] is None][0]
+    assert len(lines) == case["n_lines"]
+    assert hashlib.sha256(b"".join(sorted(lines))).hexdigest() == case["sha256"]
+    # every k-mer of the input is in the structure exactly once
+    want = oracle.count(_read("g2_reads.fa"), k)
+    assert n_kmers == want.n
