@@ -489,6 +489,7 @@ static int setup_pass_buckets(kg_ctx* c, size_t region_bytes) {
         cudaFree(c->d_blk_hist); cudaFree(c->d_blk_base); cudaFree(c->d_bucket_counts); cudaFree(c->d_bucket_offs); cudaFree(c->d_matrix);
         if (c->h_matrix) cudaFreeHost(c->h_matrix);
         c->d_blk_hist = c->d_blk_base = c->d_bucket_counts = c->d_bucket_offs = c->d_matrix = nullptr; c->h_matrix = nullptr;
+        c->nb_alloc = 0;   // nothing is allocated until every buffer below exists (an allocation may fail half way)
         KG_CUDA(c, cudaMalloc(&c->d_blk_hist, sizeof(u32) * (size_t)c->max_blocks * c->nb));
         KG_CUDA(c, cudaMalloc(&c->d_blk_base, sizeof(u32) * (size_t)c->max_blocks * c->nb));
         KG_CUDA(c, cudaMalloc(&c->d_bucket_counts, sizeof(u32) * (c->nb + 4)));
@@ -500,6 +501,10 @@ static int setup_pass_buckets(kg_ctx* c, size_t region_bytes) {
     if (c->nb + 1 > c->seg_cap) {
         for (int i = 0; i < 2; i++) {
             cudaFree(c->d_seg[i]); if (c->h_seg[i]) cudaFreeHost(c->h_seg[i]);
+            c->d_seg[i] = nullptr; c->h_seg[i] = nullptr;
+        }
+        c->seg_cap = 0;
+        for (int i = 0; i < 2; i++) {
             KG_CUDA(c, cudaMalloc(&c->d_seg[i], sizeof(u64) * 2 * (c->nb + 2)));
             KG_CUDA(c, cudaHostAlloc((void**)&c->h_seg[i], sizeof(u64) * 2 * (c->nb + 2), cudaHostAllocDefault));
         }
@@ -1132,7 +1137,7 @@ extern "C" int kg_compact(kg_ctx* c, kg_compact_stats* stats) {
     if (c->compacted) return KG_OK;
     KG_CUDA(c, cudaSetDevice(c->cfg.device));
     cudaStream_t s = c->s_compute;
-    cudaEvent_t e0, e1;
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
     KG_CUDA(c, cudaEventCreate(&e0));
     KG_CUDA(c, cudaEventCreate(&e1));
     KG_CUDA(c, cudaEventRecord(e0, s));
@@ -1142,6 +1147,14 @@ extern "C" int kg_compact(kg_ctx* c, kg_compact_stats* stats) {
     const u64 nsb = (nwords + 1023) / 1024;
     u32 *bitmap = nullptr, *wcount = nullptr;
     u64 *prefix = nullptr, *bsum = nullptr, *scalars = nullptr;   // scalars[0] = n_kmers, scalars[1] = root counter
+    struct Scratch {   // released on every return path (the KG_CUDA early returns included)
+        u32 **a, **b; u64 **p, **q, **r; cudaEvent_t *e0, *e1;
+        ~Scratch() {
+            cudaFree(*a); cudaFree(*b); cudaFree(*p); cudaFree(*q); cudaFree(*r);
+            if (*e0) cudaEventDestroy(*e0);
+            if (*e1) cudaEventDestroy(*e1);
+        }
+    } scratch{&bitmap, &wcount, &prefix, &bsum, &scalars, &e0, &e1};
     KG_CUDA(c, cudaMalloc(&bitmap, sizeof(u32) * nwords));
     KG_CUDA(c, cudaMalloc(&wcount, sizeof(u32) * nwords));
     KG_CUDA(c, cudaMalloc(&prefix, sizeof(u64) * nwords));
@@ -1166,7 +1179,10 @@ extern "C" int kg_compact(kg_ctx* c, kg_compact_stats* stats) {
     KG_CUDA(c, cudaStreamSynchronize(s));
     const u64 n_roots = h[1];
     KgKaarme ks{nullptr, nullptr, n_kmers, n_roots};
+    cudaFree(c->kaarme.slots); cudaFree(c->kaarme.roots);      // left-overs of an attempt that failed half way
+    c->kaarme = KgKaarme{nullptr, nullptr, 0, 0};
     KG_CUDA(c, cudaMalloc(&ks.slots, sizeof(u64) * (n_kmers ? n_kmers : 1)));
+    c->kaarme.slots = ks.slots;                                 // owned by the context from here on (freed by kg_destroy)
     KG_CUDA(c, cudaMalloc(&ks.roots, sizeof(u64) * (n_roots ? n_roots : 1) * c->W));
     KG_CUDA(c, cudaMemsetAsync(scalars + 1, 0, sizeof(u64), s));
     KG_DISPATCH_W(c->W, launch_kaarme_build, c, bitmap, prefix, ks, scalars + 1);
@@ -1177,7 +1193,6 @@ extern "C" int kg_compact(kg_ctx* c, kg_compact_stats* stats) {
     KG_CUDA(c, cudaMemcpyAsync(&cs, c->d_cstats, sizeof(cs), cudaMemcpyDeviceToHost, s));
     KG_CUDA(c, cudaStreamSynchronize(s));
     KG_CUDA(c, cudaGetLastError());
-    cudaFree(bitmap); cudaFree(wcount); cudaFree(prefix); cudaFree(bsum); cudaFree(scalars);
     // the plain table has served its purpose: from here on only the compact structure exists
     cudaFree(c->table.slots);
     c->table.slots = nullptr;
@@ -1185,7 +1200,6 @@ extern "C" int kg_compact(kg_ctx* c, kg_compact_stats* stats) {
     c->compacted = true;
     float ms = 0;
     cudaEventElapsedTime(&ms, e0, e1);
-    cudaEventDestroy(e0); cudaEventDestroy(e1);
     if (cs.bad) { c->err = "kg_compact: malformed predecessor chain"; return KG_ECUDA; }
     if (stats) {
         stats->kmers = n_kmers;
@@ -1418,9 +1432,13 @@ extern "C" int kg_atomic_ceiling(int device, uint64_t region_bytes, uint64_t n_o
     kg_ctx* c = nullptr;
     KG_CUDA(c, cudaSetDevice(device));
     u32* region = nullptr;
+    cudaEvent_t a = nullptr, b = nullptr;
+    struct Guard {
+        u32** r; cudaEvent_t *a, *b;
+        ~Guard() { cudaFree(*r); if (*a) cudaEventDestroy(*a); if (*b) cudaEventDestroy(*b); }
+    } guard{&region, &a, &b};
     KG_CUDA(c, cudaMalloc(&region, region_bytes));
     KG_CUDA(c, cudaMemset(region, 0, region_bytes));
-    cudaEvent_t a, b;
     KG_CUDA(c, cudaEventCreate(&a));
     KG_CUDA(c, cudaEventCreate(&b));
     cudaDeviceProp prop;
@@ -1436,8 +1454,6 @@ extern "C" int kg_atomic_ceiling(int device, uint64_t region_bytes, uint64_t n_o
         KG_CUDA(c, cudaEventElapsedTime(&ms, a, b));
         if (r > 0 && ms > 0) { double v = (double)n_ops / (ms * 1e-3); if (v > best) best = v; }
     }
-    cudaEventDestroy(a); cudaEventDestroy(b);
-    cudaFree(region);
     *sectors_per_s = best;
     return KG_OK;
 }
