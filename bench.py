@@ -188,6 +188,10 @@ def main():
         uid = [kg.comm_unique_id() if rank == 0 else None]
         dist.broadcast_object_list(uid, src=0)
         ctr.comm_init(uid[0], rank, world)
+        if os.environ.get("KAARME_PEER") == "1":   # opt-in: fused bucket -> peer-store exchange (kg_peer_connect)
+            handles = [None] * world
+            dist.all_gather_object(handles, ctr.peer_export())
+            ctr.peer_connect(handles)
 
     def barrier():
         if world > 1:
@@ -337,7 +341,8 @@ def main():
                       "table_bytes_per_gpu": ctr.table_info()["slots"] * ctr.table_info()["slot_bytes"],
                       "input_kmers_per_gpu": meta["input_kmers"], "distinct_rank0": distinct,
                       "l2": "inputs (2 GB/GPU) and table (4 GB/GPU) are far larger than the 126 MB L2; no flush between steps",
-                      "parallelism": f"hash-sharded x{world}" if world > 1 else "single GPU",
+                      "parallelism": (f"hash-sharded x{world}, " + ("peer-store exchange" if os.environ.get("KAARME_PEER") == "1"
+                                                                   else "nccl send/recv exchange")) if world > 1 else "single GPU",
                       "partitions": st["partitions"], "batch_mb": args.batch_mb},
            "clocks": clocks, "gpu_launches": launches, "roofline": roofline, "e2e": e2e,
            "stage_ms_per_step": {"parse": parse_ms / args.steps, "bucket+insert": count_ms / args.steps,

@@ -12,15 +12,18 @@
 #include <vector>
 
 #include <dlfcn.h>
+#include <unistd.h>
 #include <nccl.h>   // types and prototypes only: the library is bound at run time (see kg_nccl below)
 
 #include "kg_count.cuh"
 #include "kg_device.cuh"
+#include "kg_exchange_plan.hpp"
 #include "kg_kaarme.cuh"
 #include "kg_parse.cuh"
 #include "kg_text.cuh"
 
 #define KG_MAX_W 8
+#define KG_MAX_WORLD 64
 #define KG_DISPATCH_W(W_, fn, ...)                     \
     switch (W_) {                                      \
         case 1: fn<1>(__VA_ARGS__); break;             \
@@ -119,6 +122,14 @@ struct kg_ctx {
     bool scatter_configured = false;
     u32 reserve_cap = 0;                // keys per bucket region of the one-pass (reserve) scatter
     size_t send_alloc = 0;              // keys each d_send buffer can hold
+    // peer exchange (kg_peer_export / kg_peer_connect): scatter kernels store straight into the owners' receive buffers
+    bool peer_ready = false;
+    u64* peer_recv[2][KG_MAX_WORLD] = {};   // receive buffers of every rank as mapped into this process ([parity][rank])
+    void* peer_opened[2][KG_MAX_WORLD] = {};// IPC mappings to close at destroy
+    u64** d_peer_ptrs[2] = {nullptr, nullptr};      // device copies of peer_recv[parity][*]
+    u64 *d_remote_base[2] = {nullptr, nullptr}, *h_remote_base[2] = {nullptr, nullptr};   // [KG_MAX_BUCKETS] per parity
+    u32* d_barrier = nullptr;           // world + 1 words for the "all scatters have landed" collective
+    uint64_t peer_rounds = 0, peer_fallback_rounds = 0;
     u32* d_work = nullptr;              // work counter of the persistent insert kernels
     u32 insert_grid = 148 * 8;          // resident blocks of the grid-stride insert kernels (SMs x blocks/SM)
     // Kaarme representation (after kg_compact)
@@ -264,6 +275,12 @@ static void free_all(kg_ctx* c) {
     if (c->s_comm) cudaStreamSynchronize(c->s_comm);
     if (c->s_insert) cudaStreamSynchronize(c->s_insert);
     if (c->s_ctl) cudaStreamSynchronize(c->s_ctl);
+    for (int i = 0; i < 2; i++) {
+        for (int r = 0; r < KG_MAX_WORLD; r++) if (c->peer_opened[i][r]) cudaIpcCloseMemHandle(c->peer_opened[i][r]);
+        cudaFree(c->d_peer_ptrs[i]); cudaFree(c->d_remote_base[i]);
+        if (c->h_remote_base[i]) cudaFreeHost(c->h_remote_base[i]);
+    }
+    cudaFree(c->d_barrier);
     if (c->comm) { kg_nccl().CommDestroy(c->comm); c->comm = nullptr; }
     if (c->ctl_comm) { kg_nccl().CommDestroy(c->ctl_comm); c->ctl_comm = nullptr; }
     for (int i = 0; i < 2; i++) {
@@ -757,10 +774,11 @@ static void launch_reserve(kg_ctx* c, const KgReserveArgs& a, u32 nwords, int si
 //   s_comm:   grouped ncclSend/ncclRecv of the key slices
 //   s_insert: insert kernel over what arrived (partition-major across senders through a segment table),
 //             overlapping the next batch's parse + bucketing on s_compute
-static int exchange_round(kg_ctx* c, bool have_batch, bool* all_done) {
+static int exchange_round(kg_ctx* c, bool have_batch, bool* all_done, bool counts_gathered = false) {
     const u32 nb = c->nb, pl = c->pl, world = (u32)c->cfg.world, rank = (u32)c->cfg.rank;
     const int sb = (int)(c->round & 1);
     const size_t row = nb + 1;
+    if (!counts_gathered) {          // (the peer path gathers the counts itself before it decides to fall back here)
     if (!have_batch) {
         KG_CUDA(c, cudaMemsetAsync(c->d_bucket_counts, 0, sizeof(u32) * nb, c->s_compute));
         KG_CUDA(c, cudaMemsetAsync(c->d_bucket_counts + nb, 1, sizeof(u32), c->s_compute));   // non-zero = done
@@ -771,6 +789,7 @@ static int exchange_round(kg_ctx* c, bool have_batch, bool* all_done) {
     KG_CUDA(c, cudaMemcpyAsync(c->h_matrix, c->d_matrix, sizeof(u32) * row * world, cudaMemcpyDeviceToHost, c->s_ctl));
     KG_CUDA(c, cudaEventRecord(c->ev_matrix, c->s_ctl));
     KG_CUDA(c, cudaEventSynchronize(c->ev_matrix));
+    }
     const u32* M = c->h_matrix;   // M[r*row + b] = keys rank r holds for bucket b; M[r*row + nb] = done flag
     auto to_owner = [&](u32 r, u32 d) { u64 t = 0; for (u32 p = 0; p < pl; p++) t += M[r * row + d * pl + p]; return t; };
     bool done = true;
@@ -859,6 +878,165 @@ static int exchange_round(kg_ctx* c, bool have_batch, bool* all_done) {
     return KG_OK;
 }
 
+// ---- peer exchange: the fused bucket -> peer-store path --------------------------------------------------------
+// With kg_peer_connect every rank has every other rank's two receive buffers mapped (CUDA IPC between processes, plain
+// peer access inside one process).  A round then is:
+//   s_compute: hist -> column scan (bucket_batch)                                  counts of this batch
+//   s_ctl:     wait "my receive buffer of this parity is free" -> all-gather of the counts -> host
+//              (so the gathered matrix also says: EVERY rank's buffer of this parity is free)
+//   host:      kg_peer_plan: where each of my (bucket) runs starts in its owner's buffer (partition-major there)
+//   s_compute: kg_owner_scatter_peer: the scatter's coalesced 16-byte runs go straight to the owners over NVLink
+//   s_comm:    one-word all-gather = "all scatters of this round have completed" (kernel completion makes peer
+//              stores visible)
+//   s_insert:  kg_insert_keys_kernel over my receive buffer, front to back = partition-major (L2-blocked, section 5)
+// No send buffer, no NCCL copy kernels on the SMs, no segment table; NVLink carries each key once.
+// A round whose busiest owner would overflow a receive buffer (heavy skew) falls back to the ncclSend/ncclRecv path.
+struct KgPeerHandle {               // KG_PEER_HANDLE_BYTES on the wire
+    uint64_t magic, pid;
+    int32_t rank, device;
+    uint64_t ptr[2], cap_keys;
+    cudaIpcMemHandle_t ipc[2];
+};
+static_assert(sizeof(KgPeerHandle) <= KG_PEER_HANDLE_BYTES, "peer handle size");
+#define KG_PEER_MAGIC 0x4B47504545523031ULL   // "KGPEER01"
+
+extern "C" int kg_peer_export(kg_ctx* c, void* handle_out) {
+    if (!c || !handle_out) return KG_EBADARG;
+    if (c->cfg.world < 2 || !c->bucketed) { c->err = "kg_peer_export needs world > 1"; return KG_EBADARG; }
+    if (c->pass) { c->err = "kg_peer_export inside a pass"; return KG_EBADARG; }
+    KG_CUDA(c, cudaSetDevice(c->cfg.device));
+    for (int i = 0; i < 2; i++)
+        if (!c->d_recv[i]) KG_CUDA(c, cudaMalloc(&c->d_recv[i], c->recv_cap * c->W * sizeof(u64)));
+    KgPeerHandle h;
+    memset(&h, 0, sizeof(h));
+    h.magic = KG_PEER_MAGIC;
+    h.pid = (uint64_t)getpid();
+    h.rank = c->cfg.rank;
+    h.device = c->cfg.device;
+    h.cap_keys = c->recv_cap;
+    for (int i = 0; i < 2; i++) {
+        h.ptr[i] = (uint64_t)(uintptr_t)c->d_recv[i];
+        KG_CUDA(c, cudaIpcGetMemHandle(&h.ipc[i], c->d_recv[i]));
+    }
+    memset(handle_out, 0, KG_PEER_HANDLE_BYTES);
+    memcpy(handle_out, &h, sizeof(h));
+    return KG_OK;
+}
+
+extern "C" int kg_peer_connect(kg_ctx* c, const void* handles, int world) {
+    if (!c || !handles) return KG_EBADARG;
+    if (world != c->cfg.world || world < 2 || world > KG_MAX_WORLD) { c->err = "kg_peer_connect: world differs from kg_config"; return KG_EBADARG; }
+    if (c->pass || c->peer_ready) { c->err = "kg_peer_connect: call once, outside a pass"; return KG_EBADARG; }
+    if (!c->d_recv[0] || !c->d_recv[1]) { c->err = "kg_peer_connect before kg_peer_export"; return KG_EBADARG; }
+    KG_CUDA(c, cudaSetDevice(c->cfg.device));
+    const uint64_t me = (uint64_t)getpid();
+    for (int r = 0; r < world; r++) {
+        KgPeerHandle h;
+        memcpy(&h, (const char*)handles + (size_t)r * KG_PEER_HANDLE_BYTES, sizeof(h));
+        if (h.magic != KG_PEER_MAGIC || h.rank != r || h.cap_keys != c->recv_cap) { c->err = "kg_peer_connect: bad handle (order must be rank order; same batch size on every rank)"; return KG_EBADARG; }
+        for (int i = 0; i < 2; i++) {
+            if (r == c->cfg.rank) {
+                c->peer_recv[i][r] = c->d_recv[i];
+            } else if (h.pid == me) {                       // another context of this process (one host thread per GPU)
+                int can = 0;
+                KG_CUDA(c, cudaDeviceCanAccessPeer(&can, c->cfg.device, h.device));
+                if (!can) { c->err = "kg_peer_connect: no peer access between the devices"; return KG_ECUDA; }
+                cudaError_t e = cudaDeviceEnablePeerAccess(h.device, 0);
+                if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) KG_CUDA(c, e);
+                cudaGetLastError();
+                c->peer_recv[i][r] = (u64*)(uintptr_t)h.ptr[i];
+            } else {                                        // another process: map its allocation
+                void* p = nullptr;
+                KG_CUDA(c, cudaIpcOpenMemHandle(&p, h.ipc[i], cudaIpcMemLazyEnablePeerAccess));
+                c->peer_opened[i][r] = p;
+                c->peer_recv[i][r] = (u64*)p;
+            }
+        }
+    }
+    for (int i = 0; i < 2; i++) {
+        KG_CUDA(c, cudaMalloc(&c->d_peer_ptrs[i], sizeof(u64*) * KG_MAX_WORLD));
+        KG_CUDA(c, cudaMemcpy(c->d_peer_ptrs[i], c->peer_recv[i], sizeof(u64*) * KG_MAX_WORLD, cudaMemcpyHostToDevice));
+        KG_CUDA(c, cudaMalloc(&c->d_remote_base[i], sizeof(u64) * KG_MAX_BUCKETS));
+        KG_CUDA(c, cudaHostAlloc((void**)&c->h_remote_base[i], sizeof(u64) * KG_MAX_BUCKETS, cudaHostAllocDefault));
+    }
+    KG_CUDA(c, cudaMalloc(&c->d_barrier, sizeof(u32) * (KG_MAX_WORLD + 1)));
+    KG_CUDA(c, cudaMemset(c->d_barrier, 0, sizeof(u32) * (KG_MAX_WORLD + 1)));
+    c->peer_ready = true;
+    return KG_OK;
+}
+
+extern "C" int kg_peer_stats(const kg_ctx* c, uint64_t* peer_rounds, uint64_t* fallback_rounds) {
+    if (!c) return KG_EBADARG;
+    if (peer_rounds) *peer_rounds = c->peer_rounds;
+    if (fallback_rounds) *fallback_rounds = c->peer_fallback_rounds;
+    return KG_OK;
+}
+
+template <int W>
+static void launch_scatter_peer(kg_ctx* c, const KgBucketArgs& a, const KgPeerArgs& pa, u32 nwords) {
+    using G = KgBucketGeom<W>;
+    const u32 grid = (nwords + G::WPB - 1) / G::WPB;
+    cudaFuncSetAttribute(kg_owner_scatter_peer<W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G::smem_bytes(KG_MAX_BUCKETS));
+    kg_owner_scatter_peer<W><<<grid, G::TPB, G::smem_bytes(a.nb), c->s_compute>>>(a, pa);
+    c->launches++;
+}
+
+// One round of the peer exchange (collective).  have_batch: hist + column scan of this rank's batch are queued on
+// s_compute and ev_counts is recorded (bucket_batch); otherwise the rank contributes nothing and reports "done".
+static int peer_round(kg_ctx* c, bool have_batch, const KgBucketArgs* a, u32 nthreads, bool* all_done) {
+    const u32 nb = c->nb, pl = c->pl, world = (u32)c->cfg.world, rank = (u32)c->cfg.rank;
+    const int rb = (int)(c->round & 1);
+    const size_t row = nb + 1;
+    if (!have_batch) {
+        KG_CUDA(c, cudaMemsetAsync(c->d_bucket_counts, 0, sizeof(u32) * nb, c->s_compute));
+        KG_CUDA(c, cudaMemsetAsync(c->d_bucket_counts + nb, 1, sizeof(u32), c->s_compute));   // non-zero = done
+        KG_CUDA(c, cudaEventRecord(c->ev_counts, c->s_compute));
+    }
+    KG_CUDA(c, cudaStreamWaitEvent(c->s_ctl, c->ev_counts, 0));
+    KG_CUDA(c, cudaStreamWaitEvent(c->s_ctl, c->ev_recv_free[rb], 0));   // gathered matrix => every rank's buffer rb is free
+    KG_NCCL(c, kg_nccl().AllGather(c->d_bucket_counts, c->d_matrix, row, ncclUint32, c->ctl_comm, c->s_ctl));
+    KG_CUDA(c, cudaMemcpyAsync(c->h_matrix, c->d_matrix, sizeof(u32) * row * world, cudaMemcpyDeviceToHost, c->s_ctl));
+    KG_CUDA(c, cudaEventRecord(c->ev_matrix, c->s_ctl));
+    KG_CUDA(c, cudaEventSynchronize(c->ev_matrix));
+    const KgPeerPlan plan = kg_peer_plan(c->h_matrix, world, pl, rank);
+    *all_done = plan.all_done;
+    if (plan.max_in > c->recv_cap) {
+        // heavy skew: the busiest owner cannot take its keys in one piece -> this round goes through the send buffer
+        // and ncclSend/ncclRecv in sub-rounds (every rank sees the same matrix and takes the same decision)
+        c->peer_fallback_rounds++;
+        if (have_batch) {
+            const int sb = (int)(c->round & 1);
+            KgBucketArgs b = *a;
+            b.out_keys = c->d_send[sb];
+            KG_CUDA(c, cudaStreamWaitEvent(c->s_compute, c->ev_send_free[sb], 0));
+            bucket_kernel(c, b, nthreads, true);
+            KG_CUDA(c, cudaEventRecord(c->ev_scatter, c->s_compute));
+        }
+        return exchange_round(c, have_batch, all_done, /*counts_gathered=*/true);
+    }
+    c->peer_rounds++;
+    if (plan.max_in == 0) { c->round++; return KG_OK; }     // nobody moves anything this round
+    if (have_batch) {
+        memcpy(c->h_remote_base[rb], plan.remote_base.data(), sizeof(u64) * nb);
+        KG_CUDA(c, cudaMemcpyAsync(c->d_remote_base[rb], c->h_remote_base[rb], sizeof(u64) * nb, cudaMemcpyHostToDevice, c->s_compute));
+        KgPeerArgs pa;
+        pa.peer = c->d_peer_ptrs[rb];
+        pa.remote_base = c->d_remote_base[rb];
+        pa.pl = pl;
+        KG_DISPATCH_W(c->W, launch_scatter_peer, c, *a, pa, nthreads);
+        KG_CUDA(c, cudaEventRecord(c->ev_scatter, c->s_compute));
+        KG_CUDA(c, cudaStreamWaitEvent(c->s_comm, c->ev_scatter, 0));
+    }
+    // "every scatter of this round has completed": a collective on s_comm that each rank enters after its own scatter
+    KG_NCCL(c, kg_nccl().AllGather(c->d_barrier + KG_MAX_WORLD, c->d_barrier, 1, ncclUint32, c->comm, c->s_comm));
+    KG_CUDA(c, cudaEventRecord(c->ev_recv_full[rb], c->s_comm));
+    KG_CUDA(c, cudaStreamWaitEvent(c->s_insert, c->ev_recv_full[rb], 0));
+    if (plan.my_in) insert_keys(c, c->s_insert, c->d_recv[rb], plan.my_in, nullptr);   // contiguous, partition-major
+    KG_CUDA(c, cudaEventRecord(c->ev_recv_free[rb], c->s_insert));
+    c->round++;
+    return KG_OK;
+}
+
 // bucket the k-mers of the batch that was just packed, then hand them on
 //   single GPU, W <= 4 : one-pass reserve scatter -> segment table -> insert (kg_scatter_reserve)
 //   otherwise          : hist -> scan -> scatter (exact layout, needed for the exchange) -> exchange / insert
@@ -896,6 +1074,12 @@ static int bucket_batch(kg_ctx* c, u32 nthreads) {
     kg_bucket_colscan<<<c->nb, 1024, 0, c->s_compute>>>(c->d_blk_hist, c->d_blk_base, grid, c->nb, c->d_bucket_counts);
     kg_bucket_offsets<<<1, 1024, 0, c->s_compute>>>(c->d_bucket_counts, c->nb, c->d_bucket_offs);
     c->launches += 2;
+    if (c->cfg.world > 1 && c->peer_ready) {   // fused bucket -> peer-store exchange (kg_peer_connect)
+        KG_CUDA(c, cudaMemsetAsync(c->d_bucket_counts + c->nb, 0, sizeof(u32), c->s_compute));   // not done
+        KG_CUDA(c, cudaEventRecord(c->ev_counts, c->s_compute));
+        bool all_done;
+        return peer_round(c, true, &a, nthreads, &all_done);
+    }
     if (c->cfg.world > 1) {
         KG_CUDA(c, cudaMemsetAsync(c->d_bucket_counts + c->nb, 0, sizeof(u32), c->s_compute));   // not done
         KG_CUDA(c, cudaEventRecord(c->ev_counts, c->s_compute));
@@ -1064,7 +1248,7 @@ extern "C" int kg_pass_end(kg_ctx* c, kg_pass_stats* out) {
         // keep taking part in exchange rounds until every rank has fed its last batch
         bool all_done = false;
         while (!all_done) {
-            int rc = exchange_round(c, false, &all_done);
+            int rc = c->peer_ready ? peer_round(c, false, nullptr, 0, &all_done) : exchange_round(c, false, &all_done);
             if (rc) return rc;
         }
         KG_CUDA(c, cudaEventRecord(c->ev_tail, c->s_comm));

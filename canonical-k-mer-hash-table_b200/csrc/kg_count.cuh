@@ -524,8 +524,18 @@ struct KgBucketGeom {
     }
 };
 
-template <int W>
-__global__ void __launch_bounds__(KgBucketGeom<W>::TPB) kg_owner_scatter(KgBucketArgs a) {
+// Peer exchange (kg_peer_connect): instead of a local send buffer the runs go STRAIGHT into the owners' receive
+// buffers over NVLink (plain stores to peer memory, visible at kernel end).  peer[d] = owner d's receive buffer for
+// this round as mapped into this process (d == own rank: a local buffer), remote_base[b] = first key index of this
+// rank's run for bucket b in that buffer (kg_exchange_plan.hpp), pl = local partitions per owner (owner = b / pl).
+struct KgPeerArgs {
+    u64* const* peer;
+    const u64* remote_base;
+    u32 pl;
+};
+
+template <int W, bool PEER>
+__device__ __forceinline__ void kg_owner_scatter_body(const KgBucketArgs& a, const KgPeerArgs& pa) {
     using G = KgBucketGeom<W>;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     u64* s_keys = reinterpret_cast<u64*>(smem_raw);                                  // KEYS * W
@@ -585,7 +595,8 @@ __global__ void __launch_bounds__(KgBucketGeom<W>::TPB) kg_owner_scatter(KgBucke
         for (u32 i = b0; i < b1; i++) {
             s_off[i] = cur;
             cur += s_cnt[i];
-            s_gbase[i] = a.bucket_offs[i] + a.blk_base[(u64)blockIdx.x * nb + i];
+            if constexpr (PEER) s_gbase[i] = (u32)pa.remote_base[i] + a.blk_base[(u64)blockIdx.x * nb + i];   // key index in the owner's buffer (< 2^32)
+            else s_gbase[i] = a.bucket_offs[i] + a.blk_base[(u64)blockIdx.x * nb + i];
         }
     }
     __syncthreads();
@@ -614,7 +625,9 @@ __global__ void __launch_bounds__(KgBucketGeom<W>::TPB) kg_owner_scatter(KgBucke
     const u32 n = s_off[nb - 1] + s_cnt[nb - 1];
     for (u32 i = tid; i < n; i += G::TPB) {
         const u32 b = s_kb[i];
-        u64* dst = a.out_keys + (u64)(s_gbase[b] + (i - s_off[b])) * W;
+        u64* dst;
+        if constexpr (PEER) dst = pa.peer[b / pa.pl] + (u64)(s_gbase[b] + (i - s_off[b])) * W;
+        else dst = a.out_keys + (u64)(s_gbase[b] + (i - s_off[b])) * W;
         if (W % 2 == 0) {
 #pragma unroll
             for (int q = 0; q < W; q += 2)
@@ -624,6 +637,16 @@ __global__ void __launch_bounds__(KgBucketGeom<W>::TPB) kg_owner_scatter(KgBucke
             for (int q = 0; q < W; q++) dst[q] = s_keys[(size_t)i * W + q];
         }
     }
+}
+
+template <int W>
+__global__ void __launch_bounds__(KgBucketGeom<W>::TPB) kg_owner_scatter(KgBucketArgs a) {
+    kg_owner_scatter_body<W, false>(a, KgPeerArgs{nullptr, nullptr, 1});
+}
+// fused bucket -> peer-store kernel: the exchange IS the scatter's write-out
+template <int W>
+__global__ void __launch_bounds__(KgBucketGeom<W>::TPB) kg_owner_scatter_peer(KgBucketArgs a, KgPeerArgs pa) {
+    kg_owner_scatter_body<W, true>(a, pa);
 }
 
 // ---- single-GPU one-pass bucketing: reserve, don't count ----------------------------------------------------------

@@ -7,7 +7,7 @@
 //     -m,--hash-table-type {0,2}   -a,--min-k-abu N   -t,--threads N   -o,--output-file PATH
 //     -b,--use-bfilter  -f,--bfilter-fpr F   exactly one of  -s,--hash-tab-size N | -u,--unq-kmers N
 //   GPU-side extras (do not collide with the reference's flags):
-//     --device N   --gpus N   --batch-mb N   --exact-counts   --stats-json PATH   --host-format
+//     --device N   --gpus N   --peer-exchange   --batch-mb N   --exact-counts   --stats-json PATH   --host-format
 //     --dump-kaarme PATH   (-m 2: save the compact structure)      --from-kaarme   (INPUT is such a file: decode it)
 //
 // Exit codes follow the reference: 0 ok; CLI11's 105 (validation), 106 (required), 107 (requires),
@@ -56,6 +56,7 @@ struct Args {
     bool print_slices = false;    // --print-slices: show how --gpus N would shard the input, then exit (no GPU needed)
     bool host_format = false;     // --host-format: export (key, count) records and format the lines on host threads
     std::string dump_kaarme;      // --dump-kaarme PATH: write the compact structure (-m 2, one GPU) as a binary file
+    bool peer_exchange = false;   // --peer-exchange: with --gpus N, scatter kernels store straight into the owners' buffers
     bool from_kaarme = false;     // --from-kaarme: INPUT is a file written by --dump-kaarme; decode it on the GPU
 };
 
@@ -80,6 +81,8 @@ void print_help(const char* argv0) {
                  "  -f,--bfilter-fpr FLOAT     Bloom filter false positive rate (def. 0.01)\n"
                  "  --device INT               CUDA device ordinal (def. 0; with --gpus N the first of N consecutive devices)\n"
                  "  --gpus INT                 Hash-shard the k-mers over N GPUs of this box (NCCL exchange; def. 1)\n"
+                 "  --peer-exchange            With --gpus N: fused bucket -> peer-store exchange over NVLink instead of\n"
+                 "                             ncclSend/ncclRecv (experimental)\n"
                  "  --batch-mb UINT            Raw bytes per device batch in MiB (def. 128)\n"
                  "  --exact-counts             Report true 32-bit counts instead of emulating the reference's\n"
                  "                             16-bit wrap (-m 0) / 14-bit saturation (-m 2)\n"
@@ -182,6 +185,7 @@ Args parse_args(int argc, char** argv) {
         else if (s == "--print-slices") a.print_slices = true;
         else if (s == "--host-format") a.host_format = true;
         else if (s == "--from-kaarme") a.from_kaarme = true;
+        else if (s == "--peer-exchange") a.peer_exchange = true;
         else if (s == "--dump-kaarme") a.dump_kaarme = value("--dump-kaarme");
         else if (s == "--stats-json") a.stats_json = value("--stats-json");
         else if (s.size() > 1 && s[0] == '-' && !(s[1] >= '0' && s[1] <= '9')) cli_fail(109, "The following argument was not expected: " + s);
@@ -556,6 +560,7 @@ int main(int argc, char** argv) {
     const int io_threads = std::max(1, std::min(8, (args.threads - 2) / world));
     const int nbufs = 3;
     Barrier barrier(world);
+    std::vector<char> peer_handles((size_t)world * KG_PEER_HANDLE_BYTES);
     std::chrono::high_resolution_clock::time_point t_bloom0, t_bloom1, t_build0, t_build1, t_write1;
 
     // one host thread per GPU: its own context (= hash shard), its own byte range of the input
@@ -584,6 +589,11 @@ int main(int argc, char** argv) {
             }
         }
         if (world > 1) KG_CHECK(kg_comm_init(ctx, nccl_id, rank, world));
+        if (world > 1 && args.peer_exchange) {   // every rank publishes its receive buffers, then maps everybody's
+            KG_CHECK(kg_peer_export(ctx, peer_handles.data() + (size_t)rank * KG_PEER_HANDLE_BYTES));
+            barrier.wait();
+            KG_CHECK(kg_peer_connect(ctx, peer_handles.data(), world));
+        }
         uint8_t* bufs[nbufs] = {nullptr, nullptr, nullptr};
         for (int i = 0; i < nbufs; i++) KG_CHECK(kg_host_alloc(buf_bytes, (void**)&bufs[i]));
         int fd = open(args.input.c_str(), O_RDONLY);

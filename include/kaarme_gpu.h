@@ -147,6 +147,19 @@ int kg_host_free(void* p);
 int kg_comm_unique_id(void* id_out);                                   /* rank 0, then broadcast    */
 int kg_comm_init(kg_ctx* ctx, const void* id, int rank, int world);    /* collective                */
 
+/* Optional, after kg_comm_init: the fused bucket -> peer-store exchange.  Every rank describes its two receive buffers
+ * (kg_peer_export: KG_PEER_HANDLE_BYTES bytes; CUDA IPC handles between processes, plain peer pointers between the
+ * contexts of one process), the caller gathers the `world` handles in rank order by any means, and every rank maps
+ * them (kg_peer_connect).  From then on the bucketing kernel of a batch stores its key runs STRAIGHT into the owners'
+ * receive buffers over NVLink -- no send buffer, no ncclSend/ncclRecv copy kernels, each key crosses HBM once less --
+ * and NCCL only carries the per-round count all-gather and a one-word "all stores have landed" collective.  A round
+ * whose busiest owner would overflow its receive buffer falls back to the ncclSend/ncclRecv path (kg_peer_stats).
+ * Without these calls the exchange is the ncclSend/ncclRecv path.                                                 */
+#define KG_PEER_HANDLE_BYTES 256
+int kg_peer_export(kg_ctx* ctx, void* handle_out);
+int kg_peer_connect(kg_ctx* ctx, const void* handles /* world * KG_PEER_HANDLE_BYTES, rank order */, int world);
+int kg_peer_stats(const kg_ctx* ctx, uint64_t* peer_rounds, uint64_t* fallback_rounds);
+
 /* ---- passes ------------------------------------------------------------------------------------ */
 /* KG_PASS_BLOOM: clears the filters.  KG_PASS_COUNT: allocates and clears the table with
  * next_prime3mod4(min_slots) slots, or next_prime3mod4(2*new_in_second) after a Bloom pass.         */

@@ -2,7 +2,8 @@
     python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 \
         tests/multigpu_check.py
 Every rank feeds its own slice of one FASTA (record-aligned split + k-1 context), k-mers are hash-sharded over
-NCCL, and the union of the shard exports must equal the oracle's count of the whole file, bit for bit."""
+NCCL, and the union of the shard exports must equal the oracle's count of the whole file, bit for bit.
+KG_PEER=1 in the environment switches every context to the fused bucket -> peer-store exchange (kg_peer_connect)."""
 import importlib
 import os
 import sys
@@ -45,6 +46,10 @@ def main():
         uid = [kg.comm_unique_id() if rank == 0 else None]
         dist.broadcast_object_list(uid, src=0)
         c.comm_init(uid[0], rank, world)
+        if os.environ.get("KG_PEER") == "1":     # fused bucket -> peer-store exchange instead of ncclSend/ncclRecv
+            handles = [None] * world
+            dist.all_gather_object(handles, c.peer_export())
+            c.peer_connect(handles)
         stats = []
         for which in ([K.PASS_BLOOM] if use_bloom else []) + [K.PASS_COUNT]:
             c.pass_begin(which)
@@ -67,7 +72,7 @@ def main():
                 ok = ok and sum(p[3] for p in parts) == truth.total_windows
             print(f"multigpu k={k} bloom={use_bloom} uneven={uneven} partitions={npart} world={world}: {'OK' if ok else 'MISMATCH'} "
                   f"(distinct {len(allc)} vs {want.n}; input {sum(p[2] for p in parts)} vs {truth.total_windows}; "
-                  f"per-shard {[len(p[1]) for p in parts]})", flush=True)
+                  f"per-shard {[len(p[1]) for p in parts]}; peer {c.peer_stats()})", flush=True)
             failures += 0 if ok else 1
         c.close()
     dist.barrier()

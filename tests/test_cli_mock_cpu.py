@@ -188,3 +188,14 @@ def test_cli_output_to_a_pipe(exe, tmp_path):
     assert p.returncode == 0
     kmer_lines = [l for l in p.stdout.splitlines(keepends=True) if len(l) > 22 and l[21:22] == b" " and set(l[:21]) <= set(b"ACGT")]
     assert sha_of(b"".join(kmer_lines)) == (case["n_lines"], case["sha256"])
+
+
+@pytest.mark.parametrize("gpus", [2, 4])
+def test_cli_peer_exchange_handshake(exe, gpus, tmp_path):
+    """--peer-exchange: every rank exports its handle, all wait, every rank connects with the handles in rank order
+    (the mock rejects a connect that sees a missing or misplaced handle); the output is unchanged"""
+    case = [c for c in CASES if c["input"] == "g5_long.fasta" and c["k"] == 51 and c["mode"] == 0 and c["a"] == 2][0]
+    out = tmp_path / "out.txt"
+    p = run(exe, [os.path.join(GOLDEN, "g5_long.fasta"), 51, "-m", 0, "-a", 2, "-t", 6, "-o", out, "--gpus", gpus, "--peer-exchange"] + size_args(case))
+    assert p.returncode == 0, p.stderr
+    assert sorted_sha(out) == (case["n_lines"], case["sha256"])

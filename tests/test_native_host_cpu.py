@@ -179,3 +179,46 @@ def test_writer_reports_errors(writer_exe, tmp_path):
     with open("/dev/full", "wb") as full:
         p = subprocess.run([writer_exe, str(src), "-", "2", "50"], stdout=full)
     assert p.returncode == 5
+
+
+@pytest.fixture(scope="module")
+def plan_exe():
+    return _build("exchange_plan_host", ["g++", "-O2", "-std=c++17", "-Wall", os.path.join(NATIVE, "exchange_plan_host.cpp")])
+
+
+@pytest.mark.parametrize("world,pl,seed", [(2, 1, 0), (2, 4, 1), (3, 5, 2), (8, 32, 3), (8, 128, 4), (5, 1, 5), (64, 16, 6)])
+def test_peer_exchange_plan_tiles_every_receive_buffer(plan_exe, world, pl, seed):
+    """csrc/kg_exchange_plan.hpp: simulate the fused bucket -> peer-store exchange on the CPU.  Every sender writes its
+    run for every bucket at remote_base[b] in the owner's buffer; the runs must tile [0, in_keys[d]) without gap or
+    overlap, partition-major with senders in rank order (what the L2-blocked insert walks front to back)"""
+    rng = np.random.default_rng(seed)
+    nb = world * pl
+    M = rng.integers(0, 50, size=(world, nb + 1)).astype(np.uint32)
+    M[rng.random((world, nb + 1)) < 0.3] = 0                      # empty runs are common
+    M[:, nb] = (rng.random(world) < 0.5).astype(np.uint32)        # done flags
+    if seed == 5:
+        M[:, nb] = 1
+    p = subprocess.run([plan_exe], input=struct.pack("<II", world, pl) + M.tobytes(), stdout=subprocess.PIPE, check=True)
+    rows = p.stdout.decode().strip().splitlines()
+    assert len(rows) == world
+    buffers = [dict() for _ in range(world)]                      # owner -> {key index: (partition, sender)}
+    in_keys = None
+    for r, line in enumerate(rows):
+        head, ins, bases = [x.split() for x in line.split("|")]
+        rank, my_in, max_in, all_done = map(int, head)
+        ins, bases = list(map(int, ins)), list(map(int, bases))
+        assert rank == r and len(bases) == nb
+        want_in = [int(M[:, d * pl:(d + 1) * pl].sum()) for d in range(world)]
+        assert ins == want_in and my_in == want_in[r] and max_in == max(want_in)
+        assert all_done == int(all(M[:, nb] != 0))
+        in_keys = ins
+        for b in range(nb):
+            d, part = divmod(b, pl)
+            for j in range(int(M[r, b])):
+                idx = bases[b] + j
+                assert idx not in buffers[d], "two runs overlap"
+                buffers[d][idx] = (part, r)
+    for d in range(world):
+        assert sorted(buffers[d]) == list(range(in_keys[d])), "the runs must tile the buffer"
+        order = [buffers[d][i] for i in range(in_keys[d])]
+        assert order == sorted(order), "partition-major, senders in rank order"
