@@ -34,6 +34,7 @@
 #include <vector>
 
 #include "kaarme_gpu.h"
+#define KG_READER_WITH_ZLIB 1
 #include "kg_reader.hpp"
 #include "kg_writer.hpp"
 
@@ -221,8 +222,15 @@ Format file_format(const std::string& path) {
         ifs.read((char*)b, 2);
         f.gz = ifs.gcount() == 2 && b[0] == 0x1f && b[1] == 0x8b;
     }
-    std::string ext = std::filesystem::path(path).extension().string();
+    std::filesystem::path pt(path);
+    std::string ext = pt.extension().string();
     char sym = (char)b[0];
+    if (f.gz) {   // main.cpp:35-43: the format is that of the compressed content
+        while (ext == ".gz") { pt.replace_extension(); ext = pt.extension().string(); }
+        sym = 0;
+        gzFile g = gzopen(path.c_str(), "rb");
+        if (g) { if (gzread(g, &sym, 1) != 1) sym = 0; gzclose(g); }
+    }
     if (ext == ".fasta" || ext == ".fa") { f.header_symbol = '>'; f.ill_formed = sym != '>'; }
     else if (ext == ".fastq" || ext == ".fq") { f.header_symbol = '@'; f.ill_formed = sym != '@'; }
     else { f.header_symbol = 0; f.ill_formed = std::string("actgACGT").find(sym) == std::string::npos || sym == 0; }
@@ -274,17 +282,27 @@ Slice make_slice(int fd, off_t file_size, int rank, int world, uint32_t k, bool 
 }
 
 // one pass over this rank's slice: the reader ring (kg_reader.hpp) fills pinned buffers with concurrent pread(2)s
-// while this thread feeds the GPU; a buffer returns to the ring as soon as kg_feed has copied it to the device
-void feed_file(kg_ctx* ctx, const std::string& path, uint8_t* const* bufs, int nbufs, size_t buf_bytes, const Slice& sl,
-               int io_threads) {
-    KG_CHECK(kg_stream_begin(ctx, sl.in_header ? 1 : 0));
-    kg::SliceReader reader(path, sl.ctx_lo, sl.lo, sl.hi, bufs, nbufs, buf_bytes, io_threads);
+// (or, for a .gz input, inflates the stream in order) while this thread feeds the GPU; a buffer returns to the ring
+// as soon as kg_feed has copied it to the device
+template <class Reader>
+void drain_reader(kg_ctx* ctx, Reader& reader) {
     kg::ReadChunk c;
     while (reader.next(c)) {
         KG_CHECK(kg_feed(ctx, c.data, c.len, c.context ? KG_FEED_CONTEXT : 0));   // returns once the H2D copy is done
         reader.release(c.buf);
     }
     if (reader.failed()) { std::cerr << "kaarme: " << reader.error() << "\n"; std::_Exit(1); }
+}
+void feed_file(kg_ctx* ctx, const std::string& path, bool gz, uint8_t* const* bufs, int nbufs, size_t buf_bytes, const Slice& sl,
+               int io_threads) {
+    KG_CHECK(kg_stream_begin(ctx, sl.in_header ? 1 : 0));
+    if (gz) {
+        kg::GzReader reader(path, bufs, nbufs, buf_bytes);
+        drain_reader(ctx, reader);
+    } else {
+        kg::SliceReader reader(path, sl.ctx_lo, sl.lo, sl.hi, bufs, nbufs, buf_bytes, io_threads);
+        drain_reader(ctx, reader);
+    }
 }
 
 // reusable barrier for the per-GPU host threads
@@ -504,7 +522,7 @@ int main(int argc, char** argv) {
     std::cout << "  working threads:          " << args.threads << std::endl;
     std::cout << "  output file:              " << args.output << std::endl;
 
-    if (fmt.gz) { std::cout << "gzip input is not supported by the GPU build (the reference's gz path is broken, SURVEY.md section 2)\n"; return 1; }
+    if (fmt.gz && args.gpus > 1) { std::cerr << "kaarme: a gzip stream cannot be cut into byte ranges: use --gpus 1 for .gz input\n"; return 1; }
     if (input_mode == 1) { std::cout << "Not implemented yet" << std::endl; return 0; }  // parallel_parser.hpp:797-800
     if (args.mode == 1) { std::cout << "Chosen mode not recognized\n"; return 0; }       // -m 1 (superseded variant) is out of scope
     if (args.k > 256) { std::cerr << "kaarme: k > 256 is not supported by the GPU build\n"; return 1; }
@@ -532,7 +550,7 @@ int main(int argc, char** argv) {
     {
         const size_t share = (size_t)fst.st_size / (size_t)world + (size_t)args.k + 4096;
         const size_t rounded = std::max<size_t>(1u << 20, (share + (1u << 20) - 1) >> 20 << 20);
-        if (!args.batch_mb && rounded < buf_bytes) buf_bytes = rounded;
+        if (!args.batch_mb && !fmt.gz && rounded < buf_bytes) buf_bytes = rounded;   // (a .gz size says nothing about its content)
     }
     char nccl_id[KG_UNIQUE_ID_BYTES];
     if (world > 1) {
@@ -597,14 +615,14 @@ int main(int argc, char** argv) {
         uint8_t* bufs[nbufs] = {nullptr, nullptr, nullptr};
         for (int i = 0; i < nbufs; i++) KG_CHECK(kg_host_alloc(buf_bytes, (void**)&bufs[i]));
         int fd = open(args.input.c_str(), O_RDONLY);
-        const Slice sl = make_slice(fd, fst.st_size, rank, world, (uint32_t)args.k, input_mode == KG_INPUT_FASTA);
+        const Slice sl = fmt.gz ? Slice{0, 0, 0, false} : make_slice(fd, fst.st_size, rank, world, (uint32_t)args.k, input_mode == KG_INPUT_FASTA);
         close(fd);
 
         if (args.bloom) {
             barrier.wait();
             if (rank == 0) { std::cout << "Starting parallel bloom filtering\n"; t_bloom0 = std::chrono::high_resolution_clock::now(); }  // parallel_parser.hpp:2689
             KG_CHECK(kg_pass_begin(ctx, KG_PASS_BLOOM));
-            feed_file(ctx, args.input, bufs, nbufs, buf_bytes, sl, io_threads);
+            feed_file(ctx, args.input, fmt.gz, bufs, nbufs, buf_bytes, sl, io_threads);
             KG_CHECK(kg_pass_end(ctx, &bloom_stats[rank]));
             barrier.wait();
             if (rank == 0) t_bloom1 = std::chrono::high_resolution_clock::now();
@@ -622,7 +640,7 @@ int main(int argc, char** argv) {
             std::cout << (args.mode == 0 ? "Starting atomic flag basic hash table\n" : "Starting atomic variable pointer hash table\n");
             if (world == 1) std::cout << "Hash table size is: " << table_slots[0] << "\n";  // functions_math.cpp:90
         }
-        feed_file(ctx, args.input, bufs, nbufs, buf_bytes, sl, io_threads);
+        feed_file(ctx, args.input, fmt.gz, bufs, nbufs, buf_bytes, sl, io_threads);
         KG_CHECK(kg_pass_end(ctx, &count_stats[rank]));
         if (args.mode == KG_TABLE_KAARME && world == 1) {
             KG_CHECK(kg_compact(ctx, &compact_stats[rank]));

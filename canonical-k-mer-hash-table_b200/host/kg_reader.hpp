@@ -25,6 +25,9 @@
 #include <thread>
 #include <unistd.h>
 #include <vector>
+#ifdef KG_READER_WITH_ZLIB
+#include <zlib.h>
+#endif
 
 namespace kg {
 
@@ -171,5 +174,110 @@ class SliceReader {
     std::string error_;
     std::thread producer_;
 };
+
+// gzip input (a genuine extension: the reference's zlib path, text_reader.h:38-89, seeks backwards in the compressed
+// stream by the COMPRESSED size and does not work).  Same ring, same interface; one producer thread inflates the
+// stream in order with zlib (concatenated members included), so a .gz input is bound by inflate (~0.3-0.5 GB/s), not
+// by the GPU.  A compressed stream cannot be cut into byte ranges: one rank only (the CLI refuses --gpus > 1).
+#ifdef KG_READER_WITH_ZLIB
+class GzReader {
+  public:
+    GzReader(const std::string& path, uint8_t* const* bufs, int nbufs, size_t buf_bytes)
+        : path_(path), bufs_(bufs, bufs + nbufs), buf_bytes_(buf_bytes) {
+        for (int i = 0; i < nbufs; i++) free_.push_back(i);
+        producer_ = std::thread([this] { produce(); });
+    }
+    ~GzReader() {
+        {
+            std::lock_guard<std::mutex> g(m_);
+            stop_ = true;
+        }
+        cv_.notify_all();
+        if (producer_.joinable()) producer_.join();
+    }
+    GzReader(const GzReader&) = delete;
+    GzReader& operator=(const GzReader&) = delete;
+    bool next(ReadChunk& out) {
+        std::unique_lock<std::mutex> lk(m_);
+        cv_.wait(lk, [&] { return !ready_.empty() || done_; });
+        if (ready_.empty()) return false;
+        out = ready_.front();
+        ready_.pop_front();
+        return true;
+    }
+    void release(int buf) {
+        {
+            std::lock_guard<std::mutex> g(m_);
+            free_.push_back(buf);
+        }
+        cv_.notify_all();
+    }
+    bool failed() const { return failed_; }
+    const std::string& error() const { return error_; }
+
+  private:
+    void produce() {
+        gzFile f = gzopen(path_.c_str(), "rb");
+        if (!f) { finish("cannot open " + path_); return; }
+        gzbuffer(f, 1u << 20);
+        std::string err;
+        for (;;) {
+            int b;
+            {
+                std::unique_lock<std::mutex> lk(m_);
+                cv_.wait(lk, [&] { return !free_.empty() || stop_; });
+                if (stop_) break;
+                b = free_.front();
+                free_.pop_front();
+            }
+            size_t got = 0;
+            while (got < buf_bytes_) {
+                const unsigned want = (unsigned)std::min<size_t>(buf_bytes_ - got, 1u << 30);
+                const int r = gzread(f, bufs_[b] + got, want);
+                if (r < 0) { int e = 0; const char* msg = gzerror(f, &e); err = std::string("gzip error in ") + path_ + ": " + (msg ? msg : "?"); break; }
+                if (r == 0) break;
+                got += (size_t)r;
+            }
+            if (!err.empty()) break;
+            if (got == 0) {   // clean end of stream -- unless zlib saw a truncated member
+                int e = 0;
+                const char* msg = gzerror(f, &e);
+                if (e != Z_OK && e != Z_STREAM_END) err = std::string("gzip error in ") + path_ + ": " + (msg ? msg : "?");
+                break;
+            }
+            ReadChunk c;
+            c.data = bufs_[b]; c.len = got; c.context = false; c.buf = b;
+            {
+                std::lock_guard<std::mutex> g(m_);
+                ready_.push_back(c);
+            }
+            cv_.notify_all();
+        }
+        if (err.empty() && !stop_) {   // gzclose reports a stream that ended inside a member (Z_BUF_ERROR)
+            const int rc = gzclose_r(f);
+            if (rc != Z_OK) err = "gzip error in " + path_ + ": unexpected end of file";
+        } else {
+            gzclose_r(f);
+        }
+        finish(err);
+    }
+    void finish(const std::string& err) {
+        std::lock_guard<std::mutex> g(m_);
+        if (!err.empty()) { failed_ = true; error_ = err; }
+        done_ = true;
+        cv_.notify_all();
+    }
+    std::string path_;
+    std::vector<uint8_t*> bufs_;
+    size_t buf_bytes_;
+    std::mutex m_;
+    std::condition_variable cv_;
+    std::deque<int> free_;
+    std::deque<ReadChunk> ready_;
+    bool done_ = false, stop_ = false, failed_ = false;
+    std::string error_;
+    std::thread producer_;
+};
+#endif
 
 }  // namespace kg

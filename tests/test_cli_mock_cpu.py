@@ -36,7 +36,7 @@ def exe(oracle):
         subprocess.run(["g++", "-O2", "-std=c++17", "-Wall", "-fPIC", "-shared", "-o", lib, srcs[0], "-L" + odir, "-loracle",
                         "-Wl,-rpath," + odir], check=True)
         subprocess.run(["g++", "-O2", "-std=c++17", "-Wall", "-pthread", "-I" + os.path.join(ROOT, "include"), "-o", out, srcs[1],
-                        "-L" + BUILD, "-lkaarme_gpu_mock", "-Wl,-rpath,$ORIGIN"], check=True)
+                        "-L" + BUILD, "-lkaarme_gpu_mock", "-lz", "-Wl,-rpath,$ORIGIN"], check=True)
     return out
 
 
@@ -199,3 +199,51 @@ def test_cli_peer_exchange_handshake(exe, gpus, tmp_path):
     p = run(exe, [os.path.join(GOLDEN, "g5_long.fasta"), 51, "-m", 0, "-a", 2, "-t", 6, "-o", out, "--gpus", gpus, "--peer-exchange"] + size_args(case))
     assert p.returncode == 0, p.stderr
     assert sorted_sha(out) == (case["n_lines"], case["sha256"])
+
+
+def test_cli_gzip_input(exe, oracle, big_fasta, tmp_path):
+    """.gz input (the reference's zlib path does not work; here the stream is inflated in order into the same ring):
+    format taken from the name under the .gz, one member or several, many batches; truncated streams and --gpus > 1
+    are refused"""
+    import gzip
+    case = [c for c in CASES if c["input"] == "g2_reads.fa" and c["k"] == 21 and c["mode"] == 0 and c["a"] == 2 and c["unique"] is None][0]
+    raw = open(os.path.join(GOLDEN, "g2_reads.fa"), "rb").read()
+    gz = tmp_path / "g2_reads.fa.gz"
+    gz.write_bytes(gzip.compress(raw))
+    out = tmp_path / "out.txt"
+    p = run(exe, [gz, 21, "-m", 0, "-a", 2, "-s", case["slots"], "-o", out])
+    assert p.returncode == 0, p.stderr
+    assert "gzip compressed:          yes" in p.stdout and "input format:             FASTA" in p.stdout
+    assert sorted_sha(out) == (case["n_lines"], case["sha256"])
+    # two members back to back = the concatenated text; cut in the middle of a record
+    cut = raw.index(b"\n", len(raw) // 2) + 10
+    gz2 = tmp_path / "two.fa.gz"
+    gz2.write_bytes(gzip.compress(raw[:cut]) + gzip.compress(raw[cut:]))
+    p = run(exe, [gz2, 21, "-m", 0, "-a", 2, "-s", case["slots"], "-o", out])
+    assert p.returncode == 0 and sorted_sha(out) == (case["n_lines"], case["sha256"])
+    # Bloom mode reads the stream twice
+    bcase = [c for c in CASES if c["input"] == "g5_long.fasta" and c["k"] == 51 and c["mode"] == 0 and c["a"] == 2 and c["unique"]][0]
+    gz3 = tmp_path / "g5.fasta.gz"
+    gz3.write_bytes(gzip.compress(open(os.path.join(GOLDEN, "g5_long.fasta"), "rb").read()))
+    p = run(exe, [gz3, 51, "-m", 0, "-a", 2, "-o", out] + size_args(bcase))
+    assert p.returncode == 0 and sorted_sha(out) == (bcase["n_lines"], bcase["sha256"])
+    # many 1 MiB batches out of one stream
+    data = open(big_fasta, "rb").read()
+    gz4 = tmp_path / "big.fasta.gz"
+    gz4.write_bytes(gzip.compress(data, 1))
+    p = run(exe, [gz4, 31, "-m", 0, "-a", 2, "-s", 2_000_000, "-o", out, "--batch-mb", 1])
+    assert p.returncode == 0 and sorted_sha(out) == sha_of(oracle.count(data, 31).text(2, oracle.TABLE_PLAIN))
+    # default output name strips one extension, like main.cpp:189-191
+    p = run(exe, [gz, 21, "-m", 0, "-s", case["slots"]], cwd=tmp_path)
+    assert p.returncode == 0 and (tmp_path / "g2_reads.fa.kaarme_counts").exists()
+    # refused: truncated stream, sharding, content that does not match the name
+    bad = tmp_path / "cut.fa.gz"
+    bad.write_bytes(gz.read_bytes()[:-200])
+    p = run(exe, [bad, 21, "-m", 0, "-s", case["slots"], "-o", out])
+    assert p.returncode == 1 and "gzip error" in p.stderr
+    p = run(exe, [gz, 21, "-m", 0, "-s", case["slots"], "-o", out, "--gpus", 2])
+    assert p.returncode == 1 and "--gpus 1" in p.stderr
+    plain_named_fa = tmp_path / "plain.fa.gz"
+    plain_named_fa.write_bytes(gzip.compress(b"ACGTACGT\n"))
+    p = run(exe, [plain_named_fa, 5, "-s", 100])
+    assert p.returncode == 1 and "ill-formed" in p.stderr
