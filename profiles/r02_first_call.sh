@@ -1,0 +1,23 @@
+#!/bin/bash
+# First GPU call of the next round (one B200): everything that was written after this round's GPU budget ran out.
+#   1. the GPU test suite (export buffers were re-sized, CLI reader/writer changed, error paths touched)
+#   2. the rows of DESIGN.md section 9 again (profiles/io_rows_probe.sh): reader ring, GPU text dump, parallel writer
+#   3. overlap experiment: blocks per SM of the persistent insert kernel
+# Output under gpurun_out/: r02_tests.log, io_probe.log, r02_insert_grid.jsonl.  ~5 min of box time.
+set -u
+OUT=gpurun_out; mkdir -p $OUT
+timeout 400 python -u -m pytest tests -m gpu -x -q --durations=10 > $OUT/r02_tests.log 2>&1; echo "pytest rc=$?" >> $OUT/r02_tests.log
+timeout 120 bash profiles/io_rows_probe.sh > /dev/null 2>&1
+: > $OUT/r02_insert_grid.jsonl
+for g in 8 6 5 4 3; do
+  echo "# KG_INSERT_GRID=$g" >> $OUT/r02_insert_grid.jsonl
+  KG_INSERT_GRID=$g timeout 120 python bench.py --steps 3 --warmup 3 --no-cpu-baseline --no-e2e 2>/dev/null | grep '^{' >> $OUT/r02_insert_grid.jsonl
+done
+python - <<'PY'
+import json
+for line in open('gpurun_out/r02_insert_grid.jsonl'):
+    if line.startswith('#'): print(line.strip()); continue
+    d = json.loads(line)
+    print(f"  {d['value']/1e9:6.2f} G k-mers/s  {d['ms_per_step']:7.2f} ms/step  stages {d.get('stage_ms_per_step')}  roofline.frac {d['roofline']['frac']:.3f}")
+PY
+tail -3 $OUT/r02_tests.log; cat $OUT/io_probe.log
