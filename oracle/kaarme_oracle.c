@@ -239,8 +239,8 @@ static int map_add(ko_map* m, const uint64_t* key, uint64_t inc) {
 }
 
 /* sort helper: order slot indices by key, ascending (word 0 most significant) */
-static uint32_t g_sortW;
-static const uint64_t* g_sortkeys;
+static _Thread_local uint32_t g_sortW;              /* comparator context: per thread, so concurrent ko_count calls are safe */
+static _Thread_local const uint64_t* g_sortkeys;
 static int cmp_slot(const void* a, const void* b) {
     const uint64_t* ka = g_sortkeys + (*(const uint64_t*)a) * g_sortW;
     const uint64_t* kb = g_sortkeys + (*(const uint64_t*)b) * g_sortW;

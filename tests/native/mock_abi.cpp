@@ -34,7 +34,7 @@ struct Shared {
     int users = 0;
 };
 Shared g_shared;
-std::mutex g_oracle;   // the oracle is single-threaded by design (its sort comparator uses file-scope state)
+std::mutex g_oracle;   // one oracle call at a time (keeps the test double's memory use bounded with many ranks)
 thread_local std::string g_err;
 
 uint64_t next_prime3mod4(uint64_t c) { return ko_next_prime3mod4(c); }
