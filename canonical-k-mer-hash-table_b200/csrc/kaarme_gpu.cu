@@ -132,6 +132,7 @@ struct kg_ctx {
     uint64_t peer_rounds = 0, peer_fallback_rounds = 0;
     u32* d_work = nullptr;              // work counter of the persistent insert kernels
     u32 insert_grid = 148 * 8;          // resident blocks of the grid-stride insert kernels (SMs x blocks/SM)
+    bool parse_tma = false;             // KG_PARSE_TMA=1: parse tiles staged by TMA bulk copies (unmeasured; opt-in)
     // Kaarme representation (after kg_compact)
     KgKaarme kaarme{nullptr, nullptr, 0, 0};
     KgCompactStats* d_cstats = nullptr;
@@ -339,6 +340,7 @@ extern "C" int kg_create(const kg_config* cfg, kg_ctx** out) {
     c->cfg = *cfg;
     c->insert_grid = (u32)prop.multiProcessorCount * 8u;
     if (const char* e = getenv("KG_INSERT_GRID")) c->insert_grid = (u32)atoi(e) * (u32)prop.multiProcessorCount;
+    if (const char* e = getenv("KG_PARSE_TMA")) c->parse_tma = atoi(e) != 0;
     c->W = (int)((cfg->k + 31) / 32);
     c->batch_bytes = cfg->batch_bytes ? cfg->batch_bytes : KG_DEFAULT_BATCH;
     if (c->batch_bytes > KG_MAX_BATCH) c->batch_bytes = KG_MAX_BATCH;
@@ -1121,21 +1123,28 @@ static int process_batch(kg_ctx* c, const uint8_t* d_in, size_t n, uint32_t flag
     KG_CUDA(c, cudaMemsetAsync(c->d_words, 0, sizeof(u64) * nwords, s));
     KG_CUDA(c, cudaMemsetAsync(c->d_brk, 0, sizeof(u32) * nwords, s));
     kg_carry_restore<<<1, 32, 0, s>>>(c->d_words, c->d_brk, c->d_stream, c->d_carry_words, c->d_carry_brk, c->carry_max_words);
+    const bool tma = c->parse_tma;   // opt-in: tiles staged through shared memory by a TMA bulk copy (kg_fetch16<true>)
     if (fasta) {
-        kg_hdr_summary<<<ntiles, KG_PT, 0, s>>>(d_in, n, c->d_tile_hdr_eff);
+        if (tma) kg_hdr_summary<true><<<ntiles, KG_PT, 0, s>>>(d_in, n, c->d_tile_hdr_eff);
+        else kg_hdr_summary<false><<<ntiles, KG_PT, 0, s>>>(d_in, n, c->d_tile_hdr_eff);
         kg_lww_scan<<<1, 1024, 0, s>>>(c->d_tile_hdr_eff, c->d_tile_hdr_in, ntiles, &c->d_stream->in_header);
-        kg_tile_count<true><<<ntiles, KG_PT, 0, s>>>(d_in, n, c->d_tile_hdr_in, c->d_tile_nbases, c->d_tile_pend_eff);
+        if (tma) kg_tile_count<true, true><<<ntiles, KG_PT, 0, s>>>(d_in, n, c->d_tile_hdr_in, c->d_tile_nbases, c->d_tile_pend_eff);
+        else kg_tile_count<true, false><<<ntiles, KG_PT, 0, s>>>(d_in, n, c->d_tile_hdr_in, c->d_tile_nbases, c->d_tile_pend_eff);
         c->launches += 3;
     } else {
-        kg_tile_count<false><<<ntiles, KG_PT, 0, s>>>(d_in, n, c->d_tile_hdr_in, c->d_tile_nbases, c->d_tile_pend_eff);
+        if (tma) kg_tile_count<false, true><<<ntiles, KG_PT, 0, s>>>(d_in, n, c->d_tile_hdr_in, c->d_tile_nbases, c->d_tile_pend_eff);
+        else kg_tile_count<false, false><<<ntiles, KG_PT, 0, s>>>(d_in, n, c->d_tile_hdr_in, c->d_tile_nbases, c->d_tile_pend_eff);
         c->launches += 1;
     }
     kg_tile_scan<<<1, 1024, 0, s>>>(c->d_tile_nbases, c->d_tile_off, ntiles, c->d_stream);
     kg_lww_scan<<<1, 1024, 0, s>>>(c->d_tile_pend_eff, c->d_tile_pend_in, ntiles, &c->d_stream->pending_break);
-    if (fasta)
-        kg_tile_pack<true><<<ntiles, KG_PT, 0, s>>>(d_in, n, c->d_tile_hdr_in, c->d_tile_off, c->d_tile_pend_in, c->d_words, c->d_brk);
-    else
-        kg_tile_pack<false><<<ntiles, KG_PT, 0, s>>>(d_in, n, c->d_tile_hdr_in, c->d_tile_off, c->d_tile_pend_in, c->d_words, c->d_brk);
+    if (fasta) {
+        if (tma) kg_tile_pack<true, true><<<ntiles, KG_PT, 0, s>>>(d_in, n, c->d_tile_hdr_in, c->d_tile_off, c->d_tile_pend_in, c->d_words, c->d_brk);
+        else kg_tile_pack<true, false><<<ntiles, KG_PT, 0, s>>>(d_in, n, c->d_tile_hdr_in, c->d_tile_off, c->d_tile_pend_in, c->d_words, c->d_brk);
+    } else {
+        if (tma) kg_tile_pack<false, true><<<ntiles, KG_PT, 0, s>>>(d_in, n, c->d_tile_hdr_in, c->d_tile_off, c->d_tile_pend_in, c->d_words, c->d_brk);
+        else kg_tile_pack<false, false><<<ntiles, KG_PT, 0, s>>>(d_in, n, c->d_tile_hdr_in, c->d_tile_off, c->d_tile_pend_in, c->d_words, c->d_brk);
+    }
     c->launches += 4;
     if (e1) cudaEventRecord(e1, s);
     if (!(flags & KG_FEED_CONTEXT)) {

@@ -39,6 +39,44 @@ __device__ __forceinline__ uint4 kg_load_tile16(const uint8_t* in, size_t n, siz
     }
     return v;
 }
+// TMA-staged variant (opt-in, KG_PARSE_TMA=1): ONE elected thread issues a 1-D bulk copy (cp.async.bulk, the TMA unit;
+// SASS UBLKCP) of the block's whole 4 KiB tile into shared memory and arms an mbarrier with the byte count; every
+// thread waits on the barrier's phase and takes its 16 bytes with one LDS.128 -- 256 LDG.128 per block become one
+// asynchronous copy that does not occupy the LSU.  Only full tiles (the source must be 16-byte aligned and the size a
+// multiple of 16); the ragged last tile of a batch takes the LDG path.  `tile_base` is block-uniform.
+template <bool TMA>
+__device__ __forceinline__ uint4 kg_fetch16(const uint8_t* in, size_t n, size_t tile_base, size_t off) {
+    if constexpr (TMA) {
+        __shared__ __align__(128) uint8_t s_tile[KG_TILE];
+        __shared__ __align__(8) unsigned long long s_mbar;
+        if (tile_base + KG_TILE <= n) {                         // uniform over the block
+            const u32 mbar = (u32)__cvta_generic_to_shared(&s_mbar);
+            const u32 dst = (u32)__cvta_generic_to_shared(s_tile);
+            if (threadIdx.x == 0) {
+                asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(mbar) : "memory");
+                asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+            }
+            __syncthreads();
+            if (threadIdx.x == 0) {
+                asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mbar), "r"((u32)KG_TILE) : "memory");
+                asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                             ::"r"(dst), "l"(in + tile_base), "r"((u32)KG_TILE), "r"(mbar) : "memory");
+            }
+            asm volatile(
+                "{\n\t"
+                ".reg .pred p;\n\t"
+                "KG_TMA_WAIT:\n\t"
+                "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], 0;\n\t"
+                "@p bra KG_TMA_DONE;\n\t"
+                "bra KG_TMA_WAIT;\n\t"
+                "KG_TMA_DONE:\n\t"
+                "}" ::"r"(mbar) : "memory");
+            return *reinterpret_cast<const uint4*>(s_tile + (off - tile_base));
+        }
+    }
+    return kg_load_tile16(in, n, off);
+}
+
 // combine for last-writer-wins: later non-NONE effect overrides
 __device__ __forceinline__ u32 kg_lww(u32 earlier, u32 later) { return later != KG_EFF_NONE ? later : earlier; }
 
@@ -129,12 +167,13 @@ __device__ __forceinline__ u32 kg_hdr_effect16(const KgMasks16& m) {
 }
 
 // ---- pass A (FASTA only): per-tile header effect ------------------------------------------------------
+template <bool TMA>
 __global__ void __launch_bounds__(KG_PT) kg_hdr_summary(const uint8_t* __restrict__ in, size_t n,
                                                         u32* __restrict__ tile_hdr_eff) {
     __shared__ u32 sm[8];
     const size_t off = (size_t)blockIdx.x * KG_TILE + (size_t)threadIdx.x * KG_BPT;
     int nvalid = off >= n ? 0 : (n - off >= 16 ? 16 : (int)(n - off));
-    uint4 v = kg_load_tile16(in, n, off);
+    uint4 v = kg_fetch16<TMA>(in, n, (size_t)blockIdx.x * KG_TILE, off);
     const KgMasks16 m = kg_masks16(v, nvalid);
     u32 tot;
     kg_block_lww_exclusive(kg_hdr_effect16(m), sm, &tot);
@@ -258,14 +297,14 @@ __device__ __forceinline__ KgThreadParse kg_parse16(const KgMasks16& m, int nval
 }
 
 // ---- pass B: per-tile base count and pending-break effect -----------------------------------------------
-template <bool FASTA>
+template <bool FASTA, bool TMA>
 __global__ void __launch_bounds__(KG_PT) kg_tile_count(const uint8_t* __restrict__ in, size_t n,
                                                        const u32* __restrict__ tile_hdr_in,
                                                        u32* __restrict__ tile_nbases, u32* __restrict__ tile_pend_eff) {
     __shared__ u32 sm[8];
     const size_t off = (size_t)blockIdx.x * KG_TILE + (size_t)threadIdx.x * KG_BPT;
     int nvalid = off >= n ? 0 : (n - off >= 16 ? 16 : (int)(n - off));
-    uint4 v = kg_load_tile16(in, n, off);
+    uint4 v = kg_fetch16<TMA>(in, n, (size_t)blockIdx.x * KG_TILE, off);
     const KgMasks16 m = kg_masks16(v, nvalid);
     u32 hdr_in = 0, tot;
     if (FASTA) {
@@ -310,7 +349,7 @@ __global__ void __launch_bounds__(1024) kg_tile_scan(const u32* __restrict__ til
 
 // ---- pass C: pack bases and break bits ---------------------------------------------------------------------
 // words/brk must be zero beyond the carried head; tile boundary words are merged with atomicOr.
-template <bool FASTA>
+template <bool FASTA, bool TMA>
 __global__ void __launch_bounds__(KG_PT) kg_tile_pack(const uint8_t* __restrict__ in, size_t n,
                                                       const u32* __restrict__ tile_hdr_in,
                                                       const u32* __restrict__ tile_off,
@@ -321,7 +360,7 @@ __global__ void __launch_bounds__(KG_PT) kg_tile_pack(const uint8_t* __restrict_
     __shared__ u32 sb[KG_TILE / 32 + 2];
     const size_t off = (size_t)blockIdx.x * KG_TILE + (size_t)threadIdx.x * KG_BPT;
     int nvalid = off >= n ? 0 : (n - off >= 16 ? 16 : (int)(n - off));
-    uint4 v = kg_load_tile16(in, n, off);
+    uint4 v = kg_fetch16<TMA>(in, n, (size_t)blockIdx.x * KG_TILE, off);
     const KgMasks16 m = kg_masks16(v, nvalid);
     for (u32 i = threadIdx.x; i < KG_TILE / 32 + 2; i += KG_PT) { sw[i] = 0; sb[i] = 0; }
     u32 hdr_in = 0, tot;
