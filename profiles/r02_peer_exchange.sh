@@ -13,8 +13,17 @@ timeout 120 bash tests/multigpu_cli_check.sh > $OUT/r02_multigpu_cli.log 2>&1; t
 # then the bench, both ways (only meaningful if the parity lines above say OK)
 timeout 300 $TR --master-port 29513 bench.py --gpus $N --steps 3 --warmup 3 --no-cpu-baseline 2>/dev/null | grep '^{' > $OUT/r02_bench_n${N}_nccl.json
 KAARME_PEER=1 timeout 300 $TR --master-port 29514 bench.py --gpus $N --steps 3 --warmup 3 --no-cpu-baseline 2>/dev/null | grep '^{' > $OUT/r02_bench_n${N}_peer.json
+# run length on the wire vs table region size: partitions per owner in peer mode
+: > $OUT/r02_peer_partitions_n${N}.jsonl
+for p in 16 32 64 128; do
+  echo "# partitions=$p" >> $OUT/r02_peer_partitions_n${N}.jsonl
+  KAARME_PEER=1 timeout 200 $TR --master-port $((29520 + p)) bench.py --gpus $N --steps 3 --warmup 3 --no-cpu-baseline --no-e2e --partitions $p 2>/dev/null | grep '^{' >> $OUT/r02_peer_partitions_n${N}.jsonl
+done
 python - <<PY
 import json
+for line in open("gpurun_out/r02_peer_partitions_n${N}.jsonl"):
+    if line.startswith("#"): print(line.strip()); continue
+    d = json.loads(line); print(f"  {d['value']/1e9:.2f} G k-mers/s  {d['ms_per_step']:.2f} ms/step  stages {d.get('stage_ms_per_step')}")
 for tag in ("nccl", "peer"):
     try:
         d = json.load(open("gpurun_out/r02_bench_n${N}_%s.json" % tag))
