@@ -132,6 +132,7 @@ struct kg_ctx {
     uint64_t peer_rounds = 0, peer_fallback_rounds = 0;
     u32* d_work = nullptr;              // work counter of the persistent insert kernels
     u32 insert_grid = 148 * 8;          // resident blocks of the grid-stride insert kernels (SMs x blocks/SM)
+    bool feed_prefetch = false;         // KG_FEED_PREFETCH=1: pipelined H2D in kg_feed (unmeasured; opt-in)
     bool parse_tma = false;             // KG_PARSE_TMA=1: parse tiles staged by TMA bulk copies (unmeasured; opt-in)
     // Kaarme representation (after kg_compact)
     KgKaarme kaarme{nullptr, nullptr, 0, 0};
@@ -341,6 +342,7 @@ extern "C" int kg_create(const kg_config* cfg, kg_ctx** out) {
     c->insert_grid = (u32)prop.multiProcessorCount * 8u;
     if (const char* e = getenv("KG_INSERT_GRID")) c->insert_grid = (u32)atoi(e) * (u32)prop.multiProcessorCount;
     if (const char* e = getenv("KG_PARSE_TMA")) c->parse_tma = atoi(e) != 0;
+    if (const char* e = getenv("KG_FEED_PREFETCH")) c->feed_prefetch = atoi(e) != 0;
     c->W = (int)((cfg->k + 31) / 32);
     c->batch_bytes = cfg->batch_bytes ? cfg->batch_bytes : KG_DEFAULT_BATCH;
     if (c->batch_bytes > KG_MAX_BATCH) c->batch_bytes = KG_MAX_BATCH;
@@ -1211,6 +1213,38 @@ extern "C" int kg_feed_device(kg_ctx* c, const void* device_bytes, size_t n, uin
     return KG_OK;
 }
 
+// Opt-in (KG_FEED_PREFETCH=1, unmeasured): software-pipelined feed of a pinned buffer.  The H2D copy of chunk i+1 is
+// issued on the copy stream BEFORE process_batch(i) -- which, with world > 1, blocks the host on the count all-gather
+// of chunk i -- and is gated on the device (cudaStreamWaitEvent on the raw buffer's free event) instead of a host wait,
+// so the copies leave the compute stream's critical path.
+static int feed_pinned_pipelined(kg_ctx* c, const uint8_t* bytes, size_t n, uint32_t flags) {
+    const size_t B = c->batch_bytes, nchunks = (n + B - 1) / B;
+    const int raw0 = c->raw_idx;
+    auto issue = [&](size_t i) -> int {
+        const int idx = (int)((raw0 + i) & 1);
+        const size_t off = i * B, len = n - off < B ? n - off : B;
+        KG_CUDA(c, cudaStreamWaitEvent(c->s_copy, c->ev_raw_free[idx], 0));   // compute is done with this buffer (chunk i-2)
+        KG_CUDA(c, cudaMemcpyAsync(c->d_raw[idx], bytes + off, len, cudaMemcpyHostToDevice, c->s_copy));
+        KG_CUDA(c, cudaEventRecord(c->ev_copy_done[idx], c->s_copy));
+        return KG_OK;
+    };
+    int rc = issue(0);
+    if (rc) return rc;
+    for (size_t i = 0; i < nchunks; i++) {
+        const int idx = (int)((raw0 + i) & 1);
+        const size_t off = i * B, len = n - off < B ? n - off : B;
+        KG_CUDA(c, cudaStreamWaitEvent(c->s_compute, c->ev_copy_done[idx], 0));
+        if (i + 1 < nchunks) { rc = issue(i + 1); if (rc) return rc; }
+        rc = process_batch(c, c->d_raw[idx], len, flags);
+        if (rc) return rc;
+        KG_CUDA(c, cudaEventRecord(c->ev_raw_free[idx], c->s_compute));
+    }
+    c->raw_idx = (int)((raw0 + nchunks) & 1);
+    // the caller owns `bytes` again when we return: the last copies must have left it
+    KG_CUDA(c, cudaStreamSynchronize(c->s_copy));
+    return KG_OK;
+}
+
 extern "C" int kg_feed(kg_ctx* c, const uint8_t* bytes, size_t n, uint32_t flags) {
     int rc = check_feed(c);
     if (rc) return rc;
@@ -1225,6 +1259,7 @@ extern "C" int kg_feed(kg_ctx* c, const uint8_t* bytes, size_t n, uint32_t flags
     } else {
         cudaGetLastError();
     }
+    if (pinned && c->feed_prefetch && n > c->batch_bytes) return feed_pinned_pipelined(c, bytes, n, flags);
     for (size_t off = 0; off < n; off += c->batch_bytes) {
         size_t len = n - off < c->batch_bytes ? n - off : c->batch_bytes;
         const int idx = c->raw_idx; c->raw_idx ^= 1;

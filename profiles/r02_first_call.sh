@@ -20,6 +20,8 @@ for g in 8 6 5 4 3; do
   echo "# KG_INSERT_GRID=$g" >> $OUT/r02_insert_grid.jsonl
   KG_INSERT_GRID=$g timeout 120 python bench.py --steps 3 --warmup 3 --no-cpu-baseline --no-e2e 2>/dev/null | grep '^{' >> $OUT/r02_insert_grid.jsonl
 done
+KG_FEED_PREFETCH=1 timeout 200 python -u -m pytest tests/test_gpu_parity.py -x -q > $OUT/r02_tests_prefetch.log 2>&1; echo "pytest rc=$?" >> $OUT/r02_tests_prefetch.log
+tail -2 $OUT/r02_tests_prefetch.log
 python - <<'PY'
 import json
 for line in open('gpurun_out/r02_insert_grid.jsonl'):

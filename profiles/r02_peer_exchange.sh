@@ -19,8 +19,14 @@ for p in 16 32 64 128; do
   echo "# partitions=$p" >> $OUT/r02_peer_partitions_n${N}.jsonl
   KAARME_PEER=1 timeout 200 $TR --master-port $((29520 + p)) bench.py --gpus $N --steps 3 --warmup 3 --no-cpu-baseline --no-e2e --partitions $p 2>/dev/null | grep '^{' >> $OUT/r02_peer_partitions_n${N}.jsonl
 done
+# end-to-end gap: pipelined H2D in kg_feed, NCCL exchange
+KG_FEED_PREFETCH=1 timeout 300 $TR --master-port 29515 bench.py --gpus $N --steps 3 --warmup 3 --no-cpu-baseline 2>/dev/null | grep '^{' > $OUT/r02_bench_n${N}_prefetch.json
 python - <<PY
 import json
+try:
+    d = json.load(open("gpurun_out/r02_bench_n${N}_prefetch.json")); print("prefetch", f"{d['value']/1e9:.2f} G k-mers/s device  e2e {d['e2e']['value']/1e9:.2f}")
+except Exception as e:
+    print("prefetch: no result", e)
 for line in open("gpurun_out/r02_peer_partitions_n${N}.jsonl"):
     if line.startswith("#"): print(line.strip()); continue
     d = json.loads(line); print(f"  {d['value']/1e9:.2f} G k-mers/s  {d['ms_per_step']:.2f} ms/step  stages {d.get('stage_ms_per_step')}")
