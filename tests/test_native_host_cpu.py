@@ -26,6 +26,8 @@ def _build(name, cmd):
     exe = os.path.join(BUILD, name)
     srcs = [a for a in cmd if a.endswith((".cu", ".cpp"))]
     deps = srcs + [os.path.join(ROOT, "canonical-k-mer-hash-table_b200", "csrc", "kg_text.cuh"),
+                   os.path.join(ROOT, "canonical-k-mer-hash-table_b200", "csrc", "kg_refhash.cuh"),
+                   os.path.join(ROOT, "canonical-k-mer-hash-table_b200", "csrc", "kg_exchange_plan.hpp"),
                    os.path.join(ROOT, "canonical-k-mer-hash-table_b200", "host", "kg_reader.hpp"),
                    os.path.join(ROOT, "canonical-k-mer-hash-table_b200", "host", "kg_writer.hpp")]
     if not os.path.exists(exe) or any(os.path.getmtime(d) > os.path.getmtime(exe) for d in deps):
@@ -222,3 +224,54 @@ def test_peer_exchange_plan_tiles_every_receive_buffer(plan_exe, world, pl, seed
         assert sorted(buffers[d]) == list(range(in_keys[d])), "the runs must tile the buffer"
         order = [buffers[d][i] for i in range(in_keys[d])]
         assert order == sorted(order), "partition-major, senders in rank order"
+
+
+@pytest.fixture(scope="module")
+def refhash_exe():
+    nvcc = "/usr/local/cuda/bin/nvcc" if os.path.exists("/usr/local/cuda/bin/nvcc") else "nvcc"
+    return _build("refhash_host", [nvcc, "-O2", "-std=c++17", "-Wno-deprecated-gpu-targets", os.path.join(NATIVE, "refhash_host.cu")])
+
+
+def _refhash_windows(exe, codes, k):
+    payload = struct.pack("<II", k, len(codes)) + bytes(codes)
+    out = subprocess.run([exe], input=payload, stdout=subprocess.PIPE, check=True).stdout.decode().splitlines()
+    return [list(map(int, l.split())) for l in out]
+
+
+def test_refhash_known_answers_from_the_reference(refhash_exe):
+    """csrc/kg_refhash.cuh (the reference's own hashes, for the bit-exact Bloom emulation of SURVEY 8f-4) against the
+    known answers minted from the reference's objects: XXH64 of 8 bytes, base-5 hashes mod 2^54 of whole k-mers"""
+    import json
+    kats = json.load(open(os.path.join(GOLDEN, "kats.json")))
+    payload = struct.pack("<II", 0, len(kats["xxh64"])) + b"".join(struct.pack("<QQ", v, s) for v, s, _ in kats["xxh64"])
+    got = subprocess.run([refhash_exe], input=payload, stdout=subprocess.PIPE, check=True).stdout.decode().split()
+    assert list(map(int, got)) == [h for _, _, h in kats["xxh64"]]
+    n = 0
+    for seq, q, _tbm, hf, hb, _fwd in kats["roll"]:
+        if q != 1 << 54:
+            continue
+        rows = _refhash_windows(refhash_exe, ["ACGT".index(c) for c in seq], len(seq))
+        assert len(rows) == 1 and rows[0][:3] == [hf, hb, min(hf, hb)]
+        n += 1
+    assert n >= 8
+
+
+@pytest.mark.parametrize("k", [1, 5, 21, 31, 32, 33, 51, 64, 65, 127, 128, 255, 256])
+def test_refhash_rolling_equals_definition(refhash_exe, oracle, k):
+    """every window of a random run: Horner start + O(1) rolling updates == the polynomial definition (big integers),
+    a few windows == the oracle's restatement of RollingHasherDual, and the 16 XXH64 values == the oracle's XXH64"""
+    rng = np.random.default_rng(k)
+    n = k + 150
+    codes = [int(x) for x in rng.integers(0, 4, n)]
+    rows = _refhash_windows(refhash_exe, codes, k)
+    assert len(rows) == n - k + 1
+    M54 = (1 << 54) - 1
+    L = oracle.lib()
+    for j, row in enumerate(rows):
+        w = codes[j:j + k]
+        hf = sum(w[i] * 5 ** (k - 1 - i) for i in range(k)) & M54
+        hb = sum((3 - w[i]) * 5 ** i for i in range(k)) & M54
+        assert row[:3] == [hf, hb, min(hf, hb)], j
+        if j % 40 == 0:
+            assert oracle.rolling_hashes(w, k, 1 << 54, True) == (hf, hb)
+            assert row[3:] == [L.ko_xxh64_u64(min(hf, hb), L.ko_bloom_seed(i)) for i in range(16)]
