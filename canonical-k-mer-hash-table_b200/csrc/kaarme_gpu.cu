@@ -20,6 +20,7 @@
 #include "kg_exchange_plan.hpp"
 #include "kg_kaarme.cuh"
 #include "kg_parse.cuh"
+#include "kg_refbloom.cuh"
 #include "kg_text.cuh"
 
 #define KG_MAX_W 8
@@ -132,6 +133,12 @@ struct kg_ctx {
     uint64_t peer_rounds = 0, peer_fallback_rounds = 0;
     u32* d_work = nullptr;              // work counter of the persistent insert kernels
     u32 insert_grid = 148 * 8;          // resident blocks of the grid-stride insert kernels (SMs x blocks/SM)
+    // bit-exact emulation of the reference's double Bloom filter (kg_refbloom.cuh; opt-in, unvalidated on hardware)
+    bool ref_bloom = false;
+    KgRefBloom rb{nullptr, nullptr, 0, 0, 0};
+    struct RbBatch { u64* words; u32* brk; KgStream* st; u32 nthreads; };
+    std::vector<RbBatch> rb_log;        // packed stream of every batch of the Bloom pass, kept for sweeps 2 and 3
+    int rb_streams = 0;                 // streams begun in the current pass (the emulation needs exactly one)
     bool feed_prefetch = false;         // KG_FEED_PREFETCH=1: pipelined H2D in kg_feed (unmeasured; opt-in)
     bool parse_tma = false;             // KG_PARSE_TMA=1: parse tiles staged by TMA bulk copies (unmeasured; opt-in)
     // Kaarme representation (after kg_compact)
@@ -283,6 +290,9 @@ static void free_all(kg_ctx* c) {
         if (c->h_remote_base[i]) cudaFreeHost(c->h_remote_base[i]);
     }
     cudaFree(c->d_barrier);
+    for (auto& b : c->rb_log) { cudaFree(b.words); cudaFree(b.brk); cudaFree(b.st); }
+    c->rb_log.clear();
+    cudaFree(c->rb.T1); cudaFree(c->rb.T2);
     if (c->comm) { kg_nccl().CommDestroy(c->comm); c->comm = nullptr; }
     if (c->ctl_comm) { kg_nccl().CommDestroy(c->ctl_comm); c->ctl_comm = nullptr; }
     for (int i = 0; i < 2; i++) {
@@ -384,7 +394,23 @@ extern "C" int kg_create(const kg_config* cfg, kg_ctx** out) {
     KG_TRY(cudaMemset(c->d_stats, 0, sizeof(KgStats)));
     KG_TRY(cudaEventCreate(&c->ev_pass_begin));
     KG_TRY(cudaEventCreate(&c->ev_pass_end));
-    if (cfg->use_bloom) {
+    c->ref_bloom = (cfg->reserved & KG_CFG_REFERENCE_BLOOM) != 0;
+    if (c->ref_bloom) {
+        uint64_t m; uint32_t nh;
+        bloom_params(cfg->expected_unique, cfg->fpr, &m, &nh);
+        const double h = (-(double)cfg->expected_unique * std::log(cfg->fpr)) / std::pow(std::log(2.0), 2.0) / (double)cfg->expected_unique * std::log(2.0);
+        if (!cfg->use_bloom || cfg->world != 1 || m > (1ull << 31) || nh < 1 || nh > KG_RB_MAX_NH) {
+            g_err = "KG_CFG_REFERENCE_BLOOM needs use_bloom, one GPU, m <= 2^31 bits and at most 16 hash functions";
+            free_all(c); delete c; return KG_EBADARG;
+        }
+        c->bloom_m = m;
+        c->bloom.nh = nh;
+        c->rb.mask = m - 1;
+        c->rb.nh = nh;
+        c->rb.nh2 = (u32)std::floor(h);                    // main.cpp:472 passes the double; the test loop truncates it
+        KG_TRY(cudaMalloc(&c->rb.T1, sizeof(u32) * m));
+        KG_TRY(cudaMalloc(&c->rb.T2, sizeof(u32) * m));
+    } else if (cfg->use_bloom) {
         uint64_t m; uint32_t nh;
         bloom_params(cfg->expected_unique, cfg->fpr, &m, &nh);
         if (nh < 1) nh = 1;
@@ -401,7 +427,7 @@ extern "C" int kg_create(const kg_config* cfg, kg_ctx** out) {
         KG_TRY(cudaMalloc(&c->bloom.bits, c->bloom_bytes));
     }
     // partitions: 0 = choose per pass from the table / filter size, 1 = never bucket on one GPU, > 1 = as given
-    c->bucketed = cfg->world > 1 || (cfg->partitions != 1 && cfg->table_mode != KG_TABLE_KAARME);
+    c->bucketed = cfg->world > 1 || (cfg->partitions != 1 && cfg->table_mode != KG_TABLE_KAARME && !c->ref_bloom);
     if (c->bucketed) {
         const size_t max_words = c->batch_bytes / 32 + c->carry_max_words + 2;
         c->max_blocks = (u32)((max_words + 31) / 32);   // smallest block of the hist/scatter pair covers 32 words
@@ -548,7 +574,15 @@ extern "C" int kg_pass_begin(kg_ctx* c, int pass) {
     c->raw_bytes_pass = 0;
     KG_CUDA(c, cudaEventRecord(c->ev_pass_begin, c->s_compute));
     KG_CUDA(c, cudaMemsetAsync(c->d_stats, 0, sizeof(KgStats), c->s_compute));
-    if (pass == KG_PASS_BLOOM) {
+    c->rb_streams = 0;
+    if (pass == KG_PASS_BLOOM && c->ref_bloom) {
+        KG_CUDA(c, cudaMemsetAsync(c->rb.T1, 0xFF, sizeof(u32) * (c->rb.mask + 1), c->s_compute));
+        KG_CUDA(c, cudaMemsetAsync(c->rb.T2, 0xFF, sizeof(u32) * (c->rb.mask + 1), c->s_compute));
+        for (auto& b : c->rb_log) { cudaFree(b.words); cudaFree(b.brk); cudaFree(b.st); }
+        c->rb_log.clear();
+        c->bloom_done = false;
+        c->pass_bucketed = false; c->pl = 1; c->nb = 1;
+    } else if (pass == KG_PASS_BLOOM) {
         KG_CUDA(c, cudaMemsetAsync(c->bloom.bits, 0, c->bloom_bytes, c->s_compute));
         c->bloom_done = false;
         { int rc = setup_pass_buckets(c, c->bloom_bytes); if (rc) return rc; }
@@ -606,6 +640,7 @@ extern "C" int kg_pass_begin(kg_ctx* c, int pass) {
 extern "C" int kg_stream_begin(kg_ctx* c, int starts_in_header) {
     if (!c || !c->pass) return KG_EBADARG;
     KG_CUDA(c, cudaSetDevice(c->cfg.device));
+    if (c->ref_bloom && ++c->rb_streams > 1) { c->err = "KG_CFG_REFERENCE_BLOOM: one stream per pass (window ordinals are positions in it)"; return KG_EBADARG; }
     KgStream s;
     memset(&s, 0, sizeof(s));
     s.in_header = starts_in_header ? 1u : 0u;
@@ -1113,6 +1148,42 @@ static int bucket_batch(kg_ctx* c, u32 nthreads) {
     return KG_OK;
 }
 
+template <int W>
+static void launch_rb_sweep(kg_ctx* c, int sweep, const u64* words, const u32* brk, const KgStream* st, u32 nthreads) {
+    const u32 grid = (nthreads + 255) / 256;
+    if (grid == 0) return;
+    switch (sweep) {
+        case 1: kg_refbloom_sweep<W, 1><<<grid, 256, 0, c->s_compute>>>(words, brk, st, c->rb, c->d_stats, c->cfg.k); break;
+        case 2: kg_refbloom_sweep<W, 2><<<grid, 256, 0, c->s_compute>>>(words, brk, st, c->rb, c->d_stats, c->cfg.k); break;
+        case 3: kg_refbloom_sweep<W, 3><<<grid, 256, 0, c->s_compute>>>(words, brk, st, c->rb, c->d_stats, c->cfg.k); break;
+        default: break;
+    }
+    c->launches++;
+}
+template <int W>
+static void launch_rb_count(kg_ctx* c, const KgCountArgs& a, u32 nthreads) {
+    const u32 grid = (nthreads + 255) / 256;
+    if (grid == 0) return;
+    kg_refbloom_count<W><<<grid, 256, 0, c->s_compute>>>(a, c->rb);
+    c->launches++;
+}
+
+// emulation mode, Bloom pass: sweep 1 over the batch that was just packed, and keep its packed stream (with the stream
+// state it was packed under) for sweeps 2 and 3 at kg_pass_end
+static int rb_bloom_batch(kg_ctx* c, u32 nthreads) {
+    kg_ctx::RbBatch b{nullptr, nullptr, nullptr, nthreads};
+    KG_CUDA(c, cudaMalloc(&b.words, sizeof(u64) * nthreads));
+    c->rb_log.push_back(b);                                  // owned by the context from here on
+    kg_ctx::RbBatch& e = c->rb_log.back();
+    KG_CUDA(c, cudaMalloc(&e.brk, sizeof(u32) * nthreads));
+    KG_CUDA(c, cudaMalloc(&e.st, sizeof(KgStream)));
+    KG_CUDA(c, cudaMemcpyAsync(e.words, c->d_words, sizeof(u64) * nthreads, cudaMemcpyDeviceToDevice, c->s_compute));
+    KG_CUDA(c, cudaMemcpyAsync(e.brk, c->d_brk, sizeof(u32) * nthreads, cudaMemcpyDeviceToDevice, c->s_compute));
+    KG_CUDA(c, cudaMemcpyAsync(e.st, c->d_stream, sizeof(KgStream), cudaMemcpyDeviceToDevice, c->s_compute));
+    KG_DISPATCH_W(c->W, launch_rb_sweep, c, 1, e.words, e.brk, e.st, nthreads);
+    return KG_OK;
+}
+
 // parse + count one device-resident batch (n <= batch_bytes, 16-byte aligned) on the compute stream
 static int process_batch(kg_ctx* c, const uint8_t* d_in, size_t n, uint32_t flags) {
     if (n == 0) return KG_OK;
@@ -1151,7 +1222,18 @@ static int process_batch(kg_ctx* c, const uint8_t* d_in, size_t n, uint32_t flag
     if (e1) cudaEventRecord(e1, s);
     if (!(flags & KG_FEED_CONTEXT)) {
         const u32 nthreads = (u32)(n / 32 + c->carry_max_words + 2);   // upper bound on packed words
-        if (c->pass_bucketed) {
+        if (c->ref_bloom) {                                            // bit-exact emulation of the reference's filters
+            if (c->pass == KG_PASS_BLOOM) {
+                int rc = rb_bloom_batch(c, nthreads);
+                if (rc) return rc;
+            } else {
+                KgCountArgs a;
+                a.words = c->d_words; a.brk = c->d_brk; a.st = c->d_stream;
+                a.table = c->table; a.bloom = c->bloom;
+                a.stats = c->d_stats; a.k = c->cfg.k; a.rank = 0; a.world = 1;
+                KG_DISPATCH_W(c->W, launch_rb_count, c, a, nthreads);
+            }
+        } else if (c->pass_bucketed) {
             int rc = bucket_batch(c, nthreads);
             if (rc) return rc;
         } else {
@@ -1301,6 +1383,21 @@ extern "C" int kg_pass_end(kg_ctx* c, kg_pass_stats* out) {
     if (c->pass_bucketed) {
         KG_CUDA(c, cudaEventRecord(c->ev_tail, c->s_insert));
         KG_CUDA(c, cudaStreamWaitEvent(c->s_compute, c->ev_tail, 0));
+    }
+    if (c->ref_bloom && c->pass == KG_PASS_BLOOM) {
+        for (int sweep = 2; sweep <= 3; sweep++)
+            for (auto& b : c->rb_log) KG_DISPATCH_W(c->W, launch_rb_sweep, c, sweep, b.words, b.brk, b.st, b.nthreads);
+        // window ordinals are 32-bit: the stream must hold fewer than 2^32 - 1 bases
+        KgStream last;
+        KG_CUDA(c, cudaMemcpyAsync(&last, c->d_stream, sizeof(last), cudaMemcpyDeviceToHost, c->s_compute));
+        KG_CUDA(c, cudaStreamSynchronize(c->s_compute));
+        if (last.bases_seen + (u64)last.total_bases >= 0xFFFFFFFFull) {
+            c->err = "KG_CFG_REFERENCE_BLOOM: input has 2^32 bases or more (window ordinals are 32-bit)";
+            c->pass = 0; c->stream_open = false;
+            return KG_EBADARG;
+        }
+        for (auto& b : c->rb_log) { cudaFree(b.words); cudaFree(b.brk); cudaFree(b.st); }
+        c->rb_log.clear();
     }
     KG_CUDA(c, cudaEventRecord(c->ev_pass_end, c->s_compute));
     KG_CUDA(c, cudaStreamSynchronize(c->s_compute));

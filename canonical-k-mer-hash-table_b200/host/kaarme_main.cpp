@@ -57,6 +57,7 @@ struct Args {
     bool print_slices = false;    // --print-slices: show how --gpus N would shard the input, then exit (no GPU needed)
     bool host_format = false;     // --host-format: export (key, count) records and format the lines on host threads
     std::string dump_kaarme;      // --dump-kaarme PATH: write the compact structure (-m 2, one GPU) as a binary file
+    bool reference_bloom = false; // --reference-bloom: -b builds the reference's own filter bit for bit (experimental)
     bool peer_exchange = false;   // --peer-exchange: with --gpus N, scatter kernels store straight into the owners' buffers
     bool from_kaarme = false;     // --from-kaarme: INPUT is a file written by --dump-kaarme; decode it on the GPU
 };
@@ -84,6 +85,8 @@ void print_help(const char* argv0) {
                  "  --gpus INT                 Hash-shard the k-mers over N GPUs of this box (NCCL exchange; def. 1)\n"
                  "  --peer-exchange            With --gpus N: fused bucket -> peer-store exchange over NVLink instead of\n"
                  "                             ncclSend/ncclRecv (experimental)\n"
+                 "  --reference-bloom          With -b on one GPU: reproduce the reference's double Bloom filter bit for bit\n"
+                 "                             (its hash functions, counters, table size, false positives; experimental)\n"
                  "  --batch-mb UINT            Raw bytes per device batch in MiB (def. 128)\n"
                  "  --exact-counts             Report true 32-bit counts instead of emulating the reference's\n"
                  "                             16-bit wrap (-m 0) / 14-bit saturation (-m 2)\n"
@@ -187,6 +190,7 @@ Args parse_args(int argc, char** argv) {
         else if (s == "--host-format") a.host_format = true;
         else if (s == "--from-kaarme") a.from_kaarme = true;
         else if (s == "--peer-exchange") a.peer_exchange = true;
+        else if (s == "--reference-bloom") a.reference_bloom = true;
         else if (s == "--dump-kaarme") a.dump_kaarme = value("--dump-kaarme");
         else if (s == "--stats-json") a.stats_json = value("--stats-json");
         else if (s.size() > 1 && s[0] == '-' && !(s[1] >= '0' && s[1] <= '9')) cli_fail(109, "The following argument was not expected: " + s);
@@ -598,6 +602,7 @@ int main(int argc, char** argv) {
         cfg.batch_bytes = buf_bytes;
         cfg.rank = rank;
         cfg.world = world;
+        cfg.reserved = args.reference_bloom ? KG_CFG_REFERENCE_BLOOM : 0;
         {
             int rc = kg_create(&cfg, &ctx);
             if (rc != KG_OK) {

@@ -18,6 +18,7 @@ TABLE_PLAIN, TABLE_KAARME = 0, 2
 PASS_BLOOM, PASS_COUNT = 1, 2
 FEED_CONTEXT = 1
 COUNT_EXACT, COUNT_REFERENCE = 0, 1
+CFG_REFERENCE_BLOOM = 1
 
 STATUS = {0: "KG_OK", 1: "KG_EBADARG", 2: "KG_ECUDA", 3: "KG_ETABLE_FULL", 4: "KG_ENCCL", 5: "KG_ENOMEM",
           6: "KG_ESINK"}
@@ -153,9 +154,12 @@ class Counter:
     """One kg_ctx (one GPU / one hash shard)."""
 
     def __init__(self, k, table_mode=TABLE_PLAIN, input_mode=INPUT_FASTA, min_slots=0, use_bloom=False,
-                 fpr=0.01, expected_unique=0, device=0, batch_bytes=0, rank=0, world=1, partitions=0):
+                 fpr=0.01, expected_unique=0, device=0, batch_bytes=0, rank=0, world=1, partitions=0,
+                 reference_bloom=False):
+        # reference_bloom: EXPERIMENTAL KG_CFG_REFERENCE_BLOOM -- the reference's own filter, bit for bit (SURVEY 8f-4)
         self.cfg = Config(ABI_VERSION, k, table_mode, input_mode, min_slots, int(bool(use_bloom)), device,
-                          fpr, expected_unique, batch_bytes, rank, world, partitions, 0)
+                          fpr, expected_unique, batch_bytes, rank, world, partitions,
+                          CFG_REFERENCE_BLOOM if reference_bloom else 0)
         self.k, self.W = k, (k + 31) // 32
         self._h = C.c_void_p()
         rc = lib().kg_create(C.byref(self.cfg), C.byref(self._h))

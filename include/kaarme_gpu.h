@@ -84,8 +84,16 @@ typedef struct kg_config {
                                  regions of the shard's table / filter before inserting.  0 = choose per pass
                                  (~24 MiB regions; direct insert when the structure is small), 1 = always
                                  insert directly, > 1 = as given (world * partitions <= 1024)              */
-    uint32_t reserved;
+    uint32_t reserved;        /* flags: KG_CFG_* below (0 = the defaults)                                              */
 } kg_config;
+
+/* kg_config.reserved flags */
+#define KG_CFG_REFERENCE_BLOOM 1u /* EXPERIMENTAL (not yet validated on hardware): -b reproduces the reference's double
+                                     Bloom filter bit for bit as ONE worker thread builds it -- same hash functions
+                                     (base-5 rolling hash mod 2^54, XXH64 with the reference's seeds), same
+                                     new_in_first / new_in_second, same table size, same false positives at -a 1 --
+                                     instead of the blocked filter with its own hash.  One GPU, one stream per pass,
+                                     m <= 2^31 bits, < 2^32 bases.  SURVEY.md section 8f-4; DESIGN.md section 9.        */
 
 typedef struct kg_pass_stats {
     uint64_t input_kmers;    /* complete windows seen by THIS context in the pass ("input k-mers")  */

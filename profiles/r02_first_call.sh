@@ -20,6 +20,9 @@ for g in 8 6 5 4 3; do
   echo "# KG_INSERT_GRID=$g" >> $OUT/r02_insert_grid.jsonl
   KG_INSERT_GRID=$g timeout 120 python bench.py --steps 3 --warmup 3 --no-cpu-baseline --no-e2e 2>/dev/null | grep '^{' >> $OUT/r02_insert_grid.jsonl
 done
+# bit-exact Bloom emulation (KG_CFG_REFERENCE_BLOOM): its own test file, not part of the default collection yet
+timeout 300 python -u -m pytest tests/experimental_refbloom_gpu.py -x -q > $OUT/r02_tests_refbloom.log 2>&1; echo "pytest rc=$?" >> $OUT/r02_tests_refbloom.log
+tail -3 $OUT/r02_tests_refbloom.log
 KG_FEED_PREFETCH=1 timeout 200 python -u -m pytest tests/test_gpu_parity.py -x -q > $OUT/r02_tests_prefetch.log 2>&1; echo "pytest rc=$?" >> $OUT/r02_tests_prefetch.log
 tail -2 $OUT/r02_tests_prefetch.log
 python - <<'PY'

@@ -83,6 +83,7 @@ int kg_create(const kg_config* cfg, kg_ctx** out) {
     kg_ctx* c = new kg_ctx();
     c->cfg = *cfg;
     c->W = (cfg->k + 31) / 32;
+    if (getenv("KG_MOCK_SHOW_FLAGS")) fprintf(stderr, "mock: config flags %u\n", cfg->reserved);
     {
         std::lock_guard<std::mutex> g(g_shared.m);
         if (g_shared.users++ == 0) g_shared.counts.clear();

@@ -191,6 +191,18 @@ def test_cli_output_to_a_pipe(exe, tmp_path):
 
 
 @pytest.mark.parametrize("gpus", [2, 4])
+def test_cli_reference_bloom_flag_reaches_the_config(exe, tmp_path):
+    """--reference-bloom sets KG_CFG_REFERENCE_BLOOM in kg_config.reserved (the test double reports the flags it saw)"""
+    case = [c for c in CASES if c["input"] == "g5_long.fasta" and c["k"] == 51 and c["mode"] == 0 and c["a"] == 2 and c["unique"]][0]
+    out = tmp_path / "o.txt"
+    for extra, want in (([], "0"), (["--reference-bloom"], "1")):
+        p = run(exe, [os.path.join(GOLDEN, "g5_long.fasta"), 51, "-m", 0, "-a", 2, "-o", out] + size_args(case) + extra,
+                env={"KG_MOCK_SHOW_FLAGS": "1"})
+        assert p.returncode == 0 and f"mock: config flags {want}" in p.stderr
+        assert sorted_sha(out) == (case["n_lines"], case["sha256"])
+
+
+@pytest.mark.parametrize("gpus", [2, 4])
 def test_cli_peer_exchange_handshake(exe, gpus, tmp_path):
     """--peer-exchange: every rank exports its handle, all wait, every rank connects with the handles in rank order
     (the mock rejects a connect that sees a missing or misplaced handle); the output is unchanged"""
