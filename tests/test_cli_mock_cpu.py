@@ -190,7 +190,6 @@ def test_cli_output_to_a_pipe(exe, tmp_path):
     assert sha_of(b"".join(kmer_lines)) == (case["n_lines"], case["sha256"])
 
 
-@pytest.mark.parametrize("gpus", [2, 4])
 def test_cli_reference_bloom_flag_reaches_the_config(exe, tmp_path):
     """--reference-bloom sets KG_CFG_REFERENCE_BLOOM in kg_config.reserved (the test double reports the flags it saw)"""
     case = [c for c in CASES if c["input"] == "g5_long.fasta" and c["k"] == 51 and c["mode"] == 0 and c["a"] == 2 and c["unique"]][0]
