@@ -31,29 +31,67 @@ struct KgRefBloom {
     u32 nh2;       // floor(h): hash functions tested in pass 2 (main.cpp:472)
 };
 
-// bit positions of a canonical k-mer: root = min(Hf, Hb) is orientation-free, so it can be taken from the canonical key
-template <int W>
-__device__ __forceinline__ void kg_rb_positions(const u64 (&key)[W], u32 k, const KgRefBloom& rb, u64 (&pos)[KG_RB_MAX_NH]) {
-    const KgKGeom g = kg_geom(k);
-    u64 rc[W];
-    kg_revcomp<W>(key, rc, g);
-    const u64 root = kg_ref_root(kg_b5_horner(key, (u32)W, k), kg_b5_horner(rc, (u32)W, k));
-#pragma unroll
+// ---- per-window logic, __host__ __device__: tests/native/refbloom_host.cu runs exactly this code on a CPU, windows
+// in a scrambled order, against the sequential semantics ---------------------------------------------------------
+KG_RH_HD void kg_rb_min(u32* p, u32 v) {
+#if defined(__CUDA_ARCH__)
+    atomicMin(p, v);
+#else
+    if (v < *p) *p = v;
+#endif
+}
+
+KG_RH_HD void kg_rb_positions_from_root(u64 root, const KgRefBloom& rb, u64 (&pos)[KG_RB_MAX_NH]) {
     for (int i = 0; i < KG_RB_MAX_NH; i++) pos[i] = (u32)i < rb.nh ? (kg_xxh64_8(root, kg_ref_seed((u32)i)) & rb.mask) : 0;
 }
 
 // "the insert into this filter is reported as failed": a position hit twice by this window that nobody set before it
-__device__ __forceinline__ bool kg_rb_dup_on_fresh_bit(const u32* T, const u64 (&pos)[KG_RB_MAX_NH], u32 nh, u32 ord) {
+KG_RH_HD bool kg_rb_dup_on_fresh_bit(const u32* T, const u64 (&pos)[KG_RB_MAX_NH], u32 nh, u32 ord) {
     bool dup = false;
     for (u32 i = 1; i < nh; i++)
         for (u32 j = 0; j < i; j++)
             if (pos[i] == pos[j] && T[pos[i]] == ord) dup = true;
     return dup;
 }
-__device__ __forceinline__ bool kg_rb_all_before(const u32* T, const u64 (&pos)[KG_RB_MAX_NH], u32 n, u32 ord) {
+KG_RH_HD bool kg_rb_all_before(const u32* T, const u64 (&pos)[KG_RB_MAX_NH], u32 n, u32 ord) {
     bool all = true;
     for (u32 i = 0; i < n; i++) all = all && (T[pos[i]] < ord);       // KG_RB_NEVER is never < ord
     return all;
+}
+
+// what sweep SWEEP does with one window (ord = its global end position, pos = its nh bit positions)
+template <int SWEEP>
+KG_RH_HD void kg_rb_window(const KgRefBloom& rb, const u64 (&pos)[KG_RB_MAX_NH], u32 ord, u32& n1, u32& n2) {
+    if (SWEEP == 1) {
+        for (u32 i = 0; i < rb.nh; i++) kg_rb_min(&rb.T1[pos[i]], ord);
+        return;
+    }
+    const bool promoted = kg_rb_all_before(rb.T1, pos, rb.nh, ord) || kg_rb_dup_on_fresh_bit(rb.T1, pos, rb.nh, ord);
+    if (SWEEP == 2) {
+        if (promoted) for (u32 i = 0; i < rb.nh; i++) kg_rb_min(&rb.T2[pos[i]], ord);
+        return;
+    }
+    // SWEEP 3: the counters (double_bloomfilter.hpp:389-396)
+    if (kg_rb_all_before(rb.T2, pos, rb.nh, ord)) return;              // in filter 2 when it arrives: nothing happens
+    if (promoted) n2 += kg_rb_dup_on_fresh_bit(rb.T2, pos, rb.nh, ord) ? 0u : 1u;
+    else n1 += 1u;
+}
+
+// pass 2 admission (second_contains with floor(h) hashes, parallel_parser.hpp:2021-2026)
+KG_RH_HD bool kg_rb_admits(const KgRefBloom& rb, const u64 (&pos)[KG_RB_MAX_NH]) {
+    bool admit = true;
+    for (u32 i = 0; i < rb.nh2; i++) admit = admit && (rb.T2[pos[i]] != KG_RB_NEVER);
+    return admit;
+}
+
+#if defined(__CUDACC__)
+// bit positions of a canonical k-mer: root = min(Hf, Hb) is orientation-free, so it can be taken from the canonical key
+template <int W>
+__device__ __forceinline__ void kg_rb_positions(const u64 (&key)[W], u32 k, const KgRefBloom& rb, u64 (&pos)[KG_RB_MAX_NH]) {
+    const KgKGeom g = kg_geom(k);
+    u64 rc[W];
+    kg_revcomp<W>(key, rc, g);
+    kg_rb_positions_from_root(kg_ref_root(kg_b5_horner(key, (u32)W, k), kg_b5_horner(rc, (u32)W, k)), rb, pos);
 }
 
 template <int W, int SWEEP>
@@ -64,22 +102,9 @@ __global__ void __launch_bounds__(256) kg_refbloom_sweep(const u64* __restrict__
     u32 n1 = 0, n2 = 0;
     const u32 n_windows = kg_for_each_window<W>(words, brk, T, C, k, t, st->bases_seen,
         [&](const u64 (&key)[W], u64, KgOcc occ, u32) {
-            const u32 ord = (u32)(occ.word >> 4);                      // global end position of the window
             u64 pos[KG_RB_MAX_NH];
             kg_rb_positions<W>(key, k, rb, pos);
-            if (SWEEP == 1) {
-                for (u32 i = 0; i < rb.nh; i++) atomicMin(&rb.T1[pos[i]], ord);
-                return;
-            }
-            const bool promoted = kg_rb_all_before(rb.T1, pos, rb.nh, ord) || kg_rb_dup_on_fresh_bit(rb.T1, pos, rb.nh, ord);
-            if (SWEEP == 2) {
-                if (promoted) for (u32 i = 0; i < rb.nh; i++) atomicMin(&rb.T2[pos[i]], ord);
-                return;
-            }
-            // SWEEP 3: the counters (double_bloomfilter.hpp:389-396)
-            if (kg_rb_all_before(rb.T2, pos, rb.nh, ord)) return;      // in filter 2 when it arrives: nothing happens
-            if (promoted) n2 += kg_rb_dup_on_fresh_bit(rb.T2, pos, rb.nh, ord) ? 0u : 1u;
-            else n1 += 1u;
+            kg_rb_window<SWEEP>(rb, pos, (u32)(occ.word >> 4), n1, n2);    // ordinal = global end position of the window
         });
     if (SWEEP == 1) { KG_WARP_ADD(stats, n_windows, input_kmers) }
     if (SWEEP == 3) {
@@ -100,9 +125,7 @@ __global__ void __launch_bounds__(256) kg_refbloom_count(KgCountArgs a, KgRefBlo
         [&](const u64 (&key)[W], u64 h, KgOcc occ, u32) {
             u64 pos[KG_RB_MAX_NH];
             kg_rb_positions<W>(key, a.k, rb, pos);
-            bool admit = true;
-            for (u32 i = 0; i < rb.nh2; i++) admit = admit && (rb.T2[pos[i]] != KG_RB_NEVER);
-            if (!admit) { n_rej++; return; }
+            if (!kg_rb_admits(rb, pos)) { n_rej++; return; }
             bool is_new;
             u64 slot;
             if constexpr (W == 2) slot = table.packed_tb ? kg_table_add_packed(table, key, h, is_new) : kg_table_add<W>(table, key, h, is_new);
@@ -118,3 +141,4 @@ __global__ void __launch_bounds__(256) kg_refbloom_count(KgCountArgs a, KgRefBlo
     KG_WARP_ADD(a.stats, n_rej, bloom_rejected)
     if (full) a.stats->table_full = 1;
 }
+#endif

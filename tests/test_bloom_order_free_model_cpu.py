@@ -90,3 +90,51 @@ def test_order_free_formulation_equals_sequential_reference_semantics(oracle, n,
     new1, new2, f2 = order_free_pass1(L, roots_of(seq, k), m, nh)
     assert (new1, new2) == (st.new_in_first, st.new_in_second)
     assert (f2 == f2_seq).all()
+
+
+@pytest.fixture(scope="module")
+def refbloom_exe():
+    """tests/native/refbloom_host.cu: the product's own per-window functions (csrc/kg_refbloom.cuh, __host__ __device__)
+    compiled for the host -- nvcc, sm_100a code generation for the device half of the headers, no GPU touched"""
+    import os
+    import subprocess
+    from conftest import ROOT
+    native = os.path.join(ROOT, "tests", "native")
+    exe = os.path.join(native, "_build", "refbloom_host")
+    os.makedirs(os.path.dirname(exe), exist_ok=True)
+    src = os.path.join(native, "refbloom_host.cu")
+    deps = [src] + [os.path.join(ROOT, "canonical-k-mer-hash-table_b200", "csrc", f) for f in ("kg_refbloom.cuh", "kg_refhash.cuh", "kg_count.cuh", "kg_device.cuh")]
+    if not os.path.exists(exe) or any(os.path.getmtime(d) > os.path.getmtime(exe) for d in deps):
+        nvcc = "/usr/local/cuda/bin/nvcc" if os.path.exists("/usr/local/cuda/bin/nvcc") else "nvcc"
+        subprocess.run([nvcc, "-O2", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-o", exe, src], check=True,
+                       stdout=subprocess.PIPE, stderr=subprocess.PIPE)
+    return exe
+
+
+@pytest.mark.parametrize("n,k,U,fpr,first", [(3000, 21, 50, 0.01, 0), (5000, 21, 300, 0.01, 12345), (4000, 31, 2000, 0.05, 7),
+                                             (6000, 21, 100, 0.2, 4_000_000_000), (3000, 51, 4000, 0.01, 1), (2500, 127, 3000, 0.01, 99)])
+def test_product_per_window_code_equals_sequential_reference_semantics(oracle, refbloom_exe, n, k, U, fpr, first):
+    """the C++ the kernels call per window (kg_rb_window<1|2|3>, kg_rb_admits), run on the CPU in a scrambled order:
+    counters, filter 2 and the pass-2 admission of every window == the oracle's sequential execution"""
+    import struct
+    import subprocess
+    L = oracle.lib()
+    rng = np.random.default_rng(n * 7 + k)
+    g = rng.integers(0, 4, n // 2)
+    codes = np.concatenate([g, g[: n // 2]]).astype(np.uint8)
+    seq = "".join("ACGT"[x] for x in codes)
+    data = np.frombuffer((">r\n" + seq + "\n").encode(), np.uint8)
+    m, nh, nh2 = oracle.bloom_params(U, fpr)
+    st = oracle.BloomStats()
+    f2_seq = np.zeros(m // 8 + 1, np.uint8)
+    assert L.ko_bloom_pass1(data.ctypes.data, data.size, k, oracle.FASTA, U, C.c_double(fpr), f2_seq.ctypes.data, C.byref(st)) == 0
+    payload = struct.pack("<IIIIII", k, len(codes), m.bit_length() - 1, nh, nh2, first) + codes.tobytes()
+    out = subprocess.run([refbloom_exe], input=payload, stdout=subprocess.PIPE, check=True).stdout.decode().split("\n")
+    assert tuple(map(int, out[0].split())) == (st.new_in_first, st.new_in_second)
+    bits = np.unpackbits(f2_seq)[:m]
+    assert list(map(int, out[1].split())) == [int(b) for b in np.flatnonzero(bits)]
+    roots = roots_of(seq, k)
+    L.ko_bloom_admits.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64]     # (a 54-bit root does not fit the default int)
+    L.ko_bloom_admits.restype = C.c_int
+    want = "".join("1" if L.ko_bloom_admits(f2_seq.ctypes.data, C.byref(st), r) else "0" for r in roots)
+    assert out[2] == want
