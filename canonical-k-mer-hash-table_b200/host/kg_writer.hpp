@@ -61,6 +61,8 @@ class ParallelWriter {
             }
         }
         if (ok) written_ += n;
+        if (ok && seekable_) lseek(fd_, (off_t)end_, SEEK_SET);   // keep the descriptor's own offset at the end: a plain
+                                                                   // write(2) by anyone sharing it lands after the data
         return ok;
     }
 

@@ -1,7 +1,8 @@
 // CPU check of the CLI's output writer (canonical-k-mer-hash-table_b200/host/kg_writer.hpp).
-// usage: writer_host IN OUT|- THREADS CHUNK_BYTES [PREFIX]
+// usage: writer_host IN OUT|- THREADS CHUNK_BYTES [PREFIX [SUFFIX]]
 // Appends IN to OUT in CHUNK_BYTES pieces through kg::ParallelWriter ("-" = stdout, e.g. a pipe: not seekable).
-// PREFIX (optional) is written with plain write(2) first: the writer must continue at the current file offset.
+// PREFIX (optional) is written with plain write(2) first: the writer must continue at the current file offset;
+// SUFFIX (optional) with plain write(2) afterwards: it must land after everything the writer appended.
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -25,6 +26,7 @@ int main(int argc, char** argv) {
         if (!w.append(data.data() + off, std::min(chunk, data.size() - off))) return 5;
     if (!w.append(nullptr, 0)) return 6;
     if (w.bytes() != data.size()) return 7;
+    if (argc > 6 && write(fd, argv[6], strlen(argv[6])) != (ssize_t)strlen(argv[6])) return 9;   // SUFFIX via plain write(2)
     if (!to_stdout && close(fd) != 0) return 8;
     return 0;
 }

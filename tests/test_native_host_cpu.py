@@ -165,6 +165,9 @@ def test_writer_appends_buffers_back_to_back(writer_exe, tmp_path):
     out = tmp_path / "prefixed.bin"
     assert subprocess.run([writer_exe, str(src), str(out), "8", str(32 << 20), "HEADER\n"]).returncode == 0
     assert out.read_bytes() == b"HEADER\n" + blob
+    # ... and leaves it at the end: a plain write(2) through the same descriptor lands after the data
+    assert subprocess.run([writer_exe, str(src), str(out), "8", str(32 << 20), "HEADER\n", "TRAILER\n"]).returncode == 0
+    assert out.read_bytes() == b"HEADER\n" + blob + b"TRAILER\n"
 
 
 def test_writer_on_a_pipe_falls_back_to_sequential_writes(writer_exe, tmp_path):
