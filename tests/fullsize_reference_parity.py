@@ -7,7 +7,7 @@ GPU with the SAME command line, sorts both outputs and requires them to be byte-
 pytools/compare_outputs.py does, plus the line-count check it forgets).  Prints one line per configuration with the
 reference's and the GPU build's own "Time used to build hash table" timers.
 
-    python tests/fullsize_reference_parity.py [--quick]
+    python tests/fullsize_reference_parity.py [--quick] [--extras]
 
 C1/C2 use a declared STAND-IN for example/ecoli1x.fasta (absent from the reference checkout, .MISSING_LARGE_BLOBS):
 a seeded 4 641 652 bp random genome, one record, 70 columns, with 3 % of it re-inserted as repeats so that the
@@ -85,10 +85,10 @@ def sorted_digest(path):
     return n, h.hexdigest()
 
 
-def case(name, path, k, args_common):
+def case(name, path, k, args_common, gpu_extra=(), ref_threads=None):
     threads = max(3, min(64, os.cpu_count() or 3))
-    ref_log, ref_wall = run(REF, [path, k] + args_common + ["-t", threads], f"{TMP}/ref.out")
-    gpu_log, gpu_wall = run(GPU, [path, k] + args_common + ["-t", threads], f"{TMP}/gpu.out")
+    ref_log, ref_wall = run(REF, [path, k] + args_common + ["-t", ref_threads or threads], f"{TMP}/ref.out")
+    gpu_log, gpu_wall = run(GPU, [path, k] + args_common + ["-t", threads] + list(gpu_extra), f"{TMP}/gpu.out")
     rn, rh = sorted_digest(f"{TMP}/ref.out")
     gn, gh = sorted_digest(f"{TMP}/gpu.out")
     ok = (rn, rh) == (gn, gh)
@@ -121,6 +121,20 @@ def main():
     ok &= case(f"C3 {meta['n_reads']} reads k=31 -m 0 -s {s} -a 2", c3, 31, ["-m", 0, "-s", s, "-a", 2])
     ok &= case(f"C3 {meta['n_reads']} reads k=31 -m 2 -s {s} -a 2", c3, 31, ["-m", 2, "-s", s, "-a", 2])
     ok &= case(f"C3 {meta['n_reads']} reads k=31 -m 0 -b -u {s // 2} -a 2", c3, 31, ["-m", 0, "-b", "-u", s // 2, "-a", 2])
+    if "--extras" in sys.argv:
+        # rows added after the count path, at full size:
+        #  host formatter instead of the GPU text dump; saved Kaarme structure decoded again; and the bit-exact Bloom
+        #  emulation against the reference run with ONE worker (-t 3), where its -a 1 output (false positives included)
+        #  is deterministic
+        ok &= case(f"C3 k=31 -m 0 -a 2 --host-format", c3, 31, ["-m", 0, "-s", s, "-a", 2], gpu_extra=["--host-format"])
+        run(GPU, [c3, 31, "-m", 2, "-s", s, "-a", 2, "--dump-kaarme", f"{TMP}/c3.kaarme"], f"{TMP}/gpu_dump.out")
+        run(GPU, [f"{TMP}/c3.kaarme", 31, "--from-kaarme", "-a", 2], f"{TMP}/gpu_decoded.out")
+        same = sorted_digest(f"{TMP}/gpu_dump.out") == sorted_digest(f"{TMP}/gpu_decoded.out")
+        print(f"C3 k=31 -m 2 --dump-kaarme -> --from-kaarme: {'IDENTICAL' if same else 'DIFFERENT'} "
+              f"({os.path.getsize(f'{TMP}/c3.kaarme')} bytes on disk)", flush=True)
+        ok &= same
+        ok &= case("C2' ecoli-standin k=51 -m 0 -u 4000000 -b -a 1, reference with one worker vs --reference-bloom", eco, 51,
+                   ["-m", 0, "-u", 4000000, "-b", "-a", 1], gpu_extra=["--reference-bloom"], ref_threads=3)
     for f in os.listdir(TMP):
         os.remove(os.path.join(TMP, f))
     print("ALL IDENTICAL" if ok else "MISMATCH")
