@@ -97,3 +97,22 @@ def test_cli_sharding_matches_python_and_oracle(oracle, name, k, world):
     assert windows == whole.total_windows
     want = dict(zip(map(bytes, whole.keys.view(np.uint8).reshape(whole.n, whole.W * 8)), whole.counts.tolist()))
     assert {kk: cc for kk, cc in total.items() if cc} == want
+
+
+def test_fastq_is_detected_and_declined_like_the_reference(tmp_path):
+    """main.cpp:27-68 detects FASTQ by extension + '@'; parallel_parser.hpp:797-800 then prints "Not implemented yet" and
+    returns normally -- before any device is touched, so this runs without a GPU"""
+    fq = tmp_path / "reads.fastq"
+    fq.write_text("@r1\nACGTACGTACGT\n+\nIIIIIIIIIIII\n")
+    p = run(fq, 5, "-s", 1000, "-o", tmp_path / "o.txt")
+    assert p.returncode == 0 and "input format:             FASTQ" in p.stdout and "Not implemented yet" in p.stdout
+    assert not (tmp_path / "o.txt").exists()
+    bad = tmp_path / "bad.fq"
+    bad.write_text(">r1\nACGT\n")
+    p = run(bad, 5, "-s", 1000)
+    assert p.returncode == 1 and "is ill-formed" in p.stderr
+
+
+def test_mode_1_is_declined_like_an_unknown_mode(tmp_path):
+    p = run(FA, 21, "-s", 1000, "-m", 1, "-o", tmp_path / "o.txt")
+    assert p.returncode == 0 and "Chosen mode not recognized" in p.stdout and not (tmp_path / "o.txt").exists()
