@@ -11,11 +11,12 @@ timeout 400 python -u -m pytest tests -m gpu -x -q --durations=10 > $OUT/r02_tes
 timeout 120 bash profiles/io_rows_probe.sh > /dev/null 2>&1
 # the TMA-staged parse kernels (cp.async.bulk + mbarrier, opt-in): the whole parity suite under KG_PARSE_TMA=1, then a timing
 KG_PARSE_TMA=1 timeout 300 python -u -m pytest tests/test_gpu_parity.py tests/test_gpu_cli.py -x -q > $OUT/r02_tests_tma.log 2>&1; echo "pytest rc=$?" >> $OUT/r02_tests_tma.log
+: > $OUT/r02_parse_tma.jsonl
 for t in 0 1; do
   echo "# KG_PARSE_TMA=$t" >> $OUT/r02_parse_tma.jsonl
   KG_PARSE_TMA=$t timeout 120 python bench.py --steps 3 --warmup 3 --no-cpu-baseline --no-e2e 2>/dev/null | grep '^{' >> $OUT/r02_parse_tma.jsonl
 done
-: > $OUT/r02_insert_grid.jsonl; : > $OUT/r02_parse_tma.jsonl
+: > $OUT/r02_insert_grid.jsonl
 for g in 8 6 5 4 3; do
   echo "# KG_INSERT_GRID=$g" >> $OUT/r02_insert_grid.jsonl
   KG_INSERT_GRID=$g timeout 120 python bench.py --steps 3 --warmup 3 --no-cpu-baseline --no-e2e 2>/dev/null | grep '^{' >> $OUT/r02_insert_grid.jsonl
