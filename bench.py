@@ -188,10 +188,6 @@ def main():
         uid = [kg.comm_unique_id() if rank == 0 else None]
         dist.broadcast_object_list(uid, src=0)
         ctr.comm_init(uid[0], rank, world)
-        if os.environ.get("KAARME_PEER") == "1":   # opt-in: fused bucket -> peer-store exchange (kg_peer_connect)
-            handles = [None] * world
-            dist.all_gather_object(handles, ctr.peer_export())
-            ctr.peer_connect(handles)
 
     def barrier():
         if world > 1:
@@ -299,10 +295,7 @@ def main():
     rec = meta["record_bytes"]
     bytes_per_kmer = rec / (meta["L"] - k + 1) + 2 * 32 * S      # fused parse->insert figure
     bucketed = st["partitions"] > 1 or world > 1
-    # (the segment-table variant serves the exchange and the one-pass scatter of W <= 4; wider keys on one GPU use
-    # the exact hist/scatter layout and kg_insert_keys_kernel)
-    kernel = (f"kg_insert_segs_kernel<{W},TABLE>" if (world > 1 or W <= 4) else f"kg_insert_keys_kernel<{W},TABLE>") if bucketed \
-        else f"kg_count_kernel<{W},TABLE>"
+    kernel = f"kg_skm_insert<{W},TABLE>" if bucketed else f"kg_count_kernel<{W},TABLE>"
     kmers_in_kernel = inserted_rank * args.steps                   # k-mers this rank's kernel launches processed
     achieved = kmers_in_kernel * bytes_per_kmer / (insert_ms * 1e-3) / 1e9
     traffic = None
@@ -341,8 +334,8 @@ def main():
                       "table_bytes_per_gpu": ctr.table_info()["slots"] * ctr.table_info()["slot_bytes"],
                       "input_kmers_per_gpu": meta["input_kmers"], "distinct_rank0": distinct,
                       "l2": "inputs (2 GB/GPU) and table (4 GB/GPU) are far larger than the 126 MB L2; no flush between steps",
-                      "parallelism": (f"hash-sharded x{world}, " + ("peer-store exchange" if os.environ.get("KAARME_PEER") == "1"
-                                                                   else "nccl send/recv exchange")) if world > 1 else "single GPU",
+                      "parallelism": (f"minimizer-sharded x{world}: 8-byte run descriptors read in place over NVLink, packed reads "
+                                      f"pulled by the copy engines, one-word NCCL all-reduce per round") if world > 1 else "single GPU",
                       "partitions": st["partitions"], "batch_mb": args.batch_mb},
            "clocks": clocks, "gpu_launches": launches, "roofline": roofline, "e2e": e2e,
            "stage_ms_per_step": {"parse": parse_ms / args.steps, "bucket+insert": count_ms / args.steps,

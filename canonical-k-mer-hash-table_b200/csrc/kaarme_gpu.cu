@@ -1,6 +1,6 @@
 // kaarme_gpu.cu -- implementation of the C ABI in include/kaarme_gpu.h (libkaarme_gpu.so, sm_100a only).
-// Host-side orchestration: pinned double-buffered H2D on a copy stream, parse + count kernels on a compute
-// stream, device-resident stream state (no host round trip per batch), chunked export.
+// Host-side orchestration: pinned double-buffered H2D on a copy stream, parse + bucketing kernels on a compute
+// stream, the insert on its own stream, device-resident stream state (no host round trip per batch), chunked export.
 // There is no CPU fallback anywhere in this file: every data-path step is a kernel launch.
 #include "../../include/kaarme_gpu.h"
 
@@ -17,10 +17,10 @@
 
 #include "kg_count.cuh"
 #include "kg_device.cuh"
-#include "kg_exchange_plan.hpp"
 #include "kg_kaarme.cuh"
 #include "kg_parse.cuh"
 #include "kg_refbloom.cuh"
+#include "kg_skm.cuh"
 #include "kg_text.cuh"
 
 #define KG_MAX_W 8
@@ -41,6 +41,26 @@
 #define KG_DEFAULT_BATCH (128ull << 20)
 #define KG_MAX_BATCH (1ull << 30)
 
+// One of the two batch slots of the minimizer-bucketed path.  A slot is ONE device allocation
+//   [ header 64 B | bucket cursors | pad to KG_SKM_META | packed 2-bit words of the batch | descriptor regions + overflow list ]
+// so that a peer can map it with one IPC handle and pull header + cursors + words with one copy.
+struct SkmSlot {
+    uint8_t* slab = nullptr;
+    u64* hdr = nullptr;           // [0] global ordinal of position 0 of the batch, [1] bases in the packed stream
+    u32* cursors = nullptr;       // [nb + 1]
+    u64* words = nullptr;         // packed stream of the batch (parse writes it here)
+    u64* desc = nullptr;          // nb regions of skm_cap descriptors, then the overflow list
+    KgSkmSources* d_src = nullptr;    // where the insert of this slot finds every sender's words + header
+    KgSkmPeers* d_peers = nullptr;    // where kg_skm_segments finds every sender's cursors + descriptors
+    u64* d_seg_start = nullptr;
+    const u64** d_seg_ptr = nullptr;
+    cudaEvent_t ev_ready = nullptr;   // s_compute: the slot holds this rank's batch of the round
+    cudaEvent_t ev_free = nullptr;    // the slot may be overwritten (one GPU: its insert is done; several: every rank's is)
+    uint8_t* peer_slab[KG_MAX_WORLD] = {};   // every rank's slot of this parity as mapped into this process
+    void* peer_opened[KG_MAX_WORLD] = {};    // IPC mappings to close at destroy
+    uint8_t* r_buf[KG_MAX_WORLD] = {};       // local copies of the peers' header + cursors + words (pulled every round)
+};
+
 struct kg_ctx {
     kg_config cfg;
     int W = 0;
@@ -57,7 +77,7 @@ struct kg_ctx {
     // parse scratch
     u32 *d_tile_hdr_eff = nullptr, *d_tile_hdr_in = nullptr, *d_tile_nbases = nullptr, *d_tile_pend_eff = nullptr,
         *d_tile_pend_in = nullptr, *d_tile_off = nullptr;
-    u64* d_words = nullptr;
+    u64* d_words_direct = nullptr;   // packed stream of the direct path (the bucketed path packs into the batch slot)
     u32* d_brk = nullptr;
     size_t words_cap = 0;  // in words
     u64* d_carry_words = nullptr;
@@ -65,7 +85,7 @@ struct kg_ctx {
     u32 carry_max_words = 0;
     KgStream* d_stream = nullptr;
     KgStats* d_stats = nullptr;
-    KgTable table{nullptr, 0, 0, 0, 1, 0};
+    KgTable table{nullptr, 0, 0, 0, 1, 0, nullptr};
     size_t table_bytes = 0;
     KgBloom bloom{nullptr, 0, 0, 1};
     size_t bloom_bytes = 0;
@@ -80,8 +100,8 @@ struct kg_ctx {
     size_t ev_used = 0;
     std::vector<cudaEvent_t> ins_pool;  // [insert_begin, insert_end] pairs around the insert kernels of the pass
     size_t ins_used = 0;
-    uint64_t ins_launches = 0, ins_keys_upper = 0;
-    uint64_t raw_bytes_pass = 0, bases_pass = 0;
+    uint64_t ins_launches = 0;
+    uint64_t raw_bytes_pass = 0;
     uint64_t launches = 0;
     // export staging
     u64* d_out_keys[2] = {nullptr, nullptr};
@@ -99,48 +119,34 @@ struct kg_ctx {
     u64* h_text_cur = nullptr;                 // pinned, 2 words
     size_t text_cap = 0;                       // bytes per text buffer
     bool text_configured = false;
-    // bucketed path (multi-GPU exchange, or partitions > 1 on one GPU)
-    bool bucketed = false;              // this context may bucket (streams/events exist)
+    // minimizer-bucketed path (kg_skm.cuh): several GPUs, or partitions > 1 on one GPU
+    bool bucketed = false;              // this context may bucket (slots / streams exist)
     bool pass_bucketed = false;         // the current pass buckets its batches
     u32 nb = 0;                         // buckets of the current pass = world * local partitions
     u32 pl = 1;                         // local partitions of the current pass
-    u32 nb_alloc = 0;                   // buckets the scratch below was sized for
-    u64 *d_seg[2] = {nullptr, nullptr}, *h_seg[2] = {nullptr, nullptr};   // segment tables (start[nseg+1], src[nseg])
-    u32 seg_cap = 0;
-    ncclComm_t comm = nullptr;       // key slices (ncclSend/ncclRecv) on s_comm
-    ncclComm_t ctl_comm = nullptr;   // per-round count all-gather on s_ctl: its own communicator and stream, so the
-                                     // tiny control exchange of round i+1 never queues behind the key transfer of round i
-    cudaStream_t s_comm = nullptr, s_insert = nullptr, s_ctl = nullptr;
-    u64* d_send[2] = {nullptr, nullptr};
-    u64* d_recv[2] = {nullptr, nullptr};
-    size_t send_cap = 0, recv_cap = 0;  // in keys
-    u32 *d_blk_hist = nullptr, *d_blk_base = nullptr;
-    u32 max_blocks = 0;
-    u32 *d_bucket_counts = nullptr, *d_bucket_offs = nullptr, *d_matrix = nullptr, *h_matrix = nullptr;
-    cudaEvent_t ev_counts = nullptr, ev_scatter = nullptr, ev_matrix = nullptr, ev_pass_ready = nullptr, ev_tail = nullptr;
-    cudaEvent_t ev_send_free[2] = {nullptr, nullptr}, ev_recv_free[2] = {nullptr, nullptr}, ev_recv_full[2] = {nullptr, nullptr};
-    uint64_t round = 0, subround = 0;
-    bool scatter_configured = false;
-    u32 reserve_cap = 0;                // keys per bucket region of the one-pass (reserve) scatter
-    size_t send_alloc = 0;              // keys each d_send buffer can hold
-    // peer exchange (kg_peer_export / kg_peer_connect): scatter kernels store straight into the owners' receive buffers
-    bool peer_ready = false;
-    u64* peer_recv[2][KG_MAX_WORLD] = {};   // receive buffers of every rank as mapped into this process ([parity][rank])
-    void* peer_opened[2][KG_MAX_WORLD] = {};// IPC mappings to close at destroy
-    u64** d_peer_ptrs[2] = {nullptr, nullptr};      // device copies of peer_recv[parity][*]
-    u64 *d_remote_base[2] = {nullptr, nullptr}, *h_remote_base[2] = {nullptr, nullptr};   // [KG_MAX_BUCKETS] per parity
-    u32* d_barrier = nullptr;           // world + 1 words for the "all scatters have landed" collective
-    uint64_t peer_rounds = 0, peer_fallback_rounds = 0;
-    u32* d_work = nullptr;              // work counter of the persistent insert kernels
-    u32 insert_grid = 148 * 8;          // resident blocks of the grid-stride insert kernels (SMs x blocks/SM)
-    // bit-exact emulation of the reference's double Bloom filter (kg_refbloom.cuh; opt-in, unvalidated on hardware)
+    u32 skm_m = 0;                      // minimizer length for this k
+    u32 skm_cap = 0;                    // descriptors per bucket region in the current pass
+    u32 skm_ovf_cap = 0;                // descriptors the overflow list can hold (= every position of a batch)
+    u64 skm_region_total = 0, skm_desc_cap = 0;
+    size_t skm_words_bytes = 0, skm_slab_bytes = 0;
+    SkmSlot slot[2];
+    u64 *d_part_lo = nullptr, *d_bpart_lo = nullptr;   // [pl + 1] partition bounds of the table / the Bloom filter
+    ncclComm_t comm = nullptr;          // carries only the per-round one-word all-reduce (and the handle exchange)
+    cudaStream_t s_insert = nullptr;    // all-reduce, pulls, kg_skm_insert
+    u32* d_round = nullptr;             // [0] = 0, [1] = 1 (send values), [4 + parity] = sum of the round
+    u32* h_round_sum = nullptr;         // pinned
+    cudaEvent_t ev_pass_ready = nullptr, ev_tail = nullptr;
+    uint64_t round = 0;
+    u32* d_work = nullptr;              // work counter of the persistent insert kernel
+    u32 insert_grid = 148 * 8;          // resident blocks of the persistent insert kernel (SMs x blocks/SM)
+    // bit-exact emulation of the reference's double Bloom filter (kg_refbloom.cuh)
     bool ref_bloom = false;
     KgRefBloom rb{nullptr, nullptr, 0, 0, 0};
     struct RbBatch { u64* words; u32* brk; KgStream* st; u32 nthreads; };
     std::vector<RbBatch> rb_log;        // packed stream of every batch of the Bloom pass, kept for sweeps 2 and 3
     int rb_streams = 0;                 // streams begun in the current pass (the emulation needs exactly one)
-    bool feed_prefetch = false;         // KG_FEED_PREFETCH=1: pipelined H2D in kg_feed (unmeasured; opt-in)
-    bool parse_tma = false;             // KG_PARSE_TMA=1: parse tiles staged by TMA bulk copies (unmeasured; opt-in)
+    bool feed_prefetch = true;          // pipelined H2D in kg_feed (KG_FEED_PREFETCH=0 switches it off)
+    bool parse_tma = true;              // parse tiles staged by TMA bulk copies (KG_PARSE_TMA=0: plain 128-bit loads)
     // Kaarme representation (after kg_compact)
     KgKaarme kaarme{nullptr, nullptr, 0, 0};
     KgCompactStats* d_cstats = nullptr;
@@ -159,6 +165,7 @@ struct KgNccl {
     decltype(&ncclCommInitRank) CommInitRank = nullptr;
     decltype(&ncclCommDestroy) CommDestroy = nullptr;
     decltype(&ncclAllGather) AllGather = nullptr;
+    decltype(&ncclAllReduce) AllReduce = nullptr;
     decltype(&ncclSend) Send = nullptr;
     decltype(&ncclRecv) Recv = nullptr;
     decltype(&ncclGroupStart) GroupStart = nullptr;
@@ -173,10 +180,10 @@ static KgNccl& kg_nccl() {
         if (!n.handle) n.handle = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
         if (n.handle) {
 #define KG_SYM(name) n.name = (decltype(n.name))dlsym(n.handle, "nccl" #name)
-            KG_SYM(GetUniqueId); KG_SYM(CommInitRank); KG_SYM(CommDestroy); KG_SYM(AllGather); KG_SYM(Send);
+            KG_SYM(GetUniqueId); KG_SYM(CommInitRank); KG_SYM(CommDestroy); KG_SYM(AllGather); KG_SYM(AllReduce); KG_SYM(Send);
             KG_SYM(Recv); KG_SYM(GroupStart); KG_SYM(GroupEnd); KG_SYM(GetErrorString);
 #undef KG_SYM
-            n.ok = n.GetUniqueId && n.CommInitRank && n.CommDestroy && n.AllGather && n.Send && n.Recv &&
+            n.ok = n.GetUniqueId && n.CommInitRank && n.CommDestroy && n.AllGather && n.AllReduce && n.Send && n.Recv &&
                    n.GroupStart && n.GroupEnd && n.GetErrorString;
         }
     }
@@ -261,10 +268,23 @@ extern "C" int kg_host_free(void* p) {
 }
 
 // -----------------------------------------------------------------------------------------------------------
+static void free_slot(kg_ctx* c, SkmSlot& s) {
+    for (int r = 0; r < KG_MAX_WORLD; r++) {
+        if (s.peer_opened[r]) cudaIpcCloseMemHandle(s.peer_opened[r]);
+        s.peer_opened[r] = nullptr;
+        cudaFree(s.r_buf[r]);
+        s.r_buf[r] = nullptr;
+    }
+    cudaFree(s.slab); cudaFree(s.d_src); cudaFree(s.d_peers); cudaFree(s.d_seg_start); cudaFree(s.d_seg_ptr);
+    if (s.ev_ready) cudaEventDestroy(s.ev_ready);
+    if (s.ev_free) cudaEventDestroy(s.ev_free);
+    s = SkmSlot();
+    (void)c;
+}
+
 static void free_all(kg_ctx* c) {
     cudaSetDevice(c->cfg.device);
-    if (c->s_compute) cudaStreamSynchronize(c->s_compute);
-    if (c->s_copy) cudaStreamSynchronize(c->s_copy);
+    for (cudaStream_t st : {c->s_compute, c->s_copy, c->s_insert}) if (st) cudaStreamSynchronize(st);
     for (int i = 0; i < 2; i++) {
         cudaFree(c->d_raw[i]);
         if (c->h_stage[i]) cudaFreeHost(c->h_stage[i]);
@@ -277,40 +297,23 @@ static void free_all(kg_ctx* c) {
         if (c->ev_out[i]) cudaEventDestroy(c->ev_out[i]);
         cudaFree(c->d_text[i]); cudaFree(c->d_text_cur[i]);
         if (c->h_text[i]) cudaFreeHost(c->h_text[i]);
+        free_slot(c, c->slot[i]);
     }
     if (c->h_out_n) cudaFreeHost(c->h_out_n);
     if (c->h_text_cur) cudaFreeHost(c->h_text_cur);
+    if (c->h_round_sum) cudaFreeHost(c->h_round_sum);
     cudaFree(c->kaarme.slots); cudaFree(c->kaarme.roots); cudaFree(c->d_cstats); cudaFree(c->d_work);
-    if (c->s_comm) cudaStreamSynchronize(c->s_comm);
-    if (c->s_insert) cudaStreamSynchronize(c->s_insert);
-    if (c->s_ctl) cudaStreamSynchronize(c->s_ctl);
-    for (int i = 0; i < 2; i++) {
-        for (int r = 0; r < KG_MAX_WORLD; r++) if (c->peer_opened[i][r]) cudaIpcCloseMemHandle(c->peer_opened[i][r]);
-        cudaFree(c->d_peer_ptrs[i]); cudaFree(c->d_remote_base[i]);
-        if (c->h_remote_base[i]) cudaFreeHost(c->h_remote_base[i]);
-    }
-    cudaFree(c->d_barrier);
+    cudaFree(c->d_part_lo); cudaFree(c->d_bpart_lo); cudaFree(c->d_round);
     for (auto& b : c->rb_log) { cudaFree(b.words); cudaFree(b.brk); cudaFree(b.st); }
     c->rb_log.clear();
     cudaFree(c->rb.T1); cudaFree(c->rb.T2);
     if (c->comm) { kg_nccl().CommDestroy(c->comm); c->comm = nullptr; }
-    if (c->ctl_comm) { kg_nccl().CommDestroy(c->ctl_comm); c->ctl_comm = nullptr; }
-    for (int i = 0; i < 2; i++) {
-        cudaFree(c->d_send[i]); cudaFree(c->d_recv[i]);
-        if (c->ev_send_free[i]) cudaEventDestroy(c->ev_send_free[i]);
-        if (c->ev_recv_free[i]) cudaEventDestroy(c->ev_recv_free[i]);
-        if (c->ev_recv_full[i]) cudaEventDestroy(c->ev_recv_full[i]);
-    }
-    cudaFree(c->d_blk_hist); cudaFree(c->d_blk_base); cudaFree(c->d_bucket_counts); cudaFree(c->d_bucket_offs); cudaFree(c->d_matrix);
-    if (c->h_matrix) cudaFreeHost(c->h_matrix);
-    for (int i = 0; i < 2; i++) { cudaFree(c->d_seg[i]); if (c->h_seg[i]) cudaFreeHost(c->h_seg[i]); }
-    for (cudaEvent_t e : {c->ev_counts, c->ev_scatter, c->ev_matrix, c->ev_pass_ready, c->ev_tail}) if (e) cudaEventDestroy(e);
-    if (c->s_comm) cudaStreamDestroy(c->s_comm);
+    if (c->ev_tail) cudaEventDestroy(c->ev_tail);
+    if (c->ev_pass_ready) cudaEventDestroy(c->ev_pass_ready);
     if (c->s_insert) cudaStreamDestroy(c->s_insert);
-    if (c->s_ctl) cudaStreamDestroy(c->s_ctl);
     cudaFree(c->d_tile_hdr_eff); cudaFree(c->d_tile_hdr_in); cudaFree(c->d_tile_nbases);
     cudaFree(c->d_tile_pend_eff); cudaFree(c->d_tile_pend_in); cudaFree(c->d_tile_off);
-    cudaFree(c->d_words); cudaFree(c->d_brk); cudaFree(c->d_carry_words); cudaFree(c->d_carry_brk);
+    cudaFree(c->d_words_direct); cudaFree(c->d_brk); cudaFree(c->d_carry_words); cudaFree(c->d_carry_brk);
     cudaFree(c->d_stream); cudaFree(c->d_stats); cudaFree(c->table.slots); cudaFree(c->bloom.bits);
     for (auto e : c->ev_pool) cudaEventDestroy(e);
     for (auto e : c->ins_pool) cudaEventDestroy(e);
@@ -319,6 +322,66 @@ static void free_all(kg_ctx* c) {
     if (c->s_compute) cudaStreamDestroy(c->s_compute);
     if (c->s_copy) cudaStreamDestroy(c->s_copy);
     cudaGetLastError();
+}
+
+// Sizes of the minimizer-bucketing buffers of one batch slot.  A batch of n raw bytes holds at most n bases
+// (+ the carried ones), hence at most that many windows and -- worst case, one window per descriptor -- descriptors.
+//   regions   nb fixed-capacity bucket regions.  A run averages ~(k-m+2)/2 windows cut at packed-word boundaries; the
+//             regions together hold positions/4 * 1.25 descriptors when a window has >= 8 m-mers (positions * 1.25
+//             otherwise) + 256 per bucket: comfortably more than a balanced batch needs.
+//   overflow  whatever does not fit its region (skewed input) goes to one shared list that can hold EVERY position of
+//             the batch, so no input can overflow it; the insert walks it last, without L2 blocking.
+static void skm_geometry(kg_ctx* c) {
+    const u64 positions = c->batch_bytes + 32ull * c->carry_max_words + 64;
+    const u32 wlen = c->cfg.k - c->skm_m + 1;
+    c->skm_region_total = (wlen >= 8 ? positions / 4 : positions) * 5 / 4 + (u64)KG_MAX_BUCKETS * 256;
+    c->skm_ovf_cap = (u32)positions;
+    c->skm_words_bytes = ((c->words_cap * sizeof(u64)) + 255) / 256 * 256;
+    c->skm_desc_cap = c->skm_region_total + c->skm_ovf_cap + 64;
+    c->skm_slab_bytes = KG_SKM_META + c->skm_words_bytes + c->skm_desc_cap * sizeof(u64);
+}
+
+static int alloc_slots(kg_ctx* c) {
+    if (c->slot[0].slab) return KG_OK;
+    for (int b = 0; b < 2; b++) {
+        SkmSlot& s = c->slot[b];
+        KG_CUDA(c, cudaMalloc(&s.slab, c->skm_slab_bytes));
+        KG_CUDA(c, cudaMemset(s.slab, 0, KG_SKM_META));
+        s.hdr = (u64*)s.slab;
+        s.cursors = (u32*)(s.slab + 64);
+        s.words = (u64*)(s.slab + KG_SKM_META);
+        s.desc = (u64*)(s.slab + KG_SKM_META + c->skm_words_bytes);
+        KG_CUDA(c, cudaMalloc(&s.d_src, sizeof(KgSkmSources)));
+        KG_CUDA(c, cudaMalloc(&s.d_peers, sizeof(KgSkmPeers)));
+        KG_CUDA(c, cudaMalloc(&s.d_seg_start, sizeof(u64) * (KG_SKM_MAXSEG + 2)));
+        KG_CUDA(c, cudaMalloc(&s.d_seg_ptr, sizeof(u64*) * (KG_SKM_MAXSEG + 2)));
+        KG_CUDA(c, cudaEventCreateWithFlags(&s.ev_ready, cudaEventDisableTiming));
+        KG_CUDA(c, cudaEventCreateWithFlags(&s.ev_free, cudaEventDisableTiming));
+        s.peer_slab[c->cfg.rank] = s.slab;
+    }
+    return KG_OK;
+}
+
+// the device-side tables that say where every rank's words / cursors / descriptors of a slot are to be found
+static int publish_slot_tables(kg_ctx* c) {
+    const int world = c->cfg.world, me = c->cfg.rank;
+    for (int b = 0; b < 2; b++) {
+        SkmSlot& s = c->slot[b];
+        KgSkmSources src;
+        KgSkmPeers peers;
+        memset(&src, 0, sizeof(src));
+        memset(&peers, 0, sizeof(peers));
+        for (int r = 0; r < world; r++) {
+            const uint8_t* meta = r == me ? s.slab : s.r_buf[r];                 // local (copied) header + cursors + packed words
+            src.hdr[r] = (const u64*)meta;
+            src.words[r] = (const u64*)(meta + KG_SKM_META);
+            peers.cursors[r] = (const u32*)(meta + 64);
+            peers.desc[r] = (const u64*)(s.peer_slab[r] + KG_SKM_META + c->skm_words_bytes);   // read in place (NVLink for r != me)
+        }
+        KG_CUDA(c, cudaMemcpy(s.d_src, &src, sizeof(src), cudaMemcpyHostToDevice));
+        KG_CUDA(c, cudaMemcpy(s.d_peers, &peers, sizeof(peers), cudaMemcpyHostToDevice));
+    }
+    return KG_OK;
 }
 
 extern "C" int kg_create(const kg_config* cfg, kg_ctx** out) {
@@ -354,11 +417,12 @@ extern "C" int kg_create(const kg_config* cfg, kg_ctx** out) {
     if (const char* e = getenv("KG_PARSE_TMA")) c->parse_tma = atoi(e) != 0;
     if (const char* e = getenv("KG_FEED_PREFETCH")) c->feed_prefetch = atoi(e) != 0;
     c->W = (int)((cfg->k + 31) / 32);
+    c->skm_m = kg_skm_m(cfg->k);
     c->batch_bytes = cfg->batch_bytes ? cfg->batch_bytes : KG_DEFAULT_BATCH;
     if (c->batch_bytes > KG_MAX_BATCH) c->batch_bytes = KG_MAX_BATCH;
     c->batch_bytes = (c->batch_bytes + KG_TILE - 1) / KG_TILE * KG_TILE;
     c->max_tiles = (uint32_t)(c->batch_bytes / KG_TILE);
-    c->carry_max_words = (u32)c->W + 2;
+    c->carry_max_words = (u32)c->W + 3;
     c->words_cap = c->batch_bytes / 32 + c->carry_max_words + 8;
 
 #define KG_TRY(call)                              \
@@ -383,13 +447,14 @@ extern "C" int kg_create(const kg_config* cfg, kg_ctx** out) {
     KG_TRY(cudaMalloc(&c->d_tile_pend_eff, sizeof(u32) * c->max_tiles));
     KG_TRY(cudaMalloc(&c->d_tile_pend_in, sizeof(u32) * c->max_tiles));
     KG_TRY(cudaMalloc(&c->d_tile_off, sizeof(u32) * c->max_tiles));
-    KG_TRY(cudaMalloc(&c->d_words, sizeof(u64) * c->words_cap));
     KG_TRY(cudaMalloc(&c->d_brk, sizeof(u32) * c->words_cap));
     KG_TRY(cudaMalloc(&c->d_carry_words, sizeof(u64) * c->carry_max_words));
     KG_TRY(cudaMalloc(&c->d_carry_brk, sizeof(u32) * c->carry_max_words));
     KG_TRY(cudaMalloc(&c->d_stream, sizeof(KgStream)));
     KG_TRY(cudaMalloc(&c->d_stats, sizeof(KgStats)));
     KG_TRY(cudaMalloc(&c->d_work, sizeof(u32) * 4));
+    KG_TRY(cudaMalloc(&c->d_part_lo, sizeof(u64) * (KG_MAX_BUCKETS + 2)));
+    KG_TRY(cudaMalloc(&c->d_bpart_lo, sizeof(u64) * (KG_MAX_BUCKETS + 2)));
     KG_TRY(cudaMemset(c->d_stream, 0, sizeof(KgStream)));
     KG_TRY(cudaMemset(c->d_stats, 0, sizeof(KgStats)));
     KG_TRY(cudaEventCreate(&c->ev_pass_begin));
@@ -427,25 +492,25 @@ extern "C" int kg_create(const kg_config* cfg, kg_ctx** out) {
         KG_TRY(cudaMalloc(&c->bloom.bits, c->bloom_bytes));
     }
     // partitions: 0 = choose per pass from the table / filter size, 1 = never bucket on one GPU, > 1 = as given
-    c->bucketed = cfg->world > 1 || (cfg->partitions != 1 && cfg->table_mode != KG_TABLE_KAARME && !c->ref_bloom);
+    c->bucketed = cfg->world > 1 || (cfg->partitions != 1 && !c->ref_bloom);
     if (c->bucketed) {
-        const size_t max_words = c->batch_bytes / 32 + c->carry_max_words + 2;
-        c->max_blocks = (u32)((max_words + 31) / 32);   // smallest block of the hist/scatter pair covers 32 words
-        c->send_cap = c->batch_bytes + 64;                       // a batch of n bytes holds < n k-mers
-        c->recv_cap = cfg->world > 1 ? 2 * c->send_cap : 0;      // single GPU inserts straight from the send buffer
-        KG_TRY(cudaStreamCreateWithFlags(&c->s_comm, cudaStreamNonBlocking));
+        skm_geometry(c);
         KG_TRY(cudaStreamCreateWithFlags(&c->s_insert, cudaStreamNonBlocking));
-        KG_TRY(cudaStreamCreateWithFlags(&c->s_ctl, cudaStreamNonBlocking));
-        for (int i = 0; i < 2; i++) {
-            KG_TRY(cudaEventCreateWithFlags(&c->ev_send_free[i], cudaEventDisableTiming));
-            KG_TRY(cudaEventCreateWithFlags(&c->ev_recv_free[i], cudaEventDisableTiming));
-            KG_TRY(cudaEventCreateWithFlags(&c->ev_recv_full[i], cudaEventDisableTiming));
-        }
-        KG_TRY(cudaEventCreateWithFlags(&c->ev_counts, cudaEventDisableTiming));
-        KG_TRY(cudaEventCreateWithFlags(&c->ev_scatter, cudaEventDisableTiming));
-        KG_TRY(cudaEventCreateWithFlags(&c->ev_matrix, cudaEventDisableTiming));
         KG_TRY(cudaEventCreateWithFlags(&c->ev_pass_ready, cudaEventDisableTiming));
         KG_TRY(cudaEventCreateWithFlags(&c->ev_tail, cudaEventDisableTiming));
+        KG_TRY(cudaMalloc(&c->d_round, sizeof(u32) * 8));
+        {   // d_round[0] = 0, d_round[1] = 1: the two possible contributions to a round's "ranks with a batch" sum
+            const u32 init[8] = {0, 1, 0, 0, 0, 0, 0, 0};
+            KG_TRY(cudaMemcpy(c->d_round, init, sizeof(init), cudaMemcpyHostToDevice));
+        }
+        KG_TRY(cudaHostAlloc((void**)&c->h_round_sum, sizeof(u32) * 2, cudaHostAllocDefault));
+        if (cfg->world == 1) {   // one GPU: slots now; several GPUs: kg_comm_init allocates and maps them
+            int rc = alloc_slots(c);
+            if (rc == KG_OK) rc = publish_slot_tables(c);
+            if (rc != KG_OK) { g_err = c->err; free_all(c); delete c; return rc; }
+        }
+    } else {
+        KG_TRY(cudaMalloc(&c->d_words_direct, sizeof(u64) * c->words_cap));
     }
 #undef KG_TRY
     *out = c;
@@ -473,32 +538,94 @@ extern "C" int kg_destroy(kg_ctx* c) {
 
 extern "C" int kg_comm_unique_id(void* id_out) {
     if (!id_out) return KG_EBADARG;
-    static_assert(2 * sizeof(ncclUniqueId) <= KG_UNIQUE_ID_BYTES, "unique id size");
-    ncclUniqueId id[2];
+    static_assert(sizeof(ncclUniqueId) <= KG_UNIQUE_ID_BYTES, "unique id size");
+    ncclUniqueId id;
     kg_ctx* none = nullptr;
     if (!kg_nccl().ok) { g_err = "libnccl.so.2 could not be loaded"; return KG_ENCCL; }
-    KG_NCCL(none, kg_nccl().GetUniqueId(&id[0]));     // key transfers
-    KG_NCCL(none, kg_nccl().GetUniqueId(&id[1]));     // control (count all-gather)
+    KG_NCCL(none, kg_nccl().GetUniqueId(&id));
     memset(id_out, 0, KG_UNIQUE_ID_BYTES);
-    memcpy(id_out, id, sizeof(id));
+    memcpy(id_out, &id, sizeof(id));
     return KG_OK;
 }
 
+// What one rank tells the others about its two batch slots (all-gathered through NCCL inside kg_comm_init).
+struct KgPeerHandle {
+    uint64_t magic, pid;
+    int32_t rank, device;
+    uint64_t ptr[2], slab_bytes;
+    cudaIpcMemHandle_t ipc[2];
+};
+#define KG_PEER_MAGIC 0x4B47504545523032ULL   // "KGPEER02"
+#define KG_PEER_HANDLE_BYTES 256
+static_assert(sizeof(KgPeerHandle) <= KG_PEER_HANDLE_BYTES, "peer handle size");
+
+// Collective.  Besides the NCCL communicator (which only carries the one-word "round" all-reduce) this maps every
+// rank's two batch slots into every rank: CUDA IPC handles between processes, plain peer access between the contexts
+// of one process.  The exchange itself then needs no NCCL data movement: the copy engines pull the packed words of the
+// peers' batches over NVLink and the insert kernel reads the peers' descriptors in place.
 extern "C" int kg_comm_init(kg_ctx* c, const void* id, int rank, int world) {
     if (!c || !id) return KG_EBADARG;
     if (rank != c->cfg.rank || world != c->cfg.world || world < 2) { c->err = "kg_comm_init: rank/world differ from kg_config"; return KG_EBADARG; }
+    if (c->comm) { c->err = "kg_comm_init: called twice"; return KG_EBADARG; }
     KG_CUDA(c, cudaSetDevice(c->cfg.device));
-    ncclUniqueId uid[2];
-    memcpy(uid, id, sizeof(uid));
+    ncclUniqueId uid;
+    memcpy(&uid, id, sizeof(uid));
     if (!kg_nccl().ok) { c->err = "libnccl.so.2 could not be loaded"; return KG_ENCCL; }
-    KG_NCCL(c, kg_nccl().CommInitRank(&c->comm, world, uid[0], rank));
-    KG_NCCL(c, kg_nccl().CommInitRank(&c->ctl_comm, world, uid[1], rank));
-    return KG_OK;
+    KG_NCCL(c, kg_nccl().CommInitRank(&c->comm, world, uid, rank));
+    { int rc = alloc_slots(c); if (rc) return rc; }
+    KgPeerHandle mine;
+    memset(&mine, 0, sizeof(mine));
+    mine.magic = KG_PEER_MAGIC;
+    mine.pid = (uint64_t)getpid();
+    mine.rank = rank;
+    mine.device = c->cfg.device;
+    mine.slab_bytes = c->skm_slab_bytes;
+    for (int b = 0; b < 2; b++) {
+        mine.ptr[b] = (uint64_t)(uintptr_t)c->slot[b].slab;
+        KG_CUDA(c, cudaIpcGetMemHandle(&mine.ipc[b], c->slot[b].slab));
+    }
+    char *d_all = nullptr;
+    std::vector<char> all((size_t)world * KG_PEER_HANDLE_BYTES, 0);
+    KG_CUDA(c, cudaMalloc(&d_all, all.size()));
+    struct Guard { char** p; ~Guard() { cudaFree(*p); } } guard{&d_all};
+    KG_CUDA(c, cudaMemset(d_all, 0, all.size()));
+    KG_CUDA(c, cudaMemcpy(d_all + (size_t)rank * KG_PEER_HANDLE_BYTES, &mine, sizeof(mine), cudaMemcpyHostToDevice));
+    KG_NCCL(c, kg_nccl().AllGather(d_all + (size_t)rank * KG_PEER_HANDLE_BYTES, d_all, KG_PEER_HANDLE_BYTES, ncclChar, c->comm, c->s_insert));
+    KG_CUDA(c, cudaStreamSynchronize(c->s_insert));
+    KG_CUDA(c, cudaMemcpy(all.data(), d_all, all.size(), cudaMemcpyDeviceToHost));
+    for (int r = 0; r < world; r++) {
+        if (r == rank) continue;
+        KgPeerHandle h;
+        memcpy(&h, all.data() + (size_t)r * KG_PEER_HANDLE_BYTES, sizeof(h));
+        if (h.magic != KG_PEER_MAGIC || h.rank != r || h.slab_bytes != c->skm_slab_bytes) {
+            c->err = "kg_comm_init: ranks disagree on the slot layout (k and batch_bytes must be the same on every rank)";
+            return KG_EBADARG;
+        }
+        for (int b = 0; b < 2; b++) {
+            SkmSlot& s = c->slot[b];
+            if (h.pid == mine.pid) {                        // another context of this process (one host thread per GPU)
+                int can = 0;
+                KG_CUDA(c, cudaDeviceCanAccessPeer(&can, c->cfg.device, h.device));
+                if (!can) { c->err = "kg_comm_init: no peer access between the devices"; return KG_ECUDA; }
+                cudaError_t e = cudaDeviceEnablePeerAccess(h.device, 0);
+                if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) KG_CUDA(c, e);
+                cudaGetLastError();
+                s.peer_slab[r] = (uint8_t*)(uintptr_t)h.ptr[b];
+            } else {                                        // another process: map its allocation
+                void* p = nullptr;
+                KG_CUDA(c, cudaIpcOpenMemHandle(&p, h.ipc[b], cudaIpcMemLazyEnablePeerAccess));
+                s.peer_opened[r] = p;
+                s.peer_slab[r] = (uint8_t*)p;
+            }
+            KG_CUDA(c, cudaMalloc(&s.r_buf[r], KG_SKM_META + c->skm_words_bytes));
+        }
+    }
+    return publish_slot_tables(c);
 }
 
-// Decide how the coming pass buckets its batches and size the scratch for it.  region_bytes = what the inserts
-// of this pass hit at random (count table, or the Bloom filter): local partitions are chosen so that one
-// partition's region is ~16-32 MiB, comfortably L2-resident next to the streaming keys.
+// Decide how the coming pass buckets its batches.  region_bytes = what the inserts of this pass hit at random (count
+// table, or the Bloom filter): local partitions are chosen so that one partition's region is ~16-32 MiB, comfortably
+// L2-resident next to the streamed descriptors.  Must come out the same on every rank (it fixes the bucket numbering).
 static int setup_pass_buckets(kg_ctx* c, size_t region_bytes) {
     c->pass_bucketed = false;
     c->pl = 1;
@@ -506,8 +633,7 @@ static int setup_pass_buckets(kg_ctx* c, size_t region_bytes) {
     if (!c->bucketed) return KG_OK;
     const u32 world = (u32)c->cfg.world;
     u32 pl = c->cfg.partitions;
-    if (c->cfg.table_mode == KG_TABLE_KAARME) pl = 1;          // occurrence records do not travel with bare keys
-    else if (pl == 0) {
+    if (pl == 0) {
         pl = 1;
         if (region_bytes > (96u << 20)) while ((size_t)pl * (24u << 20) < region_bytes && pl * 2 * world <= KG_MAX_BUCKETS) pl *= 2;
     }
@@ -516,47 +642,16 @@ static int setup_pass_buckets(kg_ctx* c, size_t region_bytes) {
     c->pl = pl;
     c->nb = world * pl;
     c->pass_bucketed = world > 1 || pl > 1;
-    if (!c->pass_bucketed) return KG_OK;
-    // one-pass (reserve) scatter on a single GPU: fixed-capacity bucket regions, 25 % slack + 8192 keys
-    size_t need = c->send_cap;
-    c->reserve_cap = 0;
-    if (world == 1 && c->W <= 4 && !getenv("KG_NO_RESERVE")) {
-        c->reserve_cap = (u32)(c->send_cap / pl + c->send_cap / pl / 4 + 8192);
-        need = (size_t)c->reserve_cap * pl;
-    }
-    if (need > c->send_alloc) {
-        for (int i = 0; i < 2; i++) { cudaFree(c->d_send[i]); c->d_send[i] = nullptr; }
-        c->send_alloc = need;
-    }
-    for (int i = 0; i < 2; i++) {
-        if (!c->d_send[i]) KG_CUDA(c, cudaMalloc(&c->d_send[i], c->send_alloc * c->W * sizeof(u64)));
-        if (c->recv_cap && !c->d_recv[i]) KG_CUDA(c, cudaMalloc(&c->d_recv[i], c->recv_cap * c->W * sizeof(u64)));
-    }
-    if (c->nb > c->nb_alloc) {
-        cudaFree(c->d_blk_hist); cudaFree(c->d_blk_base); cudaFree(c->d_bucket_counts); cudaFree(c->d_bucket_offs); cudaFree(c->d_matrix);
-        if (c->h_matrix) cudaFreeHost(c->h_matrix);
-        c->d_blk_hist = c->d_blk_base = c->d_bucket_counts = c->d_bucket_offs = c->d_matrix = nullptr; c->h_matrix = nullptr;
-        c->nb_alloc = 0;   // nothing is allocated until every buffer below exists (an allocation may fail half way)
-        KG_CUDA(c, cudaMalloc(&c->d_blk_hist, sizeof(u32) * (size_t)c->max_blocks * c->nb));
-        KG_CUDA(c, cudaMalloc(&c->d_blk_base, sizeof(u32) * (size_t)c->max_blocks * c->nb));
-        KG_CUDA(c, cudaMalloc(&c->d_bucket_counts, sizeof(u32) * (c->nb + 4)));
-        KG_CUDA(c, cudaMalloc(&c->d_bucket_offs, sizeof(u32) * (c->nb + 1)));
-        KG_CUDA(c, cudaMalloc(&c->d_matrix, sizeof(u32) * (size_t)(c->nb + 1) * world));
-        KG_CUDA(c, cudaHostAlloc((void**)&c->h_matrix, sizeof(u32) * (size_t)(c->nb + 1) * world, cudaHostAllocDefault));
-        c->nb_alloc = c->nb;
-    }
-    if (c->nb + 1 > c->seg_cap) {
-        for (int i = 0; i < 2; i++) {
-            cudaFree(c->d_seg[i]); if (c->h_seg[i]) cudaFreeHost(c->h_seg[i]);
-            c->d_seg[i] = nullptr; c->h_seg[i] = nullptr;
-        }
-        c->seg_cap = 0;
-        for (int i = 0; i < 2; i++) {
-            KG_CUDA(c, cudaMalloc(&c->d_seg[i], sizeof(u64) * 2 * (c->nb + 2)));
-            KG_CUDA(c, cudaHostAlloc((void**)&c->h_seg[i], sizeof(u64) * 2 * (c->nb + 2), cudaHostAllocDefault));
-        }
-        c->seg_cap = c->nb + 1;
-    }
+    c->skm_cap = (u32)(c->skm_region_total / c->nb);
+    return KG_OK;
+}
+
+// part_lo[p] = first slot (or Bloom word) of partition p of `total`
+static int upload_partition_bounds(kg_ctx* c, u64* d_dst, u64 total) {
+    std::vector<u64> lo(c->pl + 1);
+    for (u32 p = 0; p <= c->pl; p++) lo[p] = (u64)(((unsigned __int128)total * p) / c->pl);
+    KG_CUDA(c, cudaMemcpyAsync(d_dst, lo.data(), sizeof(u64) * lo.size(), cudaMemcpyHostToDevice, c->s_compute));
+    KG_CUDA(c, cudaStreamSynchronize(c->s_compute));
     return KG_OK;
 }
 
@@ -572,6 +667,7 @@ extern "C" int kg_pass_begin(kg_ctx* c, int pass) {
     c->ins_used = 0;
     c->ins_launches = 0;
     c->raw_bytes_pass = 0;
+    c->round = 0;
     KG_CUDA(c, cudaEventRecord(c->ev_pass_begin, c->s_compute));
     KG_CUDA(c, cudaMemsetAsync(c->d_stats, 0, sizeof(KgStats), c->s_compute));
     c->rb_streams = 0;
@@ -586,6 +682,7 @@ extern "C" int kg_pass_begin(kg_ctx* c, int pass) {
         KG_CUDA(c, cudaMemsetAsync(c->bloom.bits, 0, c->bloom_bytes, c->s_compute));
         c->bloom_done = false;
         { int rc = setup_pass_buckets(c, c->bloom_bytes); if (rc) return rc; }
+        { int rc = upload_partition_bounds(c, c->d_bpart_lo, c->bloom.nblocks); if (rc) return rc; }
     } else {
         if (c->compacted) {
             cudaFree(c->kaarme.slots); cudaFree(c->kaarme.roots);
@@ -599,7 +696,7 @@ extern "C" int kg_pass_begin(kg_ctx* c, int pass) {
         uint64_t nslots = next_prime3mod4(want);                                 // parallel_parser.hpp:236
         u32 stride = kg_slot_stride_words((u32)c->W, c->cfg.table_mode == KG_TABLE_KAARME);
         // packed 16-byte slots: two key words and >= 26 spare bits for the count (k = 33..51), plain table only;
-        // the count field stops at 2^(128-2k) - 2^17 (>= 66.9 M) instead of wrapping into the key
+        // the count field stops at 2^(128-2k) - 2^20 (>= 66 M) instead of wrapping into the key
         u32 packed_tb = 0;
         if (c->W == 2 && c->cfg.table_mode == KG_TABLE_PLAIN && 2 * c->cfg.k - 64 <= 38 && !getenv("KG_NO_PACKED")) {
             packed_tb = 2 * c->cfg.k - 64;
@@ -616,11 +713,12 @@ extern "C" int kg_pass_begin(kg_ctx* c, int pass) {
         c->table.nslots = nslots;
         c->table.stride = stride;
         c->table.kaarme = c->cfg.table_mode == KG_TABLE_KAARME;
-        c->table.world = (u32)c->cfg.world;
+        c->table.world = 1;            // slots are placed by partition bounds; the hash is not split between shards any more
         c->table.packed_tb = packed_tb;
+        c->table.full_flag = &c->d_stats->table_full;
         KG_CUDA(c, cudaMemsetAsync(c->table.slots, 0, bytes, c->s_compute));
         {
-            // the partition count must be identical on every rank (it fixes the bucket layout of the exchange):
+            // the partition count must be identical on every rank (it fixes the bucket numbering of the exchange):
             // derive it from configuration only.  After a Bloom pass the shard tables differ a little in size
             // (2 x the LOCAL new_in_second), so use the configured estimate there.
             size_t region = bytes;
@@ -629,7 +727,10 @@ extern "C" int kg_pass_begin(kg_ctx* c, int pass) {
             int rc = setup_pass_buckets(c, region);
             if (rc) return rc;
         }
+        { int rc = upload_partition_bounds(c, c->d_part_lo, nslots); if (rc) return rc; }
+        if (c->cfg.use_bloom && !c->ref_bloom) { int rc = upload_partition_bounds(c, c->d_bpart_lo, c->bloom.nblocks); if (rc) return rc; }
     }
+    c->bloom.world = 1;
     if (c->pass_bucketed) {   // inserts run on their own stream: order them after the clears above
         KG_CUDA(c, cudaEventRecord(c->ev_pass_ready, c->s_compute));
         KG_CUDA(c, cudaStreamWaitEvent(c->s_insert, c->ev_pass_ready, 0));
@@ -689,463 +790,74 @@ static int current_sink(const kg_ctx* c) {
 }
 
 template <int W>
-static void launch_insert_keys(kg_ctx* c, cudaStream_t s, const u64* keys, u64 n_upper, const u32* n_dev, int sink) {
-    const u32 block = 256;
-    u64 grid = (n_upper + KG_CHUNK - 1) / KG_CHUNK;
-    if (grid > c->insert_grid) grid = c->insert_grid;    // persistent kernel: just enough blocks to fill the GPU
-    if (grid == 0) return;
-    cudaMemsetAsync(c->d_work, 0, sizeof(u32), s);
+static void launch_skm_insert(kg_ctx* c, const KgSkmInsertArgs& a, int sink) {
+    const u32 grid = c->insert_grid;     // persistent: SMs x resident blocks
     switch (sink) {
-        case KG_SINK_TABLE: kg_insert_keys_kernel<W, KG_SINK_TABLE><<<(u32)grid, block, 0, s>>>(keys, n_upper, n_dev, c->table, c->bloom, c->d_stats, c->d_work); break;
-        case KG_SINK_BLOOM1: kg_insert_keys_kernel<W, KG_SINK_BLOOM1><<<(u32)grid, block, 0, s>>>(keys, n_upper, n_dev, c->table, c->bloom, c->d_stats, c->d_work); break;
-        case KG_SINK_BLOOM2: kg_insert_keys_kernel<W, KG_SINK_BLOOM2><<<(u32)grid, block, 0, s>>>(keys, n_upper, n_dev, c->table, c->bloom, c->d_stats, c->d_work); break;
+        case KG_SINK_TABLE: kg_skm_insert<W, KG_SINK_TABLE><<<grid, 256, 0, c->s_insert>>>(a); break;
+        case KG_SINK_BLOOM1: kg_skm_insert<W, KG_SINK_BLOOM1><<<grid, 256, 0, c->s_insert>>>(a); break;
+        case KG_SINK_BLOOM2: kg_skm_insert<W, KG_SINK_BLOOM2><<<grid, 256, 0, c->s_insert>>>(a); break;
         default: break;
     }
     c->launches++;
 }
 
-static void insert_keys(kg_ctx* c, cudaStream_t s, const u64* keys, u64 n_upper, const u32* n_dev) {
-    const int sink = current_sink(c);
+// One round of the minimizer-bucketed path (collective when world > 1; every rank issues the same sequence).
+//   s_compute  (have_batch: parse + kg_skm_scatter of this rank's batch were just queued into slot b = round & 1;
+//              otherwise the slot's cursors are cleared: the rank contributes nothing)            -> ev_ready
+//   s_insert   world > 1: one-word all-reduce = "every rank's slot b is ready, and every rank has finished the insert
+//              of the previous round" (so the OTHER slot may be overwritten: ev_free), its sum = ranks that had a batch;
+//              then the copy engines pull header + cursors + packed words of every peer's slot over NVLink
+//              kg_skm_segments (where are the descriptors for my partitions, partition-major across senders) and
+//              kg_skm_insert, which reads the peers' descriptors in place
+// No host synchronisation anywhere: the host only waits when kg_pass_end asks for the all-reduce's sum.
+static int skm_round(kg_ctx* c, bool have_batch, bool want_sum) {
+    const int b = (int)(c->round & 1);
+    SkmSlot& s = c->slot[b];
+    const int world = c->cfg.world, me = c->cfg.rank;
+    if (!have_batch) {
+        KG_CUDA(c, cudaStreamWaitEvent(c->s_compute, s.ev_free, 0));
+        KG_CUDA(c, cudaMemsetAsync(s.cursors, 0, sizeof(u32) * (c->nb + 1), c->s_compute));
+    }
+    KG_CUDA(c, cudaEventRecord(s.ev_ready, c->s_compute));
+    KG_CUDA(c, cudaStreamWaitEvent(c->s_insert, s.ev_ready, 0));
+    if (world > 1) {
+        KG_NCCL(c, kg_nccl().AllReduce(c->d_round + (have_batch ? 1 : 0), c->d_round + 4 + b, 1, ncclUint32, ncclSum, c->comm, c->s_insert));
+        KG_CUDA(c, cudaEventRecord(c->slot[b ^ 1].ev_free, c->s_insert));
+        if (want_sum) KG_CUDA(c, cudaMemcpyAsync(c->h_round_sum, c->d_round + 4 + b, sizeof(u32), cudaMemcpyDeviceToHost, c->s_insert));
+        for (int r = 0; r < world; r++)
+            if (r != me) KG_CUDA(c, cudaMemcpyAsync(s.r_buf[r], s.peer_slab[r], KG_SKM_META + c->skm_words_bytes, cudaMemcpyDefault, c->s_insert));
+    }
+    const u32 nseg = (u32)world * c->pl + (u32)world;
+    kg_skm_segments<<<1, 1024, 0, c->s_insert>>>(s.d_peers, (u32)world, (u32)me, c->pl, c->nb, c->skm_cap, c->skm_ovf_cap, s.d_seg_start, s.d_seg_ptr);
+    c->launches++;
+    KG_CUDA(c, cudaMemsetAsync(c->d_work, 0, sizeof(u32), c->s_insert));
+    KgSkmInsertArgs a;
+    a.seg_start = s.d_seg_start; a.seg_ptr = s.d_seg_ptr; a.nseg = nseg; a.my_rank = (u32)me; a.src = s.d_src;
+    a.part_lo = c->d_part_lo; a.bpart_lo = c->d_bpart_lo; a.table = c->table; a.bloom = c->bloom; a.stats = c->d_stats;
+    a.work = c->d_work; a.k = c->cfg.k;
     cudaEvent_t ia = next_ins_event(c), ib = next_ins_event(c);
-    if (ia) cudaEventRecord(ia, s);
+    if (ia) cudaEventRecord(ia, c->s_insert);
     c->ins_launches++;
-    switch (c->W) {
-        case 1: launch_insert_keys<1>(c, s, keys, n_upper, n_dev, sink); break;
-        case 2: launch_insert_keys<2>(c, s, keys, n_upper, n_dev, sink); break;
-        case 3: launch_insert_keys<3>(c, s, keys, n_upper, n_dev, sink); break;
-        case 4: launch_insert_keys<4>(c, s, keys, n_upper, n_dev, sink); break;
-        case 5: launch_insert_keys<5>(c, s, keys, n_upper, n_dev, sink); break;
-        case 6: launch_insert_keys<6>(c, s, keys, n_upper, n_dev, sink); break;
-        case 7: launch_insert_keys<7>(c, s, keys, n_upper, n_dev, sink); break;
-        case 8: launch_insert_keys<8>(c, s, keys, n_upper, n_dev, sink); break;
-    }
-    if (ib) cudaEventRecord(ib, s);
-}
-
-template <int W>
-static void launch_bucket(kg_ctx* c, const KgBucketArgs& a, u32 nwords, bool scatter) {
-    using G = KgBucketGeom<W>;
-    const u32 grid = (nwords + G::WPB - 1) / G::WPB;
-    if (scatter) {
-        const size_t smem = G::smem_bytes(a.nb);
-        if (!c->scatter_configured) {   // per device (one context per device, possibly several in one process)
-            cudaFuncSetAttribute(kg_owner_scatter<W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G::smem_bytes(KG_MAX_BUCKETS));
-            c->scatter_configured = true;
-        }
-        kg_owner_scatter<W><<<grid, G::TPB, smem, c->s_compute>>>(a);
-    } else {
-        kg_owner_hist<W><<<grid, G::WPB, 0, c->s_compute>>>(a);
-    }
-    c->launches++;
-}
-template <int W>
-static u32 bucket_grid(u32 nwords) { return (nwords + KgBucketGeom<W>::WPB - 1) / KgBucketGeom<W>::WPB; }
-static u32 bucket_blocks(const kg_ctx* c, u32 nwords) {
-    switch (c->W) {
-        case 1: return bucket_grid<1>(nwords);
-        case 2: return bucket_grid<2>(nwords);
-        case 3: return bucket_grid<3>(nwords);
-        case 4: return bucket_grid<4>(nwords);
-        case 5: return bucket_grid<5>(nwords);
-        case 6: return bucket_grid<6>(nwords);
-        case 7: return bucket_grid<7>(nwords);
-        default: return bucket_grid<8>(nwords);
-    }
-}
-static void bucket_kernel(kg_ctx* c, const KgBucketArgs& a, u32 grid, bool scatter) {
-    switch (c->W) {
-        case 1: launch_bucket<1>(c, a, grid, scatter); break;
-        case 2: launch_bucket<2>(c, a, grid, scatter); break;
-        case 3: launch_bucket<3>(c, a, grid, scatter); break;
-        case 4: launch_bucket<4>(c, a, grid, scatter); break;
-        case 5: launch_bucket<5>(c, a, grid, scatter); break;
-        case 6: launch_bucket<6>(c, a, grid, scatter); break;
-        case 7: launch_bucket<7>(c, a, grid, scatter); break;
-        case 8: launch_bucket<8>(c, a, grid, scatter); break;
-    }
-}
-
-template <int W>
-static void launch_insert_segs(kg_ctx* c, cudaStream_t s, const u64* keys, const u64* seg, u32 nseg, u64 n, int sink) {
-    u64 grid = (n + KG_CHUNK - 1) / KG_CHUNK;
-    if (grid > c->insert_grid) grid = c->insert_grid;
-    if (grid == 0) return;
-    cudaMemsetAsync(c->d_work, 0, sizeof(u32), s);
-    const u64* start = seg;
-    const u64* src = seg + (nseg + 1);
-    switch (sink) {
-        case KG_SINK_TABLE: kg_insert_segs_kernel<W, KG_SINK_TABLE><<<(u32)grid, 256, 0, s>>>(keys, start, src, nseg, c->table, c->bloom, c->d_stats, c->d_work); break;
-        case KG_SINK_BLOOM1: kg_insert_segs_kernel<W, KG_SINK_BLOOM1><<<(u32)grid, 256, 0, s>>>(keys, start, src, nseg, c->table, c->bloom, c->d_stats, c->d_work); break;
-        case KG_SINK_BLOOM2: kg_insert_segs_kernel<W, KG_SINK_BLOOM2><<<(u32)grid, 256, 0, s>>>(keys, start, src, nseg, c->table, c->bloom, c->d_stats, c->d_work); break;
-        default: break;
-    }
-    c->launches++;
-}
-
-template <int W>
-static void launch_reserve(kg_ctx* c, const KgReserveArgs& a, u32 nwords, int sink) {
-    if constexpr (W <= 4) {
-        using G = KgBucketGeom<W>;
-        const u32 grid = (nwords + G::WPB - 1) / G::WPB;
-        const size_t smem = (size_t)G::KEYS * W * 8 + (size_t)a.nb * 12 + (size_t)G::KEYS * 2 + 64;
-        const int max_smem = (int)((size_t)G::KEYS * W * 8 + (size_t)KG_MAX_BUCKETS * 12 + (size_t)G::KEYS * 2 + 64);
-        switch (sink) {
-            case KG_SINK_TABLE:
-                cudaFuncSetAttribute(kg_scatter_reserve<W, KG_SINK_TABLE>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem);
-                kg_scatter_reserve<W, KG_SINK_TABLE><<<grid, G::TPB, smem, c->s_compute>>>(a); break;
-            case KG_SINK_BLOOM1:
-                cudaFuncSetAttribute(kg_scatter_reserve<W, KG_SINK_BLOOM1>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem);
-                kg_scatter_reserve<W, KG_SINK_BLOOM1><<<grid, G::TPB, smem, c->s_compute>>>(a); break;
-            case KG_SINK_BLOOM2:
-                cudaFuncSetAttribute(kg_scatter_reserve<W, KG_SINK_BLOOM2>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem);
-                kg_scatter_reserve<W, KG_SINK_BLOOM2><<<grid, G::TPB, smem, c->s_compute>>>(a); break;
-            default: break;
-        }
-        c->launches++;
-    }
-}
-
-// One exchange round (collective when world > 1).  have_batch: this rank's send buffer (round & 1) was just
-// filled by bucket_batch; otherwise the rank contributes nothing and reports "done".  Returns via *all_done
-// whether every rank reported done in this round.
-//   buckets are owner-major: owner d holds buckets [d*pl, (d+1)*pl) = its local partitions, in table order
-//   s_ctl:    all-gather of the per-bucket counts -> host (own communicator, never behind a key transfer)
-//   s_comm:   grouped ncclSend/ncclRecv of the key slices
-//   s_insert: insert kernel over what arrived (partition-major across senders through a segment table),
-//             overlapping the next batch's parse + bucketing on s_compute
-static int exchange_round(kg_ctx* c, bool have_batch, bool* all_done, bool counts_gathered = false) {
-    const u32 nb = c->nb, pl = c->pl, world = (u32)c->cfg.world, rank = (u32)c->cfg.rank;
-    const int sb = (int)(c->round & 1);
-    const size_t row = nb + 1;
-    if (!counts_gathered) {          // (the peer path gathers the counts itself before it decides to fall back here)
-    if (!have_batch) {
-        KG_CUDA(c, cudaMemsetAsync(c->d_bucket_counts, 0, sizeof(u32) * nb, c->s_compute));
-        KG_CUDA(c, cudaMemsetAsync(c->d_bucket_counts + nb, 1, sizeof(u32), c->s_compute));   // non-zero = done
-        KG_CUDA(c, cudaEventRecord(c->ev_counts, c->s_compute));
-    }
-    KG_CUDA(c, cudaStreamWaitEvent(c->s_ctl, c->ev_counts, 0));
-    KG_NCCL(c, kg_nccl().AllGather(c->d_bucket_counts, c->d_matrix, row, ncclUint32, c->ctl_comm, c->s_ctl));
-    KG_CUDA(c, cudaMemcpyAsync(c->h_matrix, c->d_matrix, sizeof(u32) * row * world, cudaMemcpyDeviceToHost, c->s_ctl));
-    KG_CUDA(c, cudaEventRecord(c->ev_matrix, c->s_ctl));
-    KG_CUDA(c, cudaEventSynchronize(c->ev_matrix));
-    }
-    const u32* M = c->h_matrix;   // M[r*row + b] = keys rank r holds for bucket b; M[r*row + nb] = done flag
-    auto to_owner = [&](u32 r, u32 d) { u64 t = 0; for (u32 p = 0; p < pl; p++) t += M[r * row + d * pl + p]; return t; };
-    bool done = true;
-    u64 max_in = 0, any = 0;
-    for (u32 r = 0; r < world; r++) done = done && M[r * row + nb] != 0;
-    for (u32 d = 0; d < world; d++) {
-        u64 in = 0;
-        for (u32 r = 0; r < world; r++) in += to_owner(r, d);
-        if (in > max_in) max_in = in;
-        any += in;
-    }
-    *all_done = done;
-    if (any) {
-        // sub-rounds so that no rank receives more than recv_cap keys at once (identical on every rank)
-        const u64 S = (max_in + c->recv_cap - 1) / c->recv_cap;
-        std::vector<u64> send_off(world + 1, 0);
-        for (u32 d = 0; d < world; d++) send_off[d + 1] = send_off[d] + to_owner(rank, d);
-        if (have_batch) KG_CUDA(c, cudaStreamWaitEvent(c->s_comm, c->ev_scatter, 0));
-        for (u64 sr = 0; sr < S; sr++) {
-            const int rb = (int)(c->subround & 1);
-            KG_CUDA(c, cudaStreamWaitEvent(c->s_comm, c->ev_recv_free[rb], 0));
-            KG_CUDA(c, cudaEventSynchronize(c->ev_recv_full[rb]));   // the previous upload of h_seg[rb] has been consumed
-            std::vector<u64> recv_off(world + 1, 0), rlo_of(world), rhi_of(world);
-            KG_NCCL(c, kg_nccl().GroupStart());
-            for (u32 peer = 0; peer < world; peer++) {
-                const u64 ns = to_owner(rank, peer), lo = ns * sr / S, hi = ns * (sr + 1) / S;      // my slice for peer
-                const u64 nr = to_owner(peer, rank), rlo = nr * sr / S, rhi = nr * (sr + 1) / S;    // peer's slice for me
-                const u64* src = c->d_send[sb] + (send_off[peer] + lo) * c->W;
-                u64* dst = c->d_recv[rb] + recv_off[peer] * c->W;
-                if (peer == rank) {
-                    if (hi > lo) KG_CUDA(c, cudaMemcpyAsync(dst, src, (hi - lo) * c->W * sizeof(u64), cudaMemcpyDeviceToDevice, c->s_comm));
-                } else {
-                    if (hi > lo) KG_NCCL(c, kg_nccl().Send(src, (hi - lo) * c->W, ncclUint64, (int)peer, c->comm, c->s_comm));
-                    if (rhi > rlo) KG_NCCL(c, kg_nccl().Recv(dst, (rhi - rlo) * c->W, ncclUint64, (int)peer, c->comm, c->s_comm));
-                }
-                rlo_of[peer] = rlo; rhi_of[peer] = rhi;
-                recv_off[peer + 1] = recv_off[peer] + (rhi - rlo);
-            }
-            KG_NCCL(c, kg_nccl().GroupEnd());
-            const u64 n_recv = recv_off[world];
-            // segment table, partition-major across senders: sender s delivered keys [rlo, rhi) of its run for me,
-            // which is its partitions 0..pl-1 back to back
-            u32 nseg = 0;
-            u64* hs = c->h_seg[rb];
-            const u32 maxseg = c->nb;                      // world * pl segments at most
-            u64* h_start = hs;
-            u64* h_src = hs + (maxseg + 1);
-            u64 acc = 0;
-            for (u32 p = 0; p < pl; p++) {
-                for (u32 sdr = 0; sdr < world; sdr++) {
-                    u64 pbeg = 0;                           // start of partition p inside sender sdr's run for me
-                    for (u32 q = 0; q < p; q++) pbeg += M[sdr * row + rank * pl + q];
-                    const u64 pend = pbeg + M[sdr * row + rank * pl + p];
-                    const u64 a0 = pbeg > rlo_of[sdr] ? pbeg : rlo_of[sdr];
-                    const u64 a1 = pend < rhi_of[sdr] ? pend : rhi_of[sdr];
-                    if (a1 > a0) {
-                        h_start[nseg] = acc;
-                        h_src[nseg] = recv_off[sdr] + (a0 - rlo_of[sdr]);
-                        acc += a1 - a0;
-                        nseg++;
-                    }
-                }
-            }
-            h_start[nseg] = acc;
-            if (n_recv) {
-                // device layout: start[0..nseg], then src[0..nseg-1]
-                KG_CUDA(c, cudaMemcpyAsync(c->d_seg[rb], h_start, sizeof(u64) * (nseg + 1), cudaMemcpyHostToDevice, c->s_comm));
-                KG_CUDA(c, cudaMemcpyAsync(c->d_seg[rb] + (nseg + 1), h_src, sizeof(u64) * nseg, cudaMemcpyHostToDevice, c->s_comm));
-            }
-            KG_CUDA(c, cudaEventRecord(c->ev_recv_full[rb], c->s_comm));
-            KG_CUDA(c, cudaStreamWaitEvent(c->s_insert, c->ev_recv_full[rb], 0));
-            if (n_recv) {
-                const int sink = current_sink(c);
-                cudaEvent_t ia = next_ins_event(c), ib = next_ins_event(c);
-                if (ia) cudaEventRecord(ia, c->s_insert);
-                c->ins_launches++;
-                KG_DISPATCH_W(c->W, launch_insert_segs, c, c->s_insert, c->d_recv[rb], c->d_seg[rb], nseg, n_recv, sink);
-                if (ib) cudaEventRecord(ib, c->s_insert);
-            }
-            KG_CUDA(c, cudaEventRecord(c->ev_recv_free[rb], c->s_insert));
-            c->subround++;
-        }
-    }
-    KG_CUDA(c, cudaEventRecord(c->ev_send_free[sb], c->s_comm));
+    KG_DISPATCH_W(c->W, launch_skm_insert, c, a, current_sink(c));
+    if (ib) cudaEventRecord(ib, c->s_insert);
+    if (world == 1) KG_CUDA(c, cudaEventRecord(s.ev_free, c->s_insert));
     c->round++;
     return KG_OK;
 }
 
-// ---- peer exchange: the fused bucket -> peer-store path --------------------------------------------------------
-// With kg_peer_connect every rank has every other rank's two receive buffers mapped (CUDA IPC between processes, plain
-// peer access inside one process).  A round then is:
-//   s_compute: hist -> column scan (bucket_batch)                                  counts of this batch
-//   s_ctl:     wait "my receive buffer of this parity is free" -> all-gather of the counts -> host
-//              (so the gathered matrix also says: EVERY rank's buffer of this parity is free)
-//   host:      kg_peer_plan: where each of my (bucket) runs starts in its owner's buffer (partition-major there)
-//   s_compute: kg_owner_scatter_peer: the scatter's coalesced 16-byte runs go straight to the owners over NVLink
-//   s_comm:    one-word all-gather = "all scatters of this round have completed" (kernel completion makes peer
-//              stores visible)
-//   s_insert:  kg_insert_keys_kernel over my receive buffer, front to back = partition-major (L2-blocked, section 5)
-// No send buffer, no NCCL copy kernels on the SMs, no segment table; NVLink carries each key once.
-// A round whose busiest owner would overflow a receive buffer (heavy skew) falls back to the ncclSend/ncclRecv path.
-struct KgPeerHandle {               // KG_PEER_HANDLE_BYTES on the wire
-    uint64_t magic, pid;
-    int32_t rank, device;
-    uint64_t ptr[2], cap_keys;
-    cudaIpcMemHandle_t ipc[2];
-};
-static_assert(sizeof(KgPeerHandle) <= KG_PEER_HANDLE_BYTES, "peer handle size");
-#define KG_PEER_MAGIC 0x4B47504545523031ULL   // "KGPEER01"
-
-extern "C" int kg_peer_export(kg_ctx* c, void* handle_out) {
-    if (!c || !handle_out) return KG_EBADARG;
-    if (c->cfg.world < 2 || !c->bucketed) { c->err = "kg_peer_export needs world > 1"; return KG_EBADARG; }
-    if (c->pass) { c->err = "kg_peer_export inside a pass"; return KG_EBADARG; }
-    KG_CUDA(c, cudaSetDevice(c->cfg.device));
-    for (int i = 0; i < 2; i++)
-        if (!c->d_recv[i]) KG_CUDA(c, cudaMalloc(&c->d_recv[i], c->recv_cap * c->W * sizeof(u64)));
-    KgPeerHandle h;
-    memset(&h, 0, sizeof(h));
-    h.magic = KG_PEER_MAGIC;
-    h.pid = (uint64_t)getpid();
-    h.rank = c->cfg.rank;
-    h.device = c->cfg.device;
-    h.cap_keys = c->recv_cap;
-    for (int i = 0; i < 2; i++) {
-        h.ptr[i] = (uint64_t)(uintptr_t)c->d_recv[i];
-        KG_CUDA(c, cudaIpcGetMemHandle(&h.ipc[i], c->d_recv[i]));
-    }
-    memset(handle_out, 0, KG_PEER_HANDLE_BYTES);
-    memcpy(handle_out, &h, sizeof(h));
-    return KG_OK;
-}
-
-extern "C" int kg_peer_connect(kg_ctx* c, const void* handles, int world) {
-    if (!c || !handles) return KG_EBADARG;
-    if (world != c->cfg.world || world < 2 || world > KG_MAX_WORLD) { c->err = "kg_peer_connect: world differs from kg_config"; return KG_EBADARG; }
-    if (c->pass || c->peer_ready) { c->err = "kg_peer_connect: call once, outside a pass"; return KG_EBADARG; }
-    if (!c->d_recv[0] || !c->d_recv[1]) { c->err = "kg_peer_connect before kg_peer_export"; return KG_EBADARG; }
-    KG_CUDA(c, cudaSetDevice(c->cfg.device));
-    const uint64_t me = (uint64_t)getpid();
-    for (int r = 0; r < world; r++) {
-        KgPeerHandle h;
-        memcpy(&h, (const char*)handles + (size_t)r * KG_PEER_HANDLE_BYTES, sizeof(h));
-        if (h.magic != KG_PEER_MAGIC || h.rank != r || h.cap_keys != c->recv_cap) { c->err = "kg_peer_connect: bad handle (order must be rank order; same batch size on every rank)"; return KG_EBADARG; }
-        for (int i = 0; i < 2; i++) {
-            if (r == c->cfg.rank) {
-                c->peer_recv[i][r] = c->d_recv[i];
-            } else if (h.pid == me) {                       // another context of this process (one host thread per GPU)
-                int can = 0;
-                KG_CUDA(c, cudaDeviceCanAccessPeer(&can, c->cfg.device, h.device));
-                if (!can) { c->err = "kg_peer_connect: no peer access between the devices"; return KG_ECUDA; }
-                cudaError_t e = cudaDeviceEnablePeerAccess(h.device, 0);
-                if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) KG_CUDA(c, e);
-                cudaGetLastError();
-                c->peer_recv[i][r] = (u64*)(uintptr_t)h.ptr[i];
-            } else {                                        // another process: map its allocation
-                void* p = nullptr;
-                KG_CUDA(c, cudaIpcOpenMemHandle(&p, h.ipc[i], cudaIpcMemLazyEnablePeerAccess));
-                c->peer_opened[i][r] = p;
-                c->peer_recv[i][r] = (u64*)p;
-            }
-        }
-    }
-    for (int i = 0; i < 2; i++) {
-        KG_CUDA(c, cudaMalloc(&c->d_peer_ptrs[i], sizeof(u64*) * KG_MAX_WORLD));
-        KG_CUDA(c, cudaMemcpy(c->d_peer_ptrs[i], c->peer_recv[i], sizeof(u64*) * KG_MAX_WORLD, cudaMemcpyHostToDevice));
-        KG_CUDA(c, cudaMalloc(&c->d_remote_base[i], sizeof(u64) * KG_MAX_BUCKETS));
-        KG_CUDA(c, cudaHostAlloc((void**)&c->h_remote_base[i], sizeof(u64) * KG_MAX_BUCKETS, cudaHostAllocDefault));
-    }
-    KG_CUDA(c, cudaMalloc(&c->d_barrier, sizeof(u32) * (KG_MAX_WORLD + 1)));
-    KG_CUDA(c, cudaMemset(c->d_barrier, 0, sizeof(u32) * (KG_MAX_WORLD + 1)));
-    c->peer_ready = true;
-    return KG_OK;
-}
-
-extern "C" int kg_peer_stats(const kg_ctx* c, uint64_t* peer_rounds, uint64_t* fallback_rounds) {
-    if (!c) return KG_EBADARG;
-    if (peer_rounds) *peer_rounds = c->peer_rounds;
-    if (fallback_rounds) *fallback_rounds = c->peer_fallback_rounds;
-    return KG_OK;
-}
-
-template <int W>
-static void launch_scatter_peer(kg_ctx* c, const KgBucketArgs& a, const KgPeerArgs& pa, u32 nwords) {
-    using G = KgBucketGeom<W>;
-    const u32 grid = (nwords + G::WPB - 1) / G::WPB;
-    cudaFuncSetAttribute(kg_owner_scatter_peer<W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G::smem_bytes(KG_MAX_BUCKETS));
-    kg_owner_scatter_peer<W><<<grid, G::TPB, G::smem_bytes(a.nb), c->s_compute>>>(a, pa);
+// bucket the windows of the batch that was just packed into the current slot, then hand the slot to the round
+static int bucket_batch(kg_ctx* c, u32 nwords) {
+    SkmSlot& s = c->slot[c->round & 1];
+    KG_CUDA(c, cudaMemsetAsync(s.cursors, 0, sizeof(u32) * (c->nb + 1), c->s_compute));
+    KgSkmScatterArgs a;
+    a.words = s.words; a.brk = c->d_brk; a.st = c->d_stream; a.cursors = s.cursors; a.regions = s.desc;
+    a.ovf = s.desc + (u64)c->nb * c->skm_cap; a.hdr = s.hdr; a.stats = c->d_stats;
+    a.k = c->cfg.k; a.m = c->skm_m; a.nb = c->nb; a.pl = c->pl; a.cap = c->skm_cap; a.src = (u32)c->cfg.rank;
+    a.ovf_cap = c->skm_ovf_cap; a.nwords = nwords;
+    const u32 grid = (nwords + KG_SKM_TPB - 1) / KG_SKM_TPB;
+    kg_skm_scatter<<<grid, KG_SKM_TPB, 0, c->s_compute>>>(a);
     c->launches++;
-}
-
-// One round of the peer exchange (collective).  have_batch: hist + column scan of this rank's batch are queued on
-// s_compute and ev_counts is recorded (bucket_batch); otherwise the rank contributes nothing and reports "done".
-static int peer_round(kg_ctx* c, bool have_batch, const KgBucketArgs* a, u32 nthreads, bool* all_done) {
-    const u32 nb = c->nb, pl = c->pl, world = (u32)c->cfg.world, rank = (u32)c->cfg.rank;
-    const int rb = (int)(c->round & 1);
-    const size_t row = nb + 1;
-    if (!have_batch) {
-        KG_CUDA(c, cudaMemsetAsync(c->d_bucket_counts, 0, sizeof(u32) * nb, c->s_compute));
-        KG_CUDA(c, cudaMemsetAsync(c->d_bucket_counts + nb, 1, sizeof(u32), c->s_compute));   // non-zero = done
-        KG_CUDA(c, cudaEventRecord(c->ev_counts, c->s_compute));
-    }
-    KG_CUDA(c, cudaStreamWaitEvent(c->s_ctl, c->ev_counts, 0));
-    KG_CUDA(c, cudaStreamWaitEvent(c->s_ctl, c->ev_recv_free[rb], 0));   // gathered matrix => every rank's buffer rb is free
-    KG_NCCL(c, kg_nccl().AllGather(c->d_bucket_counts, c->d_matrix, row, ncclUint32, c->ctl_comm, c->s_ctl));
-    KG_CUDA(c, cudaMemcpyAsync(c->h_matrix, c->d_matrix, sizeof(u32) * row * world, cudaMemcpyDeviceToHost, c->s_ctl));
-    KG_CUDA(c, cudaEventRecord(c->ev_matrix, c->s_ctl));
-    KG_CUDA(c, cudaEventSynchronize(c->ev_matrix));
-    const KgPeerPlan plan = kg_peer_plan(c->h_matrix, world, pl, rank);
-    *all_done = plan.all_done;
-    if (plan.max_in > c->recv_cap) {
-        // heavy skew: the busiest owner cannot take its keys in one piece -> this round goes through the send buffer
-        // and ncclSend/ncclRecv in sub-rounds (every rank sees the same matrix and takes the same decision)
-        c->peer_fallback_rounds++;
-        if (have_batch) {
-            const int sb = (int)(c->round & 1);
-            KgBucketArgs b = *a;
-            b.out_keys = c->d_send[sb];
-            KG_CUDA(c, cudaStreamWaitEvent(c->s_compute, c->ev_send_free[sb], 0));
-            bucket_kernel(c, b, nthreads, true);
-            KG_CUDA(c, cudaEventRecord(c->ev_scatter, c->s_compute));
-        }
-        return exchange_round(c, have_batch, all_done, /*counts_gathered=*/true);
-    }
-    c->peer_rounds++;
-    if (plan.max_in == 0) { c->round++; return KG_OK; }     // nobody moves anything this round
-    if (have_batch) {
-        memcpy(c->h_remote_base[rb], plan.remote_base.data(), sizeof(u64) * nb);
-        KG_CUDA(c, cudaMemcpyAsync(c->d_remote_base[rb], c->h_remote_base[rb], sizeof(u64) * nb, cudaMemcpyHostToDevice, c->s_compute));
-        KgPeerArgs pa;
-        pa.peer = c->d_peer_ptrs[rb];
-        pa.remote_base = c->d_remote_base[rb];
-        pa.pl = pl;
-        KG_DISPATCH_W(c->W, launch_scatter_peer, c, *a, pa, nthreads);
-        KG_CUDA(c, cudaEventRecord(c->ev_scatter, c->s_compute));
-        KG_CUDA(c, cudaStreamWaitEvent(c->s_comm, c->ev_scatter, 0));
-    }
-    // "every scatter of this round has completed": a collective on s_comm that each rank enters after its own scatter
-    KG_NCCL(c, kg_nccl().AllGather(c->d_barrier + KG_MAX_WORLD, c->d_barrier, 1, ncclUint32, c->comm, c->s_comm));
-    KG_CUDA(c, cudaEventRecord(c->ev_recv_full[rb], c->s_comm));
-    KG_CUDA(c, cudaStreamWaitEvent(c->s_insert, c->ev_recv_full[rb], 0));
-    if (plan.my_in) insert_keys(c, c->s_insert, c->d_recv[rb], plan.my_in, nullptr);   // contiguous, partition-major
-    KG_CUDA(c, cudaEventRecord(c->ev_recv_free[rb], c->s_insert));
-    c->round++;
-    return KG_OK;
-}
-
-// bucket the k-mers of the batch that was just packed, then hand them on
-//   single GPU, W <= 4 : one-pass reserve scatter -> segment table -> insert (kg_scatter_reserve)
-//   otherwise          : hist -> scan -> scatter (exact layout, needed for the exchange) -> exchange / insert
-static int bucket_batch(kg_ctx* c, u32 nthreads) {
-    if (c->cfg.world == 1 && c->reserve_cap) {
-        const int b = (int)(c->round & 1);
-        const int sink = current_sink(c);
-        u32* cursors = c->d_bucket_counts;
-        KG_CUDA(c, cudaMemsetAsync(cursors, 0, sizeof(u32) * c->nb, c->s_compute));
-        KG_CUDA(c, cudaStreamWaitEvent(c->s_compute, c->ev_send_free[b], 0));     // insert(round-2) has drained this buffer
-        KgReserveArgs r;
-        r.words = c->d_words; r.brk = c->d_brk; r.st = c->d_stream; r.cursors = cursors; r.out_keys = c->d_send[b];
-        r.stats = c->d_stats; r.table = c->table; r.bloom = c->bloom; r.k = c->cfg.k; r.nb = c->nb; r.cap = c->reserve_cap;
-        KG_DISPATCH_W(c->W, launch_reserve, c, r, nthreads, sink);
-        kg_seg_from_cursors<<<1, 1024, 0, c->s_compute>>>(cursors, c->nb, c->reserve_cap, c->d_seg[b], c->d_seg[b] + (c->nb + 1));
-        c->launches++;
-        KG_CUDA(c, cudaEventRecord(c->ev_scatter, c->s_compute));
-        KG_CUDA(c, cudaStreamWaitEvent(c->s_insert, c->ev_scatter, 0));
-        cudaEvent_t ia = next_ins_event(c), ib = next_ins_event(c);
-        if (ia) cudaEventRecord(ia, c->s_insert);
-        c->ins_launches++;
-        KG_DISPATCH_W(c->W, launch_insert_segs, c, c->s_insert, c->d_send[b], c->d_seg[b], c->nb, (u64)nthreads * 32u, sink);
-        if (ib) cudaEventRecord(ib, c->s_insert);
-        KG_CUDA(c, cudaEventRecord(c->ev_send_free[b], c->s_insert));
-        c->round++;
-        return KG_OK;
-    }
-    const u32 grid = bucket_blocks(c, nthreads);   // blocks of the hist / scatter pair
-    const int sb = c->cfg.world > 1 ? (int)(c->round & 1) : 0;
-    KgBucketArgs a;
-    a.words = c->d_words; a.brk = c->d_brk; a.st = c->d_stream;
-    a.blk_hist = c->d_blk_hist; a.blk_base = c->d_blk_base; a.bucket_offs = c->d_bucket_offs; a.out_keys = c->d_send[sb];
-    a.stats = c->d_stats; a.k = c->cfg.k; a.nb = c->nb; a.world = (u32)c->cfg.world;
-    bucket_kernel(c, a, nthreads, false);
-    kg_bucket_colscan<<<c->nb, 1024, 0, c->s_compute>>>(c->d_blk_hist, c->d_blk_base, grid, c->nb, c->d_bucket_counts);
-    kg_bucket_offsets<<<1, 1024, 0, c->s_compute>>>(c->d_bucket_counts, c->nb, c->d_bucket_offs);
-    c->launches += 2;
-    if (c->cfg.world > 1 && c->peer_ready) {   // fused bucket -> peer-store exchange (kg_peer_connect)
-        KG_CUDA(c, cudaMemsetAsync(c->d_bucket_counts + c->nb, 0, sizeof(u32), c->s_compute));   // not done
-        KG_CUDA(c, cudaEventRecord(c->ev_counts, c->s_compute));
-        bool all_done;
-        return peer_round(c, true, &a, nthreads, &all_done);
-    }
-    if (c->cfg.world > 1) {
-        KG_CUDA(c, cudaMemsetAsync(c->d_bucket_counts + c->nb, 0, sizeof(u32), c->s_compute));   // not done
-        KG_CUDA(c, cudaEventRecord(c->ev_counts, c->s_compute));
-        KG_CUDA(c, cudaStreamWaitEvent(c->s_compute, c->ev_send_free[sb], 0));   // round-2 sends have left this buffer
-        bucket_kernel(c, a, nthreads, true);
-        KG_CUDA(c, cudaEventRecord(c->ev_scatter, c->s_compute));
-        bool all_done;
-        return exchange_round(c, true, &all_done);
-    }
-    // single GPU, partitioned: the send buffer is partition-major; one insert launch walks it in order, so the
-    // blocks in flight at any moment hit one or two table regions (L2-resident).  The insert runs on its own
-    // stream and the key buffers alternate, so the (ALU-bound) parse + bucketing of the next batch overlaps the
-    // (L2-latency-bound) insert of this one.
-    {
-        const int b = (int)(c->round & 1);
-        a.out_keys = c->d_send[b];
-        KG_CUDA(c, cudaStreamWaitEvent(c->s_compute, c->ev_send_free[b], 0));     // insert(round-2) has drained it
-        bucket_kernel(c, a, nthreads, true);
-        KG_CUDA(c, cudaMemcpyAsync(c->d_bucket_counts + c->nb + 1 + b, c->d_bucket_offs + c->nb, sizeof(u32),
-                                   cudaMemcpyDeviceToDevice, c->s_compute));     // this batch's key total, kept per buffer
-        KG_CUDA(c, cudaEventRecord(c->ev_scatter, c->s_compute));
-        KG_CUDA(c, cudaStreamWaitEvent(c->s_insert, c->ev_scatter, 0));
-        insert_keys(c, c->s_insert, c->d_send[b], (u64)nthreads * 32u, c->d_bucket_counts + c->nb + 1 + b);
-        KG_CUDA(c, cudaEventRecord(c->ev_send_free[b], c->s_insert));
-        c->round++;
-    }
-    return KG_OK;
+    return skm_round(c, true, false);
 }
 
 template <int W>
@@ -1170,14 +882,14 @@ static void launch_rb_count(kg_ctx* c, const KgCountArgs& a, u32 nthreads) {
 
 // emulation mode, Bloom pass: sweep 1 over the batch that was just packed, and keep its packed stream (with the stream
 // state it was packed under) for sweeps 2 and 3 at kg_pass_end
-static int rb_bloom_batch(kg_ctx* c, u32 nthreads) {
+static int rb_bloom_batch(kg_ctx* c, const u64* words, u32 nthreads) {
     kg_ctx::RbBatch b{nullptr, nullptr, nullptr, nthreads};
     KG_CUDA(c, cudaMalloc(&b.words, sizeof(u64) * nthreads));
     c->rb_log.push_back(b);                                  // owned by the context from here on
     kg_ctx::RbBatch& e = c->rb_log.back();
     KG_CUDA(c, cudaMalloc(&e.brk, sizeof(u32) * nthreads));
     KG_CUDA(c, cudaMalloc(&e.st, sizeof(KgStream)));
-    KG_CUDA(c, cudaMemcpyAsync(e.words, c->d_words, sizeof(u64) * nthreads, cudaMemcpyDeviceToDevice, c->s_compute));
+    KG_CUDA(c, cudaMemcpyAsync(e.words, words, sizeof(u64) * nthreads, cudaMemcpyDeviceToDevice, c->s_compute));
     KG_CUDA(c, cudaMemcpyAsync(e.brk, c->d_brk, sizeof(u32) * nthreads, cudaMemcpyDeviceToDevice, c->s_compute));
     KG_CUDA(c, cudaMemcpyAsync(e.st, c->d_stream, sizeof(KgStream), cudaMemcpyDeviceToDevice, c->s_compute));
     KG_DISPATCH_W(c->W, launch_rb_sweep, c, 1, e.words, e.brk, e.st, nthreads);
@@ -1191,12 +903,20 @@ static int process_batch(kg_ctx* c, const uint8_t* d_in, size_t n, uint32_t flag
     const u32 ntiles = (u32)((n + KG_TILE - 1) / KG_TILE);
     const bool fasta = c->cfg.input_mode == KG_INPUT_FASTA;
     const size_t nwords = n / 32 + c->carry_max_words + 4;
+    // the packed stream of a bucketed batch lives in the batch slot (the insert of this batch, and the peers, read it
+    // there): wait until the round that used the slot two batches ago has let go of it
+    u64* d_words = c->d_words_direct;
+    if (c->bucketed) {
+        SkmSlot& slot = c->slot[c->round & 1];
+        KG_CUDA(c, cudaStreamWaitEvent(s, slot.ev_free, 0));
+        d_words = slot.words;
+    }
     cudaEvent_t e0 = next_event(c), e1 = next_event(c), e2 = next_event(c);
     if (e0) cudaEventRecord(e0, s);
-    KG_CUDA(c, cudaMemsetAsync(c->d_words, 0, sizeof(u64) * nwords, s));
+    KG_CUDA(c, cudaMemsetAsync(d_words, 0, sizeof(u64) * nwords, s));
     KG_CUDA(c, cudaMemsetAsync(c->d_brk, 0, sizeof(u32) * nwords, s));
-    kg_carry_restore<<<1, 32, 0, s>>>(c->d_words, c->d_brk, c->d_stream, c->d_carry_words, c->d_carry_brk, c->carry_max_words);
-    const bool tma = c->parse_tma;   // opt-in: tiles staged through shared memory by a TMA bulk copy (kg_fetch16<true>)
+    kg_carry_restore<<<1, 32, 0, s>>>(d_words, c->d_brk, c->d_stream, c->d_carry_words, c->d_carry_brk, c->carry_max_words);
+    const bool tma = c->parse_tma;   // tiles staged through shared memory by a TMA bulk copy (kg_fetch16<true>)
     if (fasta) {
         if (tma) kg_hdr_summary<true><<<ntiles, KG_PT, 0, s>>>(d_in, n, c->d_tile_hdr_eff);
         else kg_hdr_summary<false><<<ntiles, KG_PT, 0, s>>>(d_in, n, c->d_tile_hdr_eff);
@@ -1212,11 +932,11 @@ static int process_batch(kg_ctx* c, const uint8_t* d_in, size_t n, uint32_t flag
     kg_tile_scan<<<1, 1024, 0, s>>>(c->d_tile_nbases, c->d_tile_off, ntiles, c->d_stream);
     kg_lww_scan<<<1, 1024, 0, s>>>(c->d_tile_pend_eff, c->d_tile_pend_in, ntiles, &c->d_stream->pending_break);
     if (fasta) {
-        if (tma) kg_tile_pack<true, true><<<ntiles, KG_PT, 0, s>>>(d_in, n, c->d_tile_hdr_in, c->d_tile_off, c->d_tile_pend_in, c->d_words, c->d_brk);
-        else kg_tile_pack<true, false><<<ntiles, KG_PT, 0, s>>>(d_in, n, c->d_tile_hdr_in, c->d_tile_off, c->d_tile_pend_in, c->d_words, c->d_brk);
+        if (tma) kg_tile_pack<true, true><<<ntiles, KG_PT, 0, s>>>(d_in, n, c->d_tile_hdr_in, c->d_tile_off, c->d_tile_pend_in, d_words, c->d_brk);
+        else kg_tile_pack<true, false><<<ntiles, KG_PT, 0, s>>>(d_in, n, c->d_tile_hdr_in, c->d_tile_off, c->d_tile_pend_in, d_words, c->d_brk);
     } else {
-        if (tma) kg_tile_pack<false, true><<<ntiles, KG_PT, 0, s>>>(d_in, n, c->d_tile_hdr_in, c->d_tile_off, c->d_tile_pend_in, c->d_words, c->d_brk);
-        else kg_tile_pack<false, false><<<ntiles, KG_PT, 0, s>>>(d_in, n, c->d_tile_hdr_in, c->d_tile_off, c->d_tile_pend_in, c->d_words, c->d_brk);
+        if (tma) kg_tile_pack<false, true><<<ntiles, KG_PT, 0, s>>>(d_in, n, c->d_tile_hdr_in, c->d_tile_off, c->d_tile_pend_in, d_words, c->d_brk);
+        else kg_tile_pack<false, false><<<ntiles, KG_PT, 0, s>>>(d_in, n, c->d_tile_hdr_in, c->d_tile_off, c->d_tile_pend_in, d_words, c->d_brk);
     }
     c->launches += 4;
     if (e1) cudaEventRecord(e1, s);
@@ -1224,11 +944,11 @@ static int process_batch(kg_ctx* c, const uint8_t* d_in, size_t n, uint32_t flag
         const u32 nthreads = (u32)(n / 32 + c->carry_max_words + 2);   // upper bound on packed words
         if (c->ref_bloom) {                                            // bit-exact emulation of the reference's filters
             if (c->pass == KG_PASS_BLOOM) {
-                int rc = rb_bloom_batch(c, nthreads);
+                int rc = rb_bloom_batch(c, d_words, nthreads);
                 if (rc) return rc;
             } else {
                 KgCountArgs a;
-                a.words = c->d_words; a.brk = c->d_brk; a.st = c->d_stream;
+                a.words = d_words; a.brk = c->d_brk; a.st = c->d_stream;
                 a.table = c->table; a.bloom = c->bloom;
                 a.stats = c->d_stats; a.k = c->cfg.k; a.rank = 0; a.world = 1;
                 KG_DISPATCH_W(c->W, launch_rb_count, c, a, nthreads);
@@ -1238,27 +958,18 @@ static int process_batch(kg_ctx* c, const uint8_t* d_in, size_t n, uint32_t flag
             if (rc) return rc;
         } else {
             KgCountArgs a;
-            a.words = c->d_words; a.brk = c->d_brk; a.st = c->d_stream;
+            a.words = d_words; a.brk = c->d_brk; a.st = c->d_stream;
             a.table = c->table; a.bloom = c->bloom;
             a.stats = c->d_stats; a.k = c->cfg.k; a.rank = (u32)c->cfg.rank; a.world = (u32)c->cfg.world;
             const int sink = current_sink(c);
             cudaEvent_t ia = next_ins_event(c), ib = next_ins_event(c);
             if (ia) cudaEventRecord(ia, s);
             c->ins_launches++;
-            switch (c->W) {
-                case 1: launch_count<1>(c, a, nthreads, sink); break;
-                case 2: launch_count<2>(c, a, nthreads, sink); break;
-                case 3: launch_count<3>(c, a, nthreads, sink); break;
-                case 4: launch_count<4>(c, a, nthreads, sink); break;
-                case 5: launch_count<5>(c, a, nthreads, sink); break;
-                case 6: launch_count<6>(c, a, nthreads, sink); break;
-                case 7: launch_count<7>(c, a, nthreads, sink); break;
-                case 8: launch_count<8>(c, a, nthreads, sink); break;
-            }
+            KG_DISPATCH_W(c->W, launch_count, c, a, nthreads, sink);
             if (ib) cudaEventRecord(ib, s);
         }
     }
-    kg_carry_save<<<1, 32, 0, s>>>(c->d_words, c->d_brk, c->d_stream, c->d_carry_words, c->d_carry_brk, c->cfg.k, c->carry_max_words);
+    kg_carry_save<<<1, 32, 0, s>>>(d_words, c->d_brk, c->d_stream, c->d_carry_words, c->d_carry_brk, c->cfg.k, c->carry_max_words);
     c->launches += 1;
     if (e2) cudaEventRecord(e2, s);
     KG_CUDA(c, cudaGetLastError());
@@ -1295,10 +1006,9 @@ extern "C" int kg_feed_device(kg_ctx* c, const void* device_bytes, size_t n, uin
     return KG_OK;
 }
 
-// Opt-in (KG_FEED_PREFETCH=1, unmeasured): software-pipelined feed of a pinned buffer.  The H2D copy of chunk i+1 is
-// issued on the copy stream BEFORE process_batch(i) -- which, with world > 1, blocks the host on the count all-gather
-// of chunk i -- and is gated on the device (cudaStreamWaitEvent on the raw buffer's free event) instead of a host wait,
-// so the copies leave the compute stream's critical path.
+// Software-pipelined feed of a pinned buffer: the H2D copy of chunk i+1 is issued on the copy stream BEFORE the kernels
+// of chunk i are queued, and is gated on the device (cudaStreamWaitEvent on the raw buffer's free event) instead of a
+// host wait, so the copies never sit on the compute stream's critical path.  (KG_FEED_PREFETCH=0 selects the simple loop.)
 static int feed_pinned_pipelined(kg_ctx* c, const uint8_t* bytes, size_t n, uint32_t flags) {
     const size_t B = c->batch_bytes, nchunks = (n + B - 1) / B;
     const int raw0 = c->raw_idx;
@@ -1371,14 +1081,14 @@ extern "C" int kg_pass_end(kg_ctx* c, kg_pass_stats* out) {
     if (!c || !c->pass) return KG_EBADARG;
     KG_CUDA(c, cudaSetDevice(c->cfg.device));
     if (c->cfg.world > 1) {
-        // keep taking part in exchange rounds until every rank has fed its last batch
-        bool all_done = false;
-        while (!all_done) {
-            int rc = c->peer_ready ? peer_round(c, false, nullptr, 0, &all_done) : exchange_round(c, false, &all_done);
+        // keep taking part in rounds until a round in which NO rank had a batch: every rank then has issued the same
+        // number of rounds, and entering that last round's all-reduce means every insert of the pass has completed
+        for (;;) {
+            int rc = skm_round(c, false, true);
             if (rc) return rc;
+            KG_CUDA(c, cudaStreamSynchronize(c->s_insert));
+            if (c->h_round_sum[0] == 0) break;
         }
-        KG_CUDA(c, cudaEventRecord(c->ev_tail, c->s_comm));
-        KG_CUDA(c, cudaStreamWaitEvent(c->s_compute, c->ev_tail, 0));
     }
     if (c->pass_bucketed) {
         KG_CUDA(c, cudaEventRecord(c->ev_tail, c->s_insert));
@@ -1438,6 +1148,7 @@ extern "C" int kg_pass_end(kg_ctx* c, kg_pass_stats* out) {
     c->pass = 0;
     c->stream_open = false;
     if (pass == KG_PASS_COUNT) c->counted = true;
+    if (st.table_full == 2) { c->err = "internal: descriptor overflow list exhausted"; return KG_ECUDA; }
     if (pass == KG_PASS_COUNT && st.table_full) { c->err = "Hash table is full"; c->pass = 0; return KG_ETABLE_FULL; }
     return KG_OK;
 }
@@ -1445,7 +1156,10 @@ extern "C" int kg_pass_end(kg_ctx* c, kg_pass_stats* out) {
 template <int W>
 static void launch_kaarme_build(kg_ctx* c, const u32* bitmap, const u64* prefix, KgKaarme out, u64* root_counter) {
     const u32 grid = (u32)((c->table.nslots + 255) / 256);
-    kg_kaarme_build<W><<<grid, 256, 0, c->s_compute>>>(c->table, c->cfg.k, bitmap, prefix, out, root_counter);
+    KgPlacement pm;
+    pm.part_lo = c->d_part_lo; pm.pl = c->pass_bucketed ? c->pl : 1; pm.nb = c->pass_bucketed ? c->nb : 1;
+    pm.m = c->skm_m; pm.rank = (u32)c->cfg.rank;
+    kg_kaarme_build<W><<<grid, 256, 0, c->s_compute>>>(c->table, c->cfg.k, bitmap, prefix, out, root_counter, pm);
     c->launches++;
 }
 template <int W>
@@ -1457,7 +1171,6 @@ static void launch_kaarme_chain(kg_ctx* c) {
 extern "C" int kg_compact(kg_ctx* c, kg_compact_stats* stats) {
     if (!c) return KG_EBADARG;
     if (c->cfg.table_mode != KG_TABLE_KAARME) { c->err = "kg_compact needs table_mode KG_TABLE_KAARME"; return KG_EBADARG; }
-    if (c->cfg.world > 1) { c->err = "kg_compact: occurrence positions are not exchanged between shards yet (single GPU only)"; return KG_EBADARG; }
     if (!c->counted || !c->table.slots) { c->err = "kg_compact before the count pass"; return KG_EBADARG; }
     if (c->compacted) return KG_OK;
     KG_CUDA(c, cudaSetDevice(c->cfg.device));

@@ -81,6 +81,17 @@ __device__ __forceinline__ u64 kg_ld_u64(const void* p) {
     asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
     return v;
 }
+// acquire loads: what follows (the key words of a slot) is ordered after the observation of a published `meta`
+__device__ __forceinline__ u32 kg_ld_acquire_u32(const void* p) {
+    u32 v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ u64 kg_ld_acquire_u64(const void* p) {
+    u64 v;
+    asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
 __device__ __forceinline__ void kg_ld_v2(const void* p, u64& a, u64& b) {
     asm volatile("ld.relaxed.gpu.global.v2.u64 {%0, %1}, [%2];" : "=l"(a), "=l"(b) : "l"(p) : "memory");
 }
@@ -100,7 +111,15 @@ struct KgTable {
     u32 world;       // shards the hash space is split into (slot uses the in-shard fraction of the hash)
     u32 packed_tb;   // != 0: PACKED 16-byte slots (W == 2 only): word 0 = count << packed_tb | key word 0,
                      // word 1 = key word 1; packed_tb = bits of key word 0 in use (2k - 64)
+    const u32* full_flag;  // KgStats::table_full of the pass: a probe sequence that runs long gives up once it is set
 };
+
+// Probe budget.  The reference probes the whole table before it reports "full" (parallel_parser.hpp:742-746); here a
+// probe sequence may run over min(nslots, 2^20) slots -- at any load factor below ~0.9999 no cluster is that long -- and
+// once ONE insert has exhausted its budget every other long-running probe gives up within 256 steps (full_flag), so a
+// full table is reported in about a second instead of hanging the device.
+#define KG_MAX_PROBE (1ull << 20)
+#define KG_COUNT_MARGIN 0x100000u   // counters stop this far below their limit: more threads than this never race on one slot
 
 __host__ __device__ inline u32 kg_slot_stride_words(u32 W, bool kaarme) {
     u32 need = 1 + W + (kaarme ? 1u : 0u);
@@ -108,23 +127,24 @@ __host__ __device__ inline u32 kg_slot_stride_words(u32 W, bool kaarme) {
     return (need + 3u) & ~3u;          // multiple of 32 B
 }
 
-// find-or-insert `key`, count += 1.  Returns slot index, or ~0 when the probe budget is exhausted.
+// find-or-insert `key` starting at `slot`, count += 1.  Returns the slot index, or ~0 when the probe budget is exhausted.
 //   meta low 32 bits: 0 = empty, KG_LOCKED = being written, otherwise the occurrence count.
-//   Writer: CAS 0->LOCKED, store key words, release-store count=1.  Reader: meta first, then (program- and
-//   data-dependent) the key words, all as L2-coherent accesses; key words never change once published.
+//   Writer: CAS 0->LOCKED, store key words, release-store count=1.  Reader: an ACQUIRE load of meta, then the key words
+//   (W > 1; relaxed loads ordered after the acquire -- PTX does not order loads by control dependency).  W == 1 reads
+//   meta and the key in one aligned 16-byte access.  Key words never change once published.
 template <int W>
-__device__ __forceinline__ u64 kg_table_add(const KgTable& t, const u64 (&key)[W], u64 h, bool& is_new) {
-    u64 slot = kg_slot(h, t.nslots, t.world);
+__device__ __forceinline__ u64 kg_table_add(const KgTable& t, const u64 (&key)[W], u64 slot, bool& is_new) {
     is_new = false;
-    const u64 max_probe = t.nslots < 4096 ? t.nslots : 4096;
+    const u64 max_probe = t.nslots < KG_MAX_PROBE ? t.nslots : KG_MAX_PROBE;
     for (u64 probe = 0; probe < max_probe; probe++) {
         u64* p = t.slots + slot * t.stride;
-        u64 meta, k0;
-        kg_ld_v2(p, meta, k0);                 // one 16-byte access: meta and key word 0 together
+        u64 meta, k0 = 0;
+        bool k0_valid = false;
+        if (W == 1) { kg_ld_v2(p, meta, k0); k0_valid = true; }
+        else meta = kg_ld_acquire_u64(p);
         u32 m = (u32)meta;
-        bool k0_valid = true;                  // k0 was read in the same access that saw a published meta
         if (m == 0) {
-            u32 old = atomicCAS((u32*)p, 0u, KG_LOCKED);
+            const u32 old = atomicCAS((u32*)p, 0u, KG_LOCKED);
             if (old == 0) {
 #pragma unroll
                 for (int i = 0; i < W; i++) kg_st_u64(p + 1 + i, key[i]);
@@ -132,11 +152,10 @@ __device__ __forceinline__ u64 kg_table_add(const KgTable& t, const u64 (&key)[W
                 is_new = true;
                 return slot;
             }
-            m = old;
-            k0_valid = false;
+            m = KG_LOCKED;                     // somebody else owns or owned it: observe it again, with acquire
         }
         if (m == KG_LOCKED) {
-            do { m = kg_ld_u32(p); } while (m == KG_LOCKED);
+            do { m = kg_ld_acquire_u32(p); } while (m == KG_LOCKED);
             k0_valid = false;
         }
         // slot is published: compare
@@ -147,10 +166,11 @@ __device__ __forceinline__ u64 kg_table_add(const KgTable& t, const u64 (&key)[W
             for (int i = 1; i < W; i++) same = same && (kg_ld_u64(p + 1 + i) == key[i]);
         }
         if (same) {
-            atomicAdd((u32*)p, 1u);
+            if (m < 0xFFFFFFFFu - KG_COUNT_MARGIN) atomicAdd((u32*)p, 1u);      // saturates instead of reaching KG_LOCKED
             return slot;
         }
         slot = slot + 1 == t.nslots ? 0 : slot + 1;
+        if ((probe & 255u) == 255u && t.full_flag && kg_ld_u32(t.full_flag)) break;
     }
     return ~0ULL;
 }
@@ -175,13 +195,12 @@ __device__ __forceinline__ void kg_red_add_u64(u64* p, u64 v) {
     asm volatile("red.relaxed.gpu.global.add.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
 
-__device__ __forceinline__ u64 kg_table_add_packed(const KgTable& t, const u64 (&key)[2], u64 h, bool& is_new) {
-    u64 slot = kg_slot(h, t.nslots, t.world);
+__device__ __forceinline__ u64 kg_table_add_packed(const KgTable& t, const u64 (&key)[2], u64 slot, bool& is_new) {
     is_new = false;
     const u32 tb = t.packed_tb;
     const u64 keymask = (1ULL << tb) - 1, one = 1ULL << tb;
-    const u64 sat = ((~0ULL) >> tb) - 0x20000ULL;          // stop counting shortly before the field would wrap
-    const u64 max_probe = t.nslots < 4096 ? t.nslots : 4096;
+    const u64 sat = ((~0ULL) >> tb) - (u64)KG_COUNT_MARGIN;   // stop counting before the field could wrap into the key
+    const u64 max_probe = t.nslots < KG_MAX_PROBE ? t.nslots : KG_MAX_PROBE;
     for (u64 probe = 0; probe < max_probe; probe++) {
         u64* p = t.slots + slot * 2;
         u64 w0, w1;
@@ -195,15 +214,15 @@ __device__ __forceinline__ u64 kg_table_add_packed(const KgTable& t, const u64 (
             return slot;
         }
         slot = slot + 1 == t.nslots ? 0 : slot + 1;
+        if ((probe & 255u) == 255u && t.full_flag && kg_ld_u32(t.full_flag)) break;
     }
     return ~0ULL;
 }
 
-// read-only lookup (compaction / decode); returns slot or ~0
+// read-only lookup starting at `slot` (compaction / decode); returns slot or ~0
 template <int W>
-__device__ __forceinline__ u64 kg_table_find(const KgTable& t, const u64 (&key)[W], u64 h) {
-    u64 slot = kg_slot(h, t.nslots, t.world);
-    const u64 max_probe = t.nslots < 4096 ? t.nslots : 4096;
+__device__ __forceinline__ u64 kg_table_find(const KgTable& t, const u64 (&key)[W], u64 slot) {
+    const u64 max_probe = t.nslots < KG_MAX_PROBE ? t.nslots : KG_MAX_PROBE;
     for (u64 probe = 0; probe < max_probe; probe++) {
         const u64* p = t.slots + slot * t.stride;
         if ((u32)p[0] == 0) return ~0ULL;

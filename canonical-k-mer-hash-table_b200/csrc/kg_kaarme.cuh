@@ -16,7 +16,7 @@
 //   bit1 predecessor exists   bit0 occupied          (C = canonical string of the k-mer)
 // Indices are DENSE (rank among occupied table slots), so the array holds exactly one word per k-mer.
 #pragma once
-#include "kg_device.cuh"
+#include "kg_skm.cuh"
 
 struct KgKaarme {
     u64* slots;     // n_kmers words
@@ -120,12 +120,21 @@ __device__ __forceinline__ void kg_set_char(u64 (&key)[W], u32 k, u32 pos_from_l
     for (int i = 0; i < W; i++) if ((u32)i == word) key[i] |= (u64)c << sh;
 }
 
+// where a k-mer lives: owner shard and table partition follow from its minimizer bucket (kg_skm.cuh), the slot inside
+// the partition from its own hash.  nb == 1: one GPU, direct insert, the whole table is one partition.
+struct KgPlacement {
+    const u64* part_lo;   // [pl + 1]
+    u32 pl, nb, m, rank;
+};
+
 // ---- build: one thread per table slot ------------------------------------------------------------------------------
-// roots == nullptr: only count the roots (sizing pass).
+// roots == nullptr: only count the roots (sizing pass).  A predecessor that lives on ANOTHER shard (its minimizer
+// differs and hashes to a bucket of another owner: a few per cent of the k-mers) cannot be pointed at: the k-mer
+// becomes a root, so every shard's structure is self-contained and decodes on its own.
 template <int W>
 __global__ void __launch_bounds__(256) kg_kaarme_build(KgTable t, u32 k, const u32* __restrict__ bitmap,
                                                        const u64* __restrict__ word_prefix, KgKaarme out,
-                                                       u64* root_counter) {
+                                                       u64* root_counter, KgPlacement pm) {
     const u64 s = (u64)blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= t.nslots) return;
     const u64* p = t.slots + s * t.stride;
@@ -164,8 +173,14 @@ __global__ void __launch_bounds__(256) kg_kaarme_build(KgTable t, u32 k, const u
             u64 key[W];
 #pragma unroll
             for (int i = 0; i < W; i++) key[i] = pred_fwd ? P[i] : R[i];
-            pred_slot = kg_table_find<W>(t, key, kg_hash_key<W>(key));
-            if (pred_slot == ~0ULL) has_pred = false;   // predecessor was not admitted (Bloom) -> this k-mer is a root
+            const u32 bkt = pm.nb > 1 ? kg_key_bucket<W>(key, k, pm.m, pm.nb) : 0u;
+            if (bkt / pm.pl != (pm.nb > 1 ? pm.rank : 0u)) {
+                has_pred = false;                       // predecessor belongs to another shard -> root
+            } else {
+                const u64 lo = pm.part_lo[bkt % pm.pl], n_part = pm.part_lo[bkt % pm.pl + 1] - lo;
+                pred_slot = kg_table_find<W>(t, key, lo + __umul64hi(kg_hash_key<W>(key), n_part));
+                if (pred_slot == ~0ULL) has_pred = false;   // predecessor was not admitted (Bloom) -> this k-mer is a root
+            }
         }
     }
     u64 ptr;

@@ -410,14 +410,16 @@ __global__ void __launch_bounds__(KG_PT) kg_tile_pack(const uint8_t* __restrict_
 }
 
 // ---- carry: move the tail of the finished batch to the head of the next one -------------------------------
-// Keeps whole words: the carried region starts at word floor((T-(k-1))/32), so C = T - 32*that >= k-1
-// (or everything when T < k-1).  Runs AFTER the count kernel of the batch, single block.
+// Keeps whole words: the carried region starts at word floor((T-k)/32), so C = T - 32*that >= k (or everything when
+// T < k).  k bases, not k-1: the first window counted in the next batch then sees a run of k+1 whenever its read really
+// continues to the left, so "this window has a predecessor" (what the Kaarme structure records) does not depend on where
+// a batch happened to end.  Runs AFTER the count kernel of the batch, single block.
 __global__ void kg_carry_save(const u64* __restrict__ words, const u32* __restrict__ brk, KgStream* st,
                               u64* __restrict__ carry_words, u32* __restrict__ carry_brk, u32 k, u32 max_words) {
     const u32 T = st->total_bases;
-    u32 w0 = T >= (k - 1) ? (T - (k - 1)) >> 5 : 0;
+    u32 w0 = T >= k ? (T - k) >> 5 : 0;
     u32 nw = ((T + 31) >> 5) - w0;
-    if (nw > max_words) nw = max_words;  // cannot happen (max_words = W+2)
+    if (nw > max_words) nw = max_words;  // cannot happen (max_words = W+3)
     for (u32 i = threadIdx.x; i < max_words; i += blockDim.x) {
         carry_words[i] = i < nw ? words[w0 + i] : 0;
         carry_brk[i] = i < nw ? brk[w0 + i] : 0;

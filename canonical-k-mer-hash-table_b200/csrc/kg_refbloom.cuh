@@ -128,8 +128,9 @@ __global__ void __launch_bounds__(256) kg_refbloom_count(KgCountArgs a, KgRefBlo
             if (!kg_rb_admits(rb, pos)) { n_rej++; return; }
             bool is_new;
             u64 slot;
-            if constexpr (W == 2) slot = table.packed_tb ? kg_table_add_packed(table, key, h, is_new) : kg_table_add<W>(table, key, h, is_new);
-            else slot = kg_table_add<W>(table, key, h, is_new);
+            const u64 slot0 = kg_slot(h, table.nslots, table.world);
+            if constexpr (W == 2) slot = table.packed_tb ? kg_table_add_packed(table, key, slot0, is_new) : kg_table_add<W>(table, key, slot0, is_new);
+            else slot = kg_table_add<W>(table, key, slot0, is_new);
             if (slot == ~0ULL) { full = true; return; }
             n_ins++;
             n_new += is_new ? 1u : 0u;

@@ -7,7 +7,7 @@
 //     -m,--hash-table-type {0,2}   -a,--min-k-abu N   -t,--threads N   -o,--output-file PATH
 //     -b,--use-bfilter  -f,--bfilter-fpr F   exactly one of  -s,--hash-tab-size N | -u,--unq-kmers N
 //   GPU-side extras (do not collide with the reference's flags):
-//     --device N   --gpus N   --peer-exchange   --batch-mb N   --exact-counts   --stats-json PATH   --host-format
+//     --device N   --gpus N   --batch-mb N   --exact-counts   --stats-json PATH   --host-format
 //     --dump-kaarme PATH   (-m 2: save the compact structure)      --from-kaarme   (INPUT is such a file: decode it)
 //
 // Exit codes follow the reference: 0 ok; CLI11's 105 (validation), 106 (required), 107 (requires),
@@ -58,7 +58,6 @@ struct Args {
     bool host_format = false;     // --host-format: export (key, count) records and format the lines on host threads
     std::string dump_kaarme;      // --dump-kaarme PATH: write the compact structure (-m 2, one GPU) as a binary file
     bool reference_bloom = false; // --reference-bloom: -b builds the reference's own filter bit for bit (experimental)
-    bool peer_exchange = false;   // --peer-exchange: with --gpus N, scatter kernels store straight into the owners' buffers
     bool from_kaarme = false;     // --from-kaarme: INPUT is a file written by --dump-kaarme; decode it on the GPU
 };
 
@@ -83,8 +82,6 @@ void print_help(const char* argv0) {
                  "  -f,--bfilter-fpr FLOAT     Bloom filter false positive rate (def. 0.01)\n"
                  "  --device INT               CUDA device ordinal (def. 0; with --gpus N the first of N consecutive devices)\n"
                  "  --gpus INT                 Hash-shard the k-mers over N GPUs of this box (NCCL exchange; def. 1)\n"
-                 "  --peer-exchange            With --gpus N: fused bucket -> peer-store exchange over NVLink instead of\n"
-                 "                             ncclSend/ncclRecv (experimental)\n"
                  "  --reference-bloom          With -b on one GPU: reproduce the reference's double Bloom filter bit for bit\n"
                  "                             (its hash functions, counters, table size, false positives; experimental)\n"
                  "  --batch-mb UINT            Raw bytes per device batch in MiB (def. 128)\n"
@@ -189,7 +186,6 @@ Args parse_args(int argc, char** argv) {
         else if (s == "--print-slices") a.print_slices = true;
         else if (s == "--host-format") a.host_format = true;
         else if (s == "--from-kaarme") a.from_kaarme = true;
-        else if (s == "--peer-exchange") a.peer_exchange = true;
         else if (s == "--reference-bloom") a.reference_bloom = true;
         else if (s == "--dump-kaarme") a.dump_kaarme = value("--dump-kaarme");
         else if (s == "--stats-json") a.stats_json = value("--stats-json");
@@ -255,7 +251,18 @@ Format file_format(const std::string& path) {
 // [lo, hi) must also see the k-1 bases before lo (fed with KG_FEED_CONTEXT, not counted) and must know whether its
 // first byte lies inside a FASTA header.
 struct Slice { off_t ctx_lo, lo, hi; bool in_header; };
+// pread that loops over short reads; any failure is fatal (a slice computed from a partial read would silently drop the
+// k-mers that straddle a rank boundary, or misparse a slice that starts inside a header)
+static void pread_exact(int fd, char* dst, size_t n, off_t at) {
+    size_t got = 0;
+    while (got < n) {
+        const ssize_t r = pread(fd, dst + got, n - got, at + (off_t)got);
+        if (r <= 0) { std::cerr << "kaarme: IO error while reading the input file\n"; std::_Exit(1); }
+        got += (size_t)r;
+    }
+}
 Slice make_slice(int fd, off_t file_size, int rank, int world, uint32_t k, bool fasta) {
+    if (fd < 0) { std::cerr << "kaarme: cannot open the input file\n"; std::_Exit(1); }
     Slice s;
     s.lo = file_size * rank / world;
     s.hi = file_size * (rank + 1) / world;
@@ -265,7 +272,7 @@ Slice make_slice(int fd, off_t file_size, int rank, int world, uint32_t k, bool 
     std::vector<char> buf(1 << 16);
     while (i > 0 && need > 0) {
         off_t n = std::min<off_t>((off_t)buf.size(), i);
-        if (pread(fd, buf.data(), (size_t)n, i - n) != n) break;
+        pread_exact(fd, buf.data(), (size_t)n, i - n);
         for (off_t j = n - 1; j >= 0 && need > 0; j--) { i--; if (buf[j] != '\n') need--; }
     }
     s.ctx_lo = i;
@@ -274,7 +281,7 @@ Slice make_slice(int fd, off_t file_size, int rank, int world, uint32_t k, bool 
         bool decided = false;
         while (j > 0 && !decided) {
             off_t n = std::min<off_t>((off_t)buf.size(), j);
-            if (pread(fd, buf.data(), (size_t)n, j - n) != n) break;
+            pread_exact(fd, buf.data(), (size_t)n, j - n);
             for (off_t q = n - 1; q >= 0; q--) {
                 if (buf[q] == '\n') { decided = true; break; }
                 if (buf[q] == '>') { s.in_header = true; decided = true; break; }
@@ -582,7 +589,6 @@ int main(int argc, char** argv) {
     const int io_threads = std::max(1, std::min(8, (args.threads - 2) / world));
     const int nbufs = 3;
     Barrier barrier(world);
-    std::vector<char> peer_handles((size_t)world * KG_PEER_HANDLE_BYTES);
     std::chrono::high_resolution_clock::time_point t_bloom0, t_bloom1, t_build0, t_build1, t_write1;
 
     // one host thread per GPU: its own context (= hash shard), its own byte range of the input
@@ -612,11 +618,6 @@ int main(int argc, char** argv) {
             }
         }
         if (world > 1) KG_CHECK(kg_comm_init(ctx, nccl_id, rank, world));
-        if (world > 1 && args.peer_exchange) {   // every rank publishes its receive buffers, then maps everybody's
-            KG_CHECK(kg_peer_export(ctx, peer_handles.data() + (size_t)rank * KG_PEER_HANDLE_BYTES));
-            barrier.wait();
-            KG_CHECK(kg_peer_connect(ctx, peer_handles.data(), world));
-        }
         uint8_t* bufs[nbufs] = {nullptr, nullptr, nullptr};
         for (int i = 0; i < nbufs; i++) KG_CHECK(kg_host_alloc(buf_bytes, (void**)&bufs[i]));
         int fd = open(args.input.c_str(), O_RDONLY);
@@ -647,7 +648,8 @@ int main(int argc, char** argv) {
         }
         feed_file(ctx, args.input, fmt.gz, bufs, nbufs, buf_bytes, sl, io_threads);
         KG_CHECK(kg_pass_end(ctx, &count_stats[rank]));
-        if (args.mode == KG_TABLE_KAARME && world == 1) {
+        barrier.wait();                            // every shard's table is complete
+        if (args.mode == KG_TABLE_KAARME) {        // every shard builds its own self-contained structure
             KG_CHECK(kg_compact(ctx, &compact_stats[rank]));
             if (!args.dump_kaarme.empty()) {
                 const kg_compact_stats& cs = compact_stats[rank];
@@ -714,16 +716,23 @@ int main(int argc, char** argv) {
     if (world > 1) std::cout << "Hash table size is: " << slots_sum << " (" << world << " shards)\n";
     std::cout << "Time used to build hash table: " << std::chrono::duration_cast<us>(t_build1 - t_build0).count() << " microseconds\n";
     std::cout << "Time used to write k-mers in a file: " << std::chrono::duration_cast<us>(t_write1 - t_build1).count() << " microseconds\n";
-    const kg_compact_stats& cs = compact_stats[0];
+    kg_compact_stats cs = compact_stats[0];
+    for (int r = 1; r < world; r++) {
+        cs.kmers += compact_stats[r].kmers; cs.roots += compact_stats[r].roots; cs.bytes += compact_stats[r].bytes;
+        cs.reference_bytes += compact_stats[r].reference_bytes;
+        cs.max_chain = std::max(cs.max_chain, compact_stats[r].max_chain);
+    }
     if (args.mode == KG_TABLE_KAARME) {
         std::cout << "Written k-mers: " << w.written << "\n";                         // kmer_hash_table.cpp:4522-4523
         std::cout << "Skipped k-mers: " << (csum.distinct - w.written) << "\n";
         std::cout << "Main array slots used " << csum.distinct << " / " << csum.table_slots << "\n";  // parallel_parser.hpp:1560-1561
-        if (world == 1) {
-            std::cout << "Max secondary array slots used " << cs.roots << "\n";
-            std::cout << "Kaarme bytes: " << cs.bytes << " (" << (cs.kmers ? (double)cs.bytes / cs.kmers : 0.0)
-                      << " B/k-mer; reference layout would hold " << cs.reference_bytes << " B)\n";
-        }
+        std::cout << "Max secondary array slots used " << cs.roots << "\n";
+        std::cout << "Kaarme bytes: " << cs.bytes << " (" << (cs.kmers ? (double)cs.bytes / cs.kmers : 0.0)
+                  << " B/k-mer; reference layout would hold " << cs.reference_bytes << " B)\n";
+        if (world > 1)
+            for (int r = 0; r < world; r++)
+                std::cout << "  shard " << r << ": " << compact_stats[r].kmers << " k-mers, " << compact_stats[r].roots << " roots, "
+                          << (compact_stats[r].kmers ? (double)compact_stats[r].bytes / compact_stats[r].kmers : 0.0) << " B/k-mer\n";
     }
     const double dev_ms = csum.device_ms + bsum.device_ms;
     std::cout << "GPU x" << world << ": input k-mers " << csum.input_kmers << ", distinct " << csum.distinct << ", device time " << dev_ms

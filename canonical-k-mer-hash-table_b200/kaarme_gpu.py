@@ -12,7 +12,7 @@ import numpy as np
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libkaarme_gpu.so")
 
-ABI_VERSION = 1
+ABI_VERSION = 2
 INPUT_FASTA, INPUT_PLAIN = 0, 2
 TABLE_PLAIN, TABLE_KAARME = 0, 2
 PASS_BLOOM, PASS_COUNT = 1, 2
@@ -69,8 +69,7 @@ EXPORTS = ["kg_abi_version", "kg_strerror", "kg_last_error", "kg_device_count", 
            "kg_host_alloc", "kg_host_free", "kg_comm_unique_id", "kg_comm_init", "kg_pass_begin",
            "kg_stream_begin", "kg_feed", "kg_feed_device", "kg_pass_end", "kg_compact", "kg_export",
            "kg_table_info", "kg_atomic_ceiling", "kg_launch_count", "kg_kaarme_download", "kg_export_text",
-           "kg_kaarme_upload", "kg_peer_export", "kg_peer_connect", "kg_peer_stats"]
-PEER_HANDLE_BYTES = 256
+           "kg_kaarme_upload"]
 
 _lib = None
 
@@ -106,9 +105,6 @@ def lib():
         L.kg_kaarme_download.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
         L.kg_export_text.argtypes = [C.c_void_p, C.c_uint64, C.c_int, TEXT_SINK_FN, C.c_void_p]
         L.kg_kaarme_upload.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64]
-        L.kg_peer_export.argtypes = [C.c_void_p, C.c_void_p]
-        L.kg_peer_connect.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
-        L.kg_peer_stats.argtypes = [C.c_void_p, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
         _lib = L
     return _lib
 
@@ -193,26 +189,6 @@ class Counter:
     def comm_init(self, unique_id: bytes, rank: int, world: int):
         buf = C.create_string_buffer(unique_id, 256)
         self._check(lib().kg_comm_init(self._h, buf, rank, world), "kg_comm_init")
-
-    def peer_export(self) -> bytes:
-        """After comm_init: describe this rank's receive buffers (256 bytes; gather them from every rank in rank order,
-        e.g. torch.distributed.all_gather_object) for peer_connect."""
-        buf = C.create_string_buffer(PEER_HANDLE_BYTES)
-        self._check(lib().kg_peer_export(self._h, buf), "kg_peer_export")
-        return buf.raw
-
-    def peer_connect(self, handles):
-        """Map every rank's receive buffers: from here on the bucketing kernel stores its key runs straight into the
-        owners' buffers over NVLink (fused bucket -> peer-store exchange) instead of ncclSend/ncclRecv."""
-        blob = b"".join(handles)
-        assert len(blob) == PEER_HANDLE_BYTES * self.cfg.world
-        buf = C.create_string_buffer(blob, len(blob))
-        self._check(lib().kg_peer_connect(self._h, buf, self.cfg.world), "kg_peer_connect")
-
-    def peer_stats(self) -> dict:
-        a, b = C.c_uint64(), C.c_uint64()
-        lib().kg_peer_stats(self._h, C.byref(a), C.byref(b))
-        return {"peer_rounds": a.value, "fallback_rounds": b.value}
 
     def pass_begin(self, which):
         self._check(lib().kg_pass_begin(self._h, which), "kg_pass_begin")

@@ -34,7 +34,7 @@
 extern "C" {
 #endif
 
-#define KG_ABI_VERSION 1
+#define KG_ABI_VERSION 2
 
 typedef enum kg_status {
     KG_OK = 0,
@@ -80,15 +80,16 @@ typedef struct kg_config {
     uint64_t batch_bytes;     /* raw bytes per device batch; 0 = default (128 MiB)                  */
     int32_t rank;             /* hash-sharded multi-GPU: this context's shard                       */
     int32_t world;            /* number of shards (1 = single GPU)                                  */
-    uint32_t partitions;      /* L2-blocked insert: every batch is bucketed by hash into this many contiguous
-                                 regions of the shard's table / filter before inserting.  0 = choose per pass
-                                 (~24 MiB regions; direct insert when the structure is small), 1 = always
-                                 insert directly, > 1 = as given (world * partitions <= 1024)              */
+    uint32_t partitions;      /* L2-blocked insert: the windows of every batch are bucketed by the hash of their
+                                 minimizer into this many contiguous regions of the shard's table / filter before
+                                 inserting.  0 = choose per pass (~24 MiB regions; direct insert when the structure
+                                 is small), 1 = always insert directly (one GPU), > 1 = as given
+                                 (world * partitions <= 1024)                                                 */
     uint32_t reserved;        /* flags: KG_CFG_* below (0 = the defaults)                                              */
 } kg_config;
 
 /* kg_config.reserved flags */
-#define KG_CFG_REFERENCE_BLOOM 1u /* EXPERIMENTAL (not yet validated on hardware): -b reproduces the reference's double
+#define KG_CFG_REFERENCE_BLOOM 1u /* -b reproduces the reference's double
                                      Bloom filter bit for bit as ONE worker thread builds it -- same hash functions
                                      (base-5 rolling hash mod 2^54, XXH64 with the reference's seeds), same
                                      new_in_first / new_in_second, same table size, same false positives at -a 1 --
@@ -110,8 +111,8 @@ typedef struct kg_pass_stats {
     double device_ms;        /* CUDA-event time, first kernel of the pass to the last               */
     double parse_ms, count_ms, exchange_ms; /* per-stage CUDA-event sums (0 when not measured)      */
     double insert_ms;        /* CUDA-event time of the table/filter-updating kernel alone (kg_count_kernel on
-                                the direct path, kg_insert_keys/segs_kernel on the bucketed path), summed over
-                                its launches; count_ms additionally holds the bucketing kernels         */
+                                the direct path, kg_skm_insert on the bucketed path), summed over
+                                its launches; count_ms additionally holds the bucketing kernel          */
     uint64_t insert_launches;/* launches of that kernel in the pass                                         */
 } kg_pass_stats;
 
@@ -150,23 +151,16 @@ int kg_destroy(kg_ctx* ctx);
 int kg_host_alloc(size_t bytes, void** out);
 int kg_host_free(void* p);
 
-/* ---- multi-GPU (one context per GPU; shards own disjoint hash ranges) --------------------------- */
-#define KG_UNIQUE_ID_BYTES 256 /* two NCCL unique ids: key transfers and the control all-gather */
+/* ---- multi-GPU (one context per GPU; every shard owns a disjoint set of minimizer buckets) ----- */
+/* The reference is one process on one table (main.cpp:442-536); sharding has no counterpart there.  Canonical k-mers
+ * are owned by the hash of their minimizer; every GPU parses its own slice of the input and turns it into 8-byte run
+ * descriptors per owner.  kg_comm_init (collective) creates the NCCL communicator -- it carries one word per round --
+ * and maps every rank's two batch slots into every rank (CUDA IPC between processes, peer access between the contexts
+ * of one process): the packed 2-bit reads then travel by copy-engine pulls over NVLink and the insert kernels read the
+ * peers' descriptors in place.  All ranks must use the same k and batch_bytes.                                   */
+#define KG_UNIQUE_ID_BYTES 256
 int kg_comm_unique_id(void* id_out);                                   /* rank 0, then broadcast    */
 int kg_comm_init(kg_ctx* ctx, const void* id, int rank, int world);    /* collective                */
-
-/* Optional, after kg_comm_init: the fused bucket -> peer-store exchange.  Every rank describes its two receive buffers
- * (kg_peer_export: KG_PEER_HANDLE_BYTES bytes; CUDA IPC handles between processes, plain peer pointers between the
- * contexts of one process), the caller gathers the `world` handles in rank order by any means, and every rank maps
- * them (kg_peer_connect).  From then on the bucketing kernel of a batch stores its key runs STRAIGHT into the owners'
- * receive buffers over NVLink -- no send buffer, no ncclSend/ncclRecv copy kernels, each key crosses HBM once less --
- * and NCCL only carries the per-round count all-gather and a one-word "all stores have landed" collective.  A round
- * whose busiest owner would overflow its receive buffer falls back to the ncclSend/ncclRecv path (kg_peer_stats).
- * Without these calls the exchange is the ncclSend/ncclRecv path.                                                 */
-#define KG_PEER_HANDLE_BYTES 256
-int kg_peer_export(kg_ctx* ctx, void* handle_out);
-int kg_peer_connect(kg_ctx* ctx, const void* handles /* world * KG_PEER_HANDLE_BYTES, rank order */, int world);
-int kg_peer_stats(const kg_ctx* ctx, uint64_t* peer_rounds, uint64_t* fallback_rounds);
 
 /* ---- passes ------------------------------------------------------------------------------------ */
 /* KG_PASS_BLOOM: clears the filters.  KG_PASS_COUNT: allocates and clears the table with
@@ -185,7 +179,9 @@ int kg_feed_device(kg_ctx* ctx, const void* device_bytes, size_t n, uint32_t fla
 int kg_pass_end(kg_ctx* ctx, kg_pass_stats* stats);
 
 /* ---- after the count pass ---------------------------------------------------------------------- */
-/* -m 2: build the Kaarme representation (8-byte slot per k-mer + roots) from the counted table.     */
+/* -m 2: build the Kaarme representation (8-byte slot per k-mer + roots) from the counted table.  With several
+ * GPUs every shard builds its own self-contained structure: a k-mer whose predecessor is owned by another shard
+ * becomes a root.                                                                                   */
 int kg_compact(kg_ctx* ctx, kg_compact_stats* stats);
 /* Stream every k-mer whose reported count >= min_abundance to the sink (min_abundance 0 => nothing,
  * parallel_parser.hpp:860-861).  In KG_TABLE_KAARME mode after kg_compact the k-mers are DECODED from

@@ -56,7 +56,6 @@ struct kg_ctx {
     uint64_t table_slots = 0, distinct_local = 0;
     std::vector<uint64_t> kslots, kroots;   // Kaarme structure
     uint64_t launches = 0;
-    bool peer_exported = false, peer_connected = false;
     std::string err;
 };
 
@@ -108,25 +107,6 @@ int kg_comm_init(kg_ctx* c, const void* id, int rank, int world) {
     return KG_OK;
 }
 
-// peer exchange: the mock has one shared map, so there is nothing to connect; the calls only check their protocol
-int kg_peer_export(kg_ctx* c, void* out) {
-    if (!c || !out || c->cfg.world < 2 || c->pass) return KG_EBADARG;
-    memset(out, 0, KG_PEER_HANDLE_BYTES);
-    memcpy(out, &c->cfg.rank, sizeof(int32_t));
-    c->peer_exported = true;
-    return KG_OK;
-}
-int kg_peer_connect(kg_ctx* c, const void* handles, int world) {
-    if (!c || !handles || world != c->cfg.world || !c->peer_exported || c->peer_connected) return KG_EBADARG;
-    for (int r = 0; r < world; r++) {
-        int32_t who;
-        memcpy(&who, (const char*)handles + (size_t)r * KG_PEER_HANDLE_BYTES, sizeof(who));
-        if (who != r) { c->err = "mock: handles are not in rank order (or a rank had not exported yet)"; return KG_EBADARG; }
-    }
-    c->peer_connected = true;
-    return KG_OK;
-}
-int kg_peer_stats(const kg_ctx* c, uint64_t* a, uint64_t* b) { if (!c) return KG_EBADARG; if (a) *a = 0; if (b) *b = 0; return KG_OK; }
 
 int kg_pass_begin(kg_ctx* c, int pass) {
     if (!c || (pass != KG_PASS_BLOOM && pass != KG_PASS_COUNT)) return KG_EBADARG;
@@ -228,7 +208,7 @@ static std::vector<std::pair<Key, uint64_t>> owned(kg_ctx* c) {
 }
 
 int kg_compact(kg_ctx* c, kg_compact_stats* st) {
-    if (!c || c->cfg.table_mode != KG_TABLE_KAARME || c->cfg.world > 1 || !c->counted) return KG_EBADARG;
+    if (!c || c->cfg.table_mode != KG_TABLE_KAARME || !c->counted) return KG_EBADARG;
     if (!c->compacted) {
         const auto v = owned(c);
         const uint32_t k = c->cfg.k;

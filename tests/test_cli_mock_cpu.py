@@ -202,14 +202,15 @@ def test_cli_reference_bloom_flag_reaches_the_config(exe, tmp_path):
 
 
 @pytest.mark.parametrize("gpus", [2, 4])
-def test_cli_peer_exchange_handshake(exe, gpus, tmp_path):
-    """--peer-exchange: every rank exports its handle, all wait, every rank connects with the handles in rank order
-    (the mock rejects a connect that sees a missing or misplaced handle); the output is unchanged"""
-    case = [c for c in CASES if c["input"] == "g5_long.fasta" and c["k"] == 51 and c["mode"] == 0 and c["a"] == 2][0]
+def test_cli_kaarme_mode_on_several_shards(exe, gpus, tmp_path):
+    """--gpus N -m 2: every shard compacts its own structure and the output is decoded from them (the reference's
+    default table mode, main.cpp:137, on the sharded path); per-shard bytes per k-mer are reported"""
+    case = [c for c in CASES if c["input"] == "g2_reads.fa" and c["k"] == 51 and c["mode"] == 2 and c["a"] == 2 and not c["unique"]][0]
     out = tmp_path / "out.txt"
-    p = run(exe, [os.path.join(GOLDEN, "g5_long.fasta"), 51, "-m", 0, "-a", 2, "-t", 6, "-o", out, "--gpus", gpus, "--peer-exchange"] + size_args(case))
+    p = run(exe, [os.path.join(GOLDEN, "g2_reads.fa"), 51, "-m", 2, "-a", 2, "-t", 6, "-o", out, "--gpus", gpus] + size_args(case))
     assert p.returncode == 0, p.stderr
     assert sorted_sha(out) == (case["n_lines"], case["sha256"])
+    assert p.stdout.count("  shard ") == gpus and "Kaarme bytes:" in p.stdout
 
 
 def test_cli_gzip_input(exe, oracle, big_fasta, tmp_path):

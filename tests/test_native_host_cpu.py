@@ -27,7 +27,9 @@ def _build(name, cmd):
     srcs = [a for a in cmd if a.endswith((".cu", ".cpp"))]
     deps = srcs + [os.path.join(ROOT, "canonical-k-mer-hash-table_b200", "csrc", "kg_text.cuh"),
                    os.path.join(ROOT, "canonical-k-mer-hash-table_b200", "csrc", "kg_refhash.cuh"),
-                   os.path.join(ROOT, "canonical-k-mer-hash-table_b200", "csrc", "kg_exchange_plan.hpp"),
+                   os.path.join(ROOT, "canonical-k-mer-hash-table_b200", "csrc", "kg_skm.cuh"),
+                   os.path.join(ROOT, "canonical-k-mer-hash-table_b200", "csrc", "kg_count.cuh"),
+                   os.path.join(ROOT, "canonical-k-mer-hash-table_b200", "csrc", "kg_device.cuh"),
                    os.path.join(ROOT, "canonical-k-mer-hash-table_b200", "host", "kg_reader.hpp"),
                    os.path.join(ROOT, "canonical-k-mer-hash-table_b200", "host", "kg_writer.hpp")]
     if not os.path.exists(exe) or any(os.path.getmtime(d) > os.path.getmtime(exe) for d in deps):
@@ -187,46 +189,53 @@ def test_writer_reports_errors(writer_exe, tmp_path):
 
 
 @pytest.fixture(scope="module")
-def plan_exe():
-    return _build("exchange_plan_host", ["g++", "-O2", "-std=c++17", "-Wall", os.path.join(NATIVE, "exchange_plan_host.cpp")])
+def skm_exe():
+    nvcc = "/usr/local/cuda/bin/nvcc" if os.path.exists("/usr/local/cuda/bin/nvcc") else "nvcc"
+    return _build("skm_host", [nvcc, "-O2", "-std=c++17", "-Wno-deprecated-gpu-targets", os.path.join(NATIVE, "skm_host.cu")])
 
 
-@pytest.mark.parametrize("world,pl,seed", [(2, 1, 0), (2, 4, 1), (3, 5, 2), (8, 32, 3), (8, 128, 4), (5, 1, 5), (64, 16, 6)])
-def test_peer_exchange_plan_tiles_every_receive_buffer(plan_exe, world, pl, seed):
-    """csrc/kg_exchange_plan.hpp: simulate the fused bucket -> peer-store exchange on the CPU.  Every sender writes its
-    run for every bucket at remote_base[b] in the owner's buffer; the runs must tile [0, in_keys[d]) without gap or
-    overlap, partition-major with senders in rank order (what the L2-blocked insert walks front to back)"""
-    rng = np.random.default_rng(seed)
-    nb = world * pl
-    M = rng.integers(0, 50, size=(world, nb + 1)).astype(np.uint32)
-    M[rng.random((world, nb + 1)) < 0.3] = 0                      # empty runs are common
-    M[:, nb] = (rng.random(world) < 0.5).astype(np.uint32)        # done flags
-    if seed == 5:
-        M[:, nb] = 1
-    p = subprocess.run([plan_exe], input=struct.pack("<II", world, pl) + M.tobytes(), stdout=subprocess.PIPE, check=True)
-    rows = p.stdout.decode().strip().splitlines()
-    assert len(rows) == world
-    buffers = [dict() for _ in range(world)]                      # owner -> {key index: (partition, sender)}
-    in_keys = None
-    for r, line in enumerate(rows):
-        head, ins, bases = [x.split() for x in line.split("|")]
-        rank, my_in, max_in, all_done = map(int, head)
-        ins, bases = list(map(int, ins)), list(map(int, bases))
-        assert rank == r and len(bases) == nb
-        want_in = [int(M[:, d * pl:(d + 1) * pl].sum()) for d in range(world)]
-        assert ins == want_in and my_in == want_in[r] and max_in == max(want_in)
-        assert all_done == int(all(M[:, nb] != 0))
-        in_keys = ins
-        for b in range(nb):
-            d, part = divmod(b, pl)
-            for j in range(int(M[r, b])):
-                idx = bases[b] + j
-                assert idx not in buffers[d], "two runs overlap"
-                buffers[d][idx] = (part, r)
-    for d in range(world):
-        assert sorted(buffers[d]) == list(range(in_keys[d])), "the runs must tile the buffer"
-        order = [buffers[d][i] for i in range(in_keys[d])]
-        assert order == sorted(order), "partition-major, senders in rank order"
+def _skm_input(k, nb, pl, carry, runs):
+    blob = struct.pack("<IIIII", k, nb, pl, carry, len(runs))
+    for r in runs:
+        blob += struct.pack("<I", len(r)) + bytes(r)
+    return blob
+
+
+@pytest.mark.parametrize("k", [1, 5, 11, 12, 21, 26, 27, 31, 32, 33, 37, 51, 64, 65, 96, 127, 128, 200, 255, 256])
+def test_skm_scatter_logic_matches_definition(skm_exe, k):
+    """csrc/kg_skm.cuh on the CPU: the scatter's two phases (m-mer hashes per packed word with halo, sliding minimum,
+    run segmentation) driven block by block exactly as kg_skm_scatter drives them.  Every valid window must be covered by
+    exactly one descriptor, never across a packed word, with the bucket the DEFINITION gives (minimum over the window's
+    canonical m-mer hashes, brute force), the right has-predecessor flag, and kg_window_at / kg_key_bucket must agree
+    with keys packed straight from the bases (forward and reverse complement give the same bucket)."""
+    rng = np.random.default_rng(1000 + k)
+    runs = []
+    for i in range(40):
+        n = int(rng.integers(1, 3 * k + 700)) if i % 3 else int(rng.integers(1, k + 2))
+        r = rng.integers(0, 4, n).astype(np.uint8)
+        if i % 7 == 0:
+            r[:] = r[0]                                            # homopolymer: every window shares one minimizer
+        if i % 11 == 0 and n > 8:
+            r[:] = np.resize(r[:2], n)                             # dinucleotide repeat
+        runs.append(r)
+    runs.append(rng.integers(0, 4, 6000).astype(np.uint8))         # crosses a 128-word block boundary
+    for nb, pl, carry in ((1, 1, 0), (256, 256, 0), (1024, 128, k + 13), (64, 8, 0), (7, 7, 3)):
+        p = subprocess.run([skm_exe], input=_skm_input(k, nb, pl, carry, runs), stdout=subprocess.PIPE, check=True)
+        out = p.stdout.decode().strip()
+        assert out.startswith("OK"), (k, nb, pl, carry, out)
+
+
+def test_skm_buckets_balance_on_random_sequence(skm_exe):
+    """a random genome spreads evenly over the minimizer buckets (no bucket above 2x its share at 64 buckets) and the
+    descriptors are few: ~11 windows each at k = 51"""
+    rng = np.random.default_rng(7)
+    runs = [rng.integers(0, 4, 10000).astype(np.uint8) for _ in range(60)]
+    p = subprocess.run([skm_exe], input=_skm_input(51, 64, 8, 0, runs), stdout=subprocess.PIPE, check=True)
+    out = p.stdout.decode().strip()
+    assert out.startswith("OK"), out
+    f = dict(x.split("=") for x in out.split()[1:])
+    assert float(f["max_bucket_share"]) < 2.0 / 64
+    assert int(f["windows"]) / int(f["descriptors"]) > 8
 
 
 @pytest.fixture(scope="module")
