@@ -92,19 +92,40 @@ class ClockSampler:
 
 
 # ---- CPU reference leg -----------------------------------------------------------------------------------------
-def cpu_reference_run(sample_path, k, slots, threads, timeout=1500):
-    """Time the reference's own CPU implementation (oracle/_ref/kaarme) on a sample file; returns seconds
-    ('Time used to build hash table', parallel_parser.hpp:865-867: file read + count, no writing)."""
+# The reference's own counter (the unmodified binary oracle/_ref/kaarme) on this box's host cores, on a sample of the
+# SAME workload: REF_FRACTION of the genome at the same coverage (so every k-mer is seen as often as in the full job and
+# the table is hit/missed in the same proportion), table -s scaled alike.  The timed quantity is its own "Time used to
+# build hash table" (parallel_parser.hpp:865-867: read + count).  Runs pass -a 65535 so that the untimed single-threaded
+# writer emits nothing; the file_to_file leg runs once more with -a 2 and takes the wall clock.
+REF_FRACTION = 0.1
+
+
+def workload_string(c, k, scale, world, bloom=False, fpr=0.01):
+    G = int(c["G"] * scale * world)
+    tail = f"-b -u {G} -f {fpr}" if bloom else f"-s {int(c['slots'] * scale) * world}"
+    return f"{c['name']}: {G} bp genome, {c['cov']}x of {c['L']} bp reads, k={k}, -m 0 {tail}"
+
+
+def cpu_reference_run(sample_path, k, slots, threads, write=False, timeout=1500):
+    """-> dict(build_s, write_s, wall_s, out_bytes) of one run of oracle/_ref/kaarme on a file"""
     import oracle.oracle_py as o  # the one place bench.py executes oracle/: as the baseline being measured
     out = sample_path + ".out"
-    cmd = [o.REF_BIN, sample_path, str(k), "-m", "0", "-s", str(slots), "-a", "2", "-t", str(threads), "-o", out]
+    cmd = [o.REF_BIN, sample_path, str(k), "-m", "0", "-s", str(slots), "-a", "2" if write else "65535", "-t", str(threads), "-o", out]
+    t0 = time.perf_counter()
     p = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, timeout=timeout, text=True)
+    wall = time.perf_counter() - t0
+    nbytes = os.path.getsize(out) if os.path.exists(out) else 0
     if os.path.exists(out):
         os.remove(out)
+    r = {"wall_s": wall, "out_bytes": nbytes}
     for line in p.stdout.splitlines():
         if line.startswith("Time used to build hash table:"):
-            return int(line.split()[-2]) * 1e-6
-    raise RuntimeError("reference run failed: " + p.stdout[-500:])
+            r["build_s"] = int(line.split()[-2]) * 1e-6
+        if line.startswith("Time used to write k-mers in a file:"):
+            r["write_s"] = int(line.split()[-2]) * 1e-6
+    if "build_s" not in r:
+        raise RuntimeError("reference run failed: " + p.stdout[-500:])
+    return r
 
 
 def cpu_port_run(sample_bytes, k):
@@ -114,35 +135,54 @@ def cpu_port_run(sample_bytes, k):
     return time.perf_counter() - t0, c.total_windows
 
 
-def make_sample(meta, fasta_cuda, max_bytes):
-    """First whole records of the workload, at most max_bytes -> (bytes, n_reads, input_kmers)."""
-    rec = meta["record_bytes"]
-    n = max(1, min(meta["n_reads"], max_bytes // rec))
-    data = fasta_cuda[: n * rec].cpu().numpy().tobytes()
-    return data, n, n * (meta["L"] - meta["k"] + 1)
+def reference_sample(workload, k, scale, torch, bench_data, dev):
+    """the sample every reference step counts: REF_FRACTION of the workload, same coverage -> (path, meta)"""
+    fasta, meta = bench_data.make_config(workload, dev, scale=scale * REF_FRACTION)
+    path = f"/dev/shm/kaarme_bench_ref_{os.getpid()}.fasta"
+    with open(path, "wb") as f:
+        f.write(fasta.cpu().numpy().tobytes())
+    meta["input_kmers"] = meta["n_reads"] * (meta["L"] - k + 1)
+    meta["path_bytes"] = int(fasta.numel())
+    del fasta
+    return path, meta
 
 
-def cpu_baseline(meta, fasta_cuda, k, target_seconds=20.0):
+def sample_string(meta, k):
+    return (f"{REF_FRACTION:g} of the workload at the same coverage: {meta['G']} bp genome, {meta['cov']}x of {meta['L']} bp reads "
+            f"({meta['n_reads']} reads, {meta['path_bytes']} bytes, {meta['input_kmers']} input k-mers), -m 0 -s {meta['slots']}")
+
+
+def cpu_baseline(workload, k, scale, torch, bench_data, dev):
     import oracle.oracle_py as o
     cores = os.cpu_count() or 1
     if o.have_ref():
         threads = max(3, min(64, cores))
-        # one 10 MiB chunk per worker is the reference's only parallelism (parallel_parser.hpp:834-843)
-        data, n, kmers = make_sample(meta, fasta_cuda, (threads - 2) * (10 << 20))
-        path = f"/dev/shm/kaarme_bench_sample_{os.getpid()}.fasta"
-        with open(path, "wb") as f:
-            f.write(data)
+        path, meta = reference_sample(workload, k, scale, torch, bench_data, dev)
         try:
-            secs = cpu_reference_run(path, k, max(1000, int(2.5 * min(kmers, meta["G"]))), threads)
+            r = cpu_reference_run(path, k, meta["slots"], threads)
+            w = cpu_reference_run(path, k, meta["slots"], threads, write=True)      # file -> output file, wall clock
         finally:
             os.remove(path)
-        return {"value": kmers / secs, "unit": UNIT, "cores": threads - 2, "kind": "reference", "host_cores": cores,
-                "sample": f"first {n} reads ({len(data)} bytes, {kmers} input k-mers) of {meta['name']}, "
-                          f"oracle/_ref/kaarme -m 0 -t {threads}, its own build-table timer", "seconds": secs}
-    data, n, kmers = make_sample(meta, fasta_cuda, 64 << 20)
+        return {"value": meta["input_kmers"] / r["build_s"], "unit": UNIT, "cores": threads - 2, "kind": "reference", "host_cores": cores,
+                "sample": sample_string(meta, k) + f"; oracle/_ref/kaarme -t {threads}, its own build-table timer", "seconds": r["build_s"],
+                "file_to_file": {"wall_s": w["wall_s"], "kmers_per_s": meta["input_kmers"] / w["wall_s"], "output_bytes": w["out_bytes"],
+                                 "build_s": w["build_s"], "write_s": w.get("write_s")}}
+    fasta, meta = bench_data.make_config(workload, dev, scale=scale * 0.02)
+    data = fasta.cpu().numpy().tobytes()
     secs, tw = cpu_port_run(data, k)
     return {"value": tw / secs, "unit": UNIT, "cores": 1, "kind": "port", "host_cores": cores,
-            "sample": f"first {n} reads ({len(data)} bytes) of {meta['name']}, oracle/liboracle.so ko_count", "seconds": secs}
+            "sample": f"0.02 of the workload ({len(data)} bytes), oracle/liboracle.so ko_count", "seconds": secs}
+
+
+def split_u64(vals):
+    out = []
+    for v in vals:
+        out += [v & 0xFFFFFFFF, v >> 32]
+    return out
+
+
+def join_u64(parts):
+    return [(int(parts[2 * i]) + (int(parts[2 * i + 1]) << 32)) & 0xFFFFFFFFFFFFFFFF for i in range(len(parts) // 2)]
 
 
 # ---- main ------------------------------------------------------------------------------------------------------
@@ -277,10 +317,69 @@ def main():
                "ms_per_step": te.item() * 1e3 / args.steps}
         del host
 
+    # ---- correctness of what was just timed (untimed) ----------------------------------------------------------------
+    # every window counted exactly once: sum over shards of (sum of counts) == sum over ranks of input k-mers; and the
+    # sharded / bucketed result equals an independent count of the same reads by ONE table on rank 0 through the direct
+    # path (kg_count_kernel, no bucketing, no exchange): order-independent checksums (kg_checksum), additive over shards.
+    verify = None
+    if not args.bloom:
+        mine = ctr.checksum(1, KG.COUNT_EXACT)
+        tsum = torch.tensor(split_u64(mine) + [meta["input_kmers"]], dtype=torch.int64, device=dev)
+        if world > 1:
+            dist.all_reduce(tsum)
+        parts = tsum.tolist()
+        sharded = join_u64(parts[:8])
+        if rank == 0:
+            single = kg.Counter(k=k, table_mode=KG.TABLE_PLAIN, input_mode=KG.INPUT_FASTA, min_slots=total_slots, device=local_rank,
+                                batch_bytes=args.batch_mb << 20, partitions=1)
+            single.pass_begin(KG.PASS_COUNT)
+            for r in range(world):
+                fr = fasta if r == rank else bench_data.make_config(args.workload, dev, scale=args.scale, rank=r, world=world)[0]
+                single.stream_begin(False)
+                single.feed_device(fr.data_ptr(), fr.numel())
+                torch.cuda.synchronize()
+                if r != rank:
+                    del fr
+            single.pass_end()
+            ref = list(single.checksum(1, KG.COUNT_EXACT))
+            single.close()
+            verify = {"kmers": sharded[0], "sum_of_counts": sharded[1], "input_kmers_all_ranks": parts[8],
+                      "checksum": [hex(x) for x in sharded[2:]], "single_table_direct_path": {"kmers": ref[0], "sum_of_counts": ref[1],
+                                                                                             "checksum": [hex(x) for x in ref[2:]]},
+                      "match": sharded == ref and sharded[1] == parts[8],
+                      "how": "kg_checksum of every shard, added; against ONE table filled from all ranks' reads by kg_count_kernel on rank 0"}
+            assert verify["match"], verify
+    if world > 1:
+        dist.barrier()
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
         return 0
+
+    # ---- file -> output file through the CLI (wall clock; N = 1) ---------------------------------------------------------
+    file_to_file = None
+    if world == 1 and not args.no_e2e:
+        try:
+            path = f"/dev/shm/kaarme_bench_{os.getpid()}.fasta"
+            with open(path, "wb") as f:
+                f.write(fasta.cpu().numpy().tobytes())
+            exe = os.path.join(ROOT, "canonical-k-mer-hash-table_b200", "kaarme")
+            cmd = [exe, path, str(k), "-m", "0", "-s", str(total_slots), "-a", "2", "-t", str(max(3, min(64, os.cpu_count() or 3))), "-o", path + ".out"]
+            t0 = time.perf_counter()
+            p = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=600)
+            wall_cli = time.perf_counter() - t0
+            file_to_file = {"wall_s": wall_cli, "kmers_per_s": meta["input_kmers"] / wall_cli, "rc": p.returncode,
+                            "output_bytes": os.path.getsize(path + ".out") if os.path.exists(path + ".out") else 0,
+                            "input_bytes": int(fasta.numel()),
+                            "timers": {ln.split(":")[0]: ln.split(":")[1].strip() for ln in p.stdout.splitlines() if ln.startswith("Time used")},
+                            "cmd": "kaarme INPUT 51 -m 0 -s 250000000 -a 2 (FASTA and output on /dev/shm)"}
+        except Exception as e:  # noqa: BLE001
+            file_to_file = {"error": str(e)}
+        finally:
+            for q in (path, path + ".out"):
+                if os.path.exists(q):
+                    os.remove(q)
 
     # ---- roofline of the dominant kernel -----------------------------------------------------------------------
     # direct path: kg_count_kernel<W,TABLE>; bucketed path (partitions > 1 or N > 1): kg_insert_keys/segs_kernel.
@@ -328,8 +427,8 @@ def main():
     out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
            "ms_per_step": dev_ms / args.steps, "wall_ms_per_step": wall_ms / args.steps, "higher_is_better": True,
            "scaling": "weak", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
-           "config": {"workload": f"{args.workload}: {meta['G']} bp genome, {meta['cov']}x of {meta['L']} bp reads, "
-                                  f"k={k}, -m 0 " + (f"-b -u {meta['G']} -f {args.fpr}" if args.bloom else f"-s {total_slots}"), "scale": args.scale,
+           "config": {"workload": workload_string(dict(bench_data.CONFIGS[args.workload], name=args.workload), k, args.scale, world, args.bloom, args.fpr),
+                      "scale": args.scale,
                       "bloom": bloom_info or None, "fasta_bytes_per_gpu": int(fasta.numel()),
                       "table_bytes_per_gpu": ctr.table_info()["slots"] * ctr.table_info()["slot_bytes"],
                       "input_kmers_per_gpu": meta["input_kmers"], "distinct_rank0": distinct,
@@ -337,12 +436,13 @@ def main():
                       "parallelism": (f"minimizer-sharded x{world}: 8-byte run descriptors read in place over NVLink, packed reads "
                                       f"pulled by the copy engines, one-word NCCL all-reduce per round") if world > 1 else "single GPU",
                       "partitions": st["partitions"], "batch_mb": args.batch_mb},
-           "clocks": clocks, "gpu_launches": launches, "roofline": roofline, "e2e": e2e,
+           "clocks": clocks, "gpu_launches": launches, "roofline": roofline, "e2e": e2e, "verify": verify, "file_to_file": file_to_file,
            "stage_ms_per_step": {"parse": parse_ms / args.steps, "bucket+insert": count_ms / args.steps,
                                  "insert_kernel": insert_ms / args.steps}}
     if world == 1 and not args.no_cpu_baseline:
         try:
-            out["cpu_baseline"] = cpu_baseline(meta, fasta, k)
+            del fasta
+            out["cpu_baseline"] = cpu_baseline(args.workload, k, args.scale, torch, bench_data, dev)
         except Exception as e:  # noqa: BLE001
             out["cpu_baseline"] = {"error": str(e)}
     print(json.dumps(out))
@@ -352,49 +452,44 @@ def main():
 
 
 def run_reference(args, torch, bench_data):
-    """--impl reference: the reference's own CPU counter on this box's host cores, bounded sample per step."""
+    """--impl reference: the reference's own CPU counter on this box's host cores; every step counts the same bounded
+    sample of the workload (REF_FRACTION of the genome at the same coverage)."""
     import oracle.oracle_py as o
     k = args.k
     dev = torch.device("cuda", 0) if torch.cuda.is_available() else torch.device("cpu")
     cores = os.cpu_count() or 1
     threads = max(3, min(64, cores))
-    c = dict(bench_data.CONFIGS[args.workload])
-    # generate only what the sample needs (same generator, same seeds as the GPU arm's rank 0)
-    rec = bench_data.record_bytes(c["L"], c["wrap"], 9)
-    sample_bytes = (threads - 2) * (10 << 20) if o.have_ref() else (64 << 20)
-    n = max(1, min(int(c["G"] * c["cov"] / c["L"] * args.scale), sample_bytes // rec))
-    genome = bench_data.make_genome(int(c["G"] * args.scale), c["seed"], dev)
-    fasta = bench_data.make_reads_fasta(genome, n, c["L"], seed=c["seed"] * 1000, err=c["err"], wrap=c["wrap"])
-    data = fasta.cpu().numpy().tobytes()
-    kmers = n * (c["L"] - k + 1)
-    times = []
+    c = dict(bench_data.CONFIGS[args.workload], name=args.workload)
+    times, f2f = [], None
     if o.have_ref():
-        path = f"/dev/shm/kaarme_bench_ref_{os.getpid()}.fasta"
-        with open(path, "wb") as f:
-            f.write(data)
+        path, meta = reference_sample(args.workload, k, args.scale, torch, bench_data, dev)
+        kmers = meta["input_kmers"]
         try:
             for i in range(args.warmup + args.steps):
-                s = cpu_reference_run(path, k, max(1000, int(2.5 * min(kmers, c["G"] * args.scale))), threads)
+                r = cpu_reference_run(path, k, meta["slots"], threads)
                 if i >= args.warmup:
-                    times.append(s)
+                    times.append(r["build_s"])
+            w = cpu_reference_run(path, k, meta["slots"], threads, write=True)
+            f2f = {"wall_s": w["wall_s"], "kmers_per_s": kmers / w["wall_s"], "output_bytes": w["out_bytes"], "build_s": w["build_s"],
+                   "write_s": w.get("write_s")}
         finally:
             os.remove(path)
-        kind, used = "reference", threads - 2
+        kind, used, sample = "reference", threads - 2, sample_string(meta, k) + f"; oracle/_ref/kaarme -t {threads}"
     else:
+        fasta, meta = bench_data.make_config(args.workload, dev, scale=args.scale * 0.02)
+        data = fasta.cpu().numpy().tobytes()
         for i in range(args.warmup + args.steps):
-            s, _ = cpu_port_run(data, k)
+            secs, kmers = cpu_port_run(data, k)
             if i >= args.warmup:
-                times.append(s)
-        kind, used = "port", 1
+                times.append(secs)
+        kind, used, sample = "port", 1, f"0.02 of the workload ({len(data)} bytes), oracle/liboracle.so ko_count"
     value = kmers * len(times) / sum(times)
-    sample = f"first {n} reads ({len(data)} bytes, {kmers} input k-mers) of {args.workload} per step"
     out = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
            "warmup": args.warmup, "ms_per_step": 1e3 * sum(times) / len(times), "higher_is_better": True, "scaling": "weak",
            "vs_baseline": None, "dtype": "u64", "data": "synthetic",
-           "config": {"workload": f"{args.workload}: {int(c['G'] * args.scale)} bp genome, {c['cov']}x of {c['L']} bp reads, k={k}, -m 0",
-                      "scale": args.scale},
-           "cpu_baseline": {"value": value, "unit": UNIT, "cores": used, "kind": kind, "sample": sample, "host_cores": cores},
-           "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+           "config": {"workload": workload_string(c, k, args.scale, max(1, args.gpus), args.bloom, args.fpr), "scale": args.scale},
+           "cpu_baseline": {"value": value, "unit": UNIT, "cores": used, "kind": kind, "sample": sample + " per step", "host_cores": cores},
+           "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "file_to_file": f2f}
     print(json.dumps(out))
     return 0
 

@@ -42,23 +42,23 @@
 #define KG_MAX_BATCH (1ull << 30)
 
 // One of the two batch slots of the minimizer-bucketed path.  A slot is ONE device allocation
-//   [ header 64 B | bucket cursors | pad to KG_SKM_META | packed 2-bit words of the batch | descriptor regions + overflow list ]
-// so that a peer can map it with one IPC handle and pull header + cursors + words with one copy.
+//   [ header 64 B | descriptor counts | pad to KG_SKM_META | packed 2-bit words of the batch | descriptor regions + overflow list ]
+// so that a peer can map it with one IPC handle and pull header + counts + words with one copy.
 struct SkmSlot {
     uint8_t* slab = nullptr;
     u64* hdr = nullptr;           // [0] global ordinal of position 0 of the batch, [1] bases in the packed stream
-    u32* cursors = nullptr;       // [nb + 1]
+    u32* counts = nullptr;        // dense descriptor counts per (bucket, sub-region) + overflow (kg_skm_pack_counts)
     u64* words = nullptr;         // packed stream of the batch (parse writes it here)
     u64* desc = nullptr;          // nb regions of skm_cap descriptors, then the overflow list
     KgSkmSources* d_src = nullptr;    // where the insert of this slot finds every sender's words + header
-    KgSkmPeers* d_peers = nullptr;    // where kg_skm_segments finds every sender's cursors + descriptors
+    KgSkmPeers* d_peers = nullptr;    // where kg_skm_segments finds every sender's counts + descriptors
     u64* d_seg_start = nullptr;
     const u64** d_seg_ptr = nullptr;
     cudaEvent_t ev_ready = nullptr;   // s_compute: the slot holds this rank's batch of the round
     cudaEvent_t ev_free = nullptr;    // the slot may be overwritten (one GPU: its insert is done; several: every rank's is)
     uint8_t* peer_slab[KG_MAX_WORLD] = {};   // every rank's slot of this parity as mapped into this process
     void* peer_opened[KG_MAX_WORLD] = {};    // IPC mappings to close at destroy
-    uint8_t* r_buf[KG_MAX_WORLD] = {};       // local copies of the peers' header + cursors + words (pulled every round)
+    uint8_t* r_buf[KG_MAX_WORLD] = {};       // local copies of the peers' header + counts + words (pulled every round)
 };
 
 struct kg_ctx {
@@ -125,7 +125,8 @@ struct kg_ctx {
     u32 nb = 0;                         // buckets of the current pass = world * local partitions
     u32 pl = 1;                         // local partitions of the current pass
     u32 skm_m = 0;                      // minimizer length for this k
-    u32 skm_cap = 0;                    // descriptors per bucket region in the current pass
+    u32 skm_cap = 0;                    // descriptors per (bucket, sub-region) in the current pass
+    u32* d_cursors = nullptr;           // reservation counters of the scatter, one per 32-byte sector
     u32 skm_ovf_cap = 0;                // descriptors the overflow list can hold (= every position of a batch)
     u64 skm_region_total = 0, skm_desc_cap = 0;
     size_t skm_words_bytes = 0, skm_slab_bytes = 0;
@@ -303,7 +304,7 @@ static void free_all(kg_ctx* c) {
     if (c->h_text_cur) cudaFreeHost(c->h_text_cur);
     if (c->h_round_sum) cudaFreeHost(c->h_round_sum);
     cudaFree(c->kaarme.slots); cudaFree(c->kaarme.roots); cudaFree(c->d_cstats); cudaFree(c->d_work);
-    cudaFree(c->d_part_lo); cudaFree(c->d_bpart_lo); cudaFree(c->d_round);
+    cudaFree(c->d_part_lo); cudaFree(c->d_bpart_lo); cudaFree(c->d_round); cudaFree(c->d_cursors);
     for (auto& b : c->rb_log) { cudaFree(b.words); cudaFree(b.brk); cudaFree(b.st); }
     c->rb_log.clear();
     cudaFree(c->rb.T1); cudaFree(c->rb.T2);
@@ -334,7 +335,7 @@ static void free_all(kg_ctx* c) {
 static void skm_geometry(kg_ctx* c) {
     const u64 positions = c->batch_bytes + 32ull * c->carry_max_words + 64;
     const u32 wlen = c->cfg.k - c->skm_m + 1;
-    c->skm_region_total = (wlen >= 8 ? positions / 4 : positions) * 5 / 4 + (u64)KG_MAX_BUCKETS * 256;
+    c->skm_region_total = (wlen >= 8 ? positions / 4 : positions) * 5 / 4 + (u64)KG_MAX_BUCKETS * KG_SKM_SUB * 64;
     c->skm_ovf_cap = (u32)positions;
     c->skm_words_bytes = ((c->words_cap * sizeof(u64)) + 255) / 256 * 256;
     c->skm_desc_cap = c->skm_region_total + c->skm_ovf_cap + 64;
@@ -348,7 +349,7 @@ static int alloc_slots(kg_ctx* c) {
         KG_CUDA(c, cudaMalloc(&s.slab, c->skm_slab_bytes));
         KG_CUDA(c, cudaMemset(s.slab, 0, KG_SKM_META));
         s.hdr = (u64*)s.slab;
-        s.cursors = (u32*)(s.slab + 64);
+        s.counts = (u32*)(s.slab + 64);
         s.words = (u64*)(s.slab + KG_SKM_META);
         s.desc = (u64*)(s.slab + KG_SKM_META + c->skm_words_bytes);
         KG_CUDA(c, cudaMalloc(&s.d_src, sizeof(KgSkmSources)));
@@ -362,7 +363,7 @@ static int alloc_slots(kg_ctx* c) {
     return KG_OK;
 }
 
-// the device-side tables that say where every rank's words / cursors / descriptors of a slot are to be found
+// the device-side tables that say where every rank's words / counts / descriptors of a slot are to be found
 static int publish_slot_tables(kg_ctx* c) {
     const int world = c->cfg.world, me = c->cfg.rank;
     for (int b = 0; b < 2; b++) {
@@ -372,10 +373,10 @@ static int publish_slot_tables(kg_ctx* c) {
         memset(&src, 0, sizeof(src));
         memset(&peers, 0, sizeof(peers));
         for (int r = 0; r < world; r++) {
-            const uint8_t* meta = r == me ? s.slab : s.r_buf[r];                 // local (copied) header + cursors + packed words
+            const uint8_t* meta = r == me ? s.slab : s.r_buf[r];                 // local (copied) header + counts + packed words
             src.hdr[r] = (const u64*)meta;
             src.words[r] = (const u64*)(meta + KG_SKM_META);
-            peers.cursors[r] = (const u32*)(meta + 64);
+            peers.counts[r] = (const u32*)(meta + 64);
             peers.desc[r] = (const u64*)(s.peer_slab[r] + KG_SKM_META + c->skm_words_bytes);   // read in place (NVLink for r != me)
         }
         KG_CUDA(c, cudaMemcpy(s.d_src, &src, sizeof(src), cudaMemcpyHostToDevice));
@@ -499,6 +500,7 @@ extern "C" int kg_create(const kg_config* cfg, kg_ctx** out) {
         KG_TRY(cudaEventCreateWithFlags(&c->ev_pass_ready, cudaEventDisableTiming));
         KG_TRY(cudaEventCreateWithFlags(&c->ev_tail, cudaEventDisableTiming));
         KG_TRY(cudaMalloc(&c->d_round, sizeof(u32) * 8));
+        KG_TRY(cudaMalloc(&c->d_cursors, sizeof(u32) * 8 * ((size_t)KG_MAX_BUCKETS * KG_SKM_SUB + 1)));
         {   // d_round[0] = 0, d_round[1] = 1: the two possible contributions to a round's "ranks with a batch" sum
             const u32 init[8] = {0, 1, 0, 0, 0, 0, 0, 0};
             KG_TRY(cudaMemcpy(c->d_round, init, sizeof(init), cudaMemcpyHostToDevice));
@@ -634,6 +636,14 @@ static int setup_pass_buckets(kg_ctx* c, size_t region_bytes) {
     const u32 world = (u32)c->cfg.world;
     u32 pl = c->cfg.partitions;
     if (pl == 0) {
+        // Bloom mode: the filter words of a k-mer are placed by its partition, so the Bloom pass and the count pass must
+        // partition alike: size for the larger of the filter and the table the configuration promises (2 x expected
+        // distinct k-mers, main.cpp:454), whatever the pass
+        if (c->cfg.use_bloom) {
+            const size_t est_table = (size_t)(2 * c->cfg.expected_unique / (uint64_t)world) *
+                                     kg_slot_stride_words((u32)c->W, c->cfg.table_mode == KG_TABLE_KAARME) * sizeof(u64);
+            region_bytes = est_table > c->bloom_bytes ? est_table : c->bloom_bytes;
+        }
         pl = 1;
         if (region_bytes > (96u << 20)) while ((size_t)pl * (24u << 20) < region_bytes && pl * 2 * world <= KG_MAX_BUCKETS) pl *= 2;
     }
@@ -642,7 +652,7 @@ static int setup_pass_buckets(kg_ctx* c, size_t region_bytes) {
     c->pl = pl;
     c->nb = world * pl;
     c->pass_bucketed = world > 1 || pl > 1;
-    c->skm_cap = (u32)(c->skm_region_total / c->nb);
+    c->skm_cap = (u32)(c->skm_region_total / ((u64)c->nb * KG_SKM_SUB));   // descriptors per (bucket, sub-region)
     return KG_OK;
 }
 
@@ -803,10 +813,10 @@ static void launch_skm_insert(kg_ctx* c, const KgSkmInsertArgs& a, int sink) {
 
 // One round of the minimizer-bucketed path (collective when world > 1; every rank issues the same sequence).
 //   s_compute  (have_batch: parse + kg_skm_scatter of this rank's batch were just queued into slot b = round & 1;
-//              otherwise the slot's cursors are cleared: the rank contributes nothing)            -> ev_ready
+//              otherwise the slot's counts are cleared: the rank contributes nothing)            -> ev_ready
 //   s_insert   world > 1: one-word all-reduce = "every rank's slot b is ready, and every rank has finished the insert
 //              of the previous round" (so the OTHER slot may be overwritten: ev_free), its sum = ranks that had a batch;
-//              then the copy engines pull header + cursors + packed words of every peer's slot over NVLink
+//              then the copy engines pull header + counts + packed words of every peer's slot over NVLink
 //              kg_skm_segments (where are the descriptors for my partitions, partition-major across senders) and
 //              kg_skm_insert, which reads the peers' descriptors in place
 // No host synchronisation anywhere: the host only waits when kg_pass_end asks for the all-reduce's sum.
@@ -816,7 +826,7 @@ static int skm_round(kg_ctx* c, bool have_batch, bool want_sum) {
     const int world = c->cfg.world, me = c->cfg.rank;
     if (!have_batch) {
         KG_CUDA(c, cudaStreamWaitEvent(c->s_compute, s.ev_free, 0));
-        KG_CUDA(c, cudaMemsetAsync(s.cursors, 0, sizeof(u32) * (c->nb + 1), c->s_compute));
+        KG_CUDA(c, cudaMemsetAsync(s.counts, 0, sizeof(u32) * (c->nb * KG_SKM_SUB + 1), c->s_compute));
     }
     KG_CUDA(c, cudaEventRecord(s.ev_ready, c->s_compute));
     KG_CUDA(c, cudaStreamWaitEvent(c->s_insert, s.ev_ready, 0));
@@ -827,8 +837,8 @@ static int skm_round(kg_ctx* c, bool have_batch, bool want_sum) {
         for (int r = 0; r < world; r++)
             if (r != me) KG_CUDA(c, cudaMemcpyAsync(s.r_buf[r], s.peer_slab[r], KG_SKM_META + c->skm_words_bytes, cudaMemcpyDefault, c->s_insert));
     }
-    const u32 nseg = (u32)world * c->pl + (u32)world;
-    kg_skm_segments<<<1, 1024, 0, c->s_insert>>>(s.d_peers, (u32)world, (u32)me, c->pl, c->nb, c->skm_cap, c->skm_ovf_cap, s.d_seg_start, s.d_seg_ptr);
+    const u32 nseg = (u32)world * c->pl * KG_SKM_SUB + (u32)world;
+    kg_skm_segments<<<1, 1024, 0, c->s_insert>>>(s.d_peers, (u32)world, (u32)me, c->pl, c->nb, c->skm_cap, s.d_seg_start, s.d_seg_ptr);
     c->launches++;
     KG_CUDA(c, cudaMemsetAsync(c->d_work, 0, sizeof(u32), c->s_insert));
     KgSkmInsertArgs a;
@@ -848,15 +858,17 @@ static int skm_round(kg_ctx* c, bool have_batch, bool want_sum) {
 // bucket the windows of the batch that was just packed into the current slot, then hand the slot to the round
 static int bucket_batch(kg_ctx* c, u32 nwords) {
     SkmSlot& s = c->slot[c->round & 1];
-    KG_CUDA(c, cudaMemsetAsync(s.cursors, 0, sizeof(u32) * (c->nb + 1), c->s_compute));
+    const u32 nregions = c->nb * KG_SKM_SUB;
+    KG_CUDA(c, cudaMemsetAsync(c->d_cursors, 0, sizeof(u32) * 8 * (nregions + 1), c->s_compute));
     KgSkmScatterArgs a;
-    a.words = s.words; a.brk = c->d_brk; a.st = c->d_stream; a.cursors = s.cursors; a.regions = s.desc;
-    a.ovf = s.desc + (u64)c->nb * c->skm_cap; a.hdr = s.hdr; a.stats = c->d_stats;
+    a.words = s.words; a.brk = c->d_brk; a.st = c->d_stream; a.cursors = c->d_cursors; a.regions = s.desc;
+    a.ovf = s.desc + (u64)nregions * c->skm_cap; a.hdr = s.hdr; a.stats = c->d_stats;
     a.k = c->cfg.k; a.m = c->skm_m; a.nb = c->nb; a.pl = c->pl; a.cap = c->skm_cap; a.src = (u32)c->cfg.rank;
     a.ovf_cap = c->skm_ovf_cap; a.nwords = nwords;
     const u32 grid = (nwords + KG_SKM_TPB - 1) / KG_SKM_TPB;
     kg_skm_scatter<<<grid, KG_SKM_TPB, 0, c->s_compute>>>(a);
-    c->launches++;
+    kg_skm_pack_counts<<<(nregions + 256) / 256, 256, 0, c->s_compute>>>(c->d_cursors, nregions, c->skm_cap, c->skm_ovf_cap, s.counts);
+    c->launches += 2;
     return skm_round(c, true, false);
 }
 
@@ -1403,6 +1415,27 @@ extern "C" int kg_export(kg_ctx* c, uint64_t min_abundance, int count_mode, kg_s
 extern "C" int kg_export_text(kg_ctx* c, uint64_t min_abundance, int count_mode, kg_text_sink_fn sink, void* user) {
     if (!sink) return KG_EBADARG;
     return export_impl(c, min_abundance, count_mode, nullptr, sink, user);
+}
+
+template <int W>
+static void launch_checksum(kg_ctx* c, uint64_t min_ab, int count_mode, u64* d_out) {
+    if (c->compacted) kg_checksum_kaarme<W><<<148 * 8, 256, 0, c->s_compute>>>(c->kaarme, c->cfg.k, min_ab, d_out, c->d_cstats);
+    else kg_checksum_table<W><<<148 * 8, 256, 0, c->s_compute>>>(c->table, min_ab, count_mode, c->cfg.table_mode, d_out);
+    c->launches++;
+}
+extern "C" int kg_checksum(kg_ctx* c, uint64_t min_abundance, int count_mode, uint64_t out[4]) {
+    if (!c || !out || (!c->table.slots && !c->compacted)) return KG_EBADARG;
+    KG_CUDA(c, cudaSetDevice(c->cfg.device));
+    u64* d_out = nullptr;
+    KG_CUDA(c, cudaMalloc(&d_out, sizeof(u64) * 4));
+    struct Guard { u64** p; ~Guard() { cudaFree(*p); } } guard{&d_out};
+    KG_CUDA(c, cudaMemsetAsync(d_out, 0, sizeof(u64) * 4, c->s_compute));
+    if (c->compacted && !c->d_cstats) return KG_EBADARG;
+    KG_DISPATCH_W(c->W, launch_checksum, c, min_abundance, c->compacted ? KG_COUNT_REFERENCE : count_mode, d_out);
+    KG_CUDA(c, cudaMemcpyAsync(out, d_out, sizeof(u64) * 4, cudaMemcpyDeviceToHost, c->s_compute));
+    KG_CUDA(c, cudaStreamSynchronize(c->s_compute));
+    KG_CUDA(c, cudaGetLastError());
+    return KG_OK;
 }
 
 extern "C" int kg_kaarme_download(kg_ctx* c, uint64_t* slots, uint64_t* roots) {

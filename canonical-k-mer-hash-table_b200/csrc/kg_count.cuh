@@ -193,13 +193,13 @@ struct KgConsume {
     __device__ __forceinline__ void operator()(const u64 (&key)[W], u64 h, KgOcc occ, u32 = 0) {
         const u64 hl = h * (u64)hmul;
         if (SINK == KG_SINK_BLOOM1) {
-            kg_bloom_insert(bloom, h, b_lo + __umul64hi(hl, b_n), n_b1, n_b2);
+            kg_bloom_insert(bloom, h, kg_place(hl, b_lo, b_n), n_b1, n_b2);
             return;
         }
-        if (SINK == KG_SINK_BLOOM2 && !kg_bloom_admits(bloom, h, b_lo + __umul64hi(hl, b_n))) { n_rej++; return; }
+        if (SINK == KG_SINK_BLOOM2 && !kg_bloom_admits(bloom, h, kg_place(hl, b_lo, b_n))) { n_rej++; return; }
         bool is_new;
         u64 slot;
-        const u64 slot0 = t_lo + __umul64hi(hl, t_n);
+        const u64 slot0 = kg_place(hl, t_lo, t_n);
         if constexpr (W == 2) slot = table.packed_tb ? kg_table_add_packed(table, key, slot0, is_new) : kg_table_add<W>(table, key, slot0, is_new);
         else slot = kg_table_add<W>(table, key, slot0, is_new);
         if (slot == ~0ULL) { full = true; return; }

@@ -50,16 +50,19 @@ __device__ __forceinline__ u64 kg_fmix64(u64 x) {
 // is the k-mer multiset, not the slot order, so any well-mixed function of the canonical key serves)
 template <int W>
 __device__ __forceinline__ u64 kg_hash_key(const u64 (&key)[W]) {
-    // one odd multiplier per word folds the words together, one fmix64 finalises: 2 + W 64-bit multiplies
-    // (the previous version ran a full fmix64 per word: 2W multiplies, ~40 % of the window pass at W = 2)
+    // multiply-xorshift chain: one 64-bit multiply per key word and one to finish.  Consumers take the HIGH bits (range
+    // partition by multiply-high), which is where a product mixes best; the xorshift between the multiplies brings the high
+    // bits of every word back down so that they reach the high bits of the result as well.  (Two earlier versions ran a
+    // full fmix64 per word, then fmix64 once at the end: 2W resp. W + 4 multiplies; the hash was ~30 % of the
+    // instructions of the insert kernel.)
     u64 h = 0x9E3779B97F4A7C15ULL;
 #pragma unroll
     for (int i = 0; i < W; i++) {
-        const u64 m = (key[i] + 0x9E3779B97F4A7C15ULL * (u64)(i + 1)) * (0xD6E8FEB86659FD93ULL + 2ULL * (u64)i);
-        h = (h ^ m) * 0x9FB21C651E98DF25ULL;
-        h ^= h >> 29;
+        h = (h ^ key[i]) * (0xD6E8FEB86659FD93ULL + 2ULL * (u64)i);
+        h ^= h >> 32;
     }
-    return kg_fmix64(h);
+    h *= 0x9FB21C651E98DF25ULL;
+    return h ^ (h >> 29);
 }
 
 // Range partitioning of the 64-bit hash: owner shard = floor(h * world / 2^64); inside the shard the
@@ -68,7 +71,12 @@ __device__ __forceinline__ u64 kg_hash_key(const u64 (&key)[W]) {
 // range [p*nslots/nb, (p+1)*nslots/nb): inserting one partition at a time keeps the live table region in L2.
 __device__ __forceinline__ u32 kg_owner(u64 h, u32 world) { return (u32)__umul64hi(h, (u64)world); }
 __device__ __forceinline__ u64 kg_local_hash(u64 h, u32 world) { return h * (u64)world; }
-__device__ __forceinline__ u64 kg_slot(u64 h, u64 nslots, u32 world) { return __umul64hi(kg_local_hash(h, world), nslots); }
+// position of hash h inside a range of n slots starting at lo: floor(h * n / 2^64), with one 32-bit multiply when the
+// range has fewer than 2^32 slots (every partition of the bucketed path; uses the high 32 bits of h)
+__device__ __forceinline__ u64 kg_place(u64 h, u64 lo, u64 n) {
+    return lo + ((n >> 32) ? __umul64hi(h, n) : (((h >> 32) * (n & 0xFFFFFFFFULL)) >> 32));
+}
+__device__ __forceinline__ u64 kg_slot(u64 h, u64 nslots, u32 world) { return kg_place(kg_local_hash(h, world), 0, nslots); }
 
 // ---- strong (L2-coherent, L1-bypassing) accesses used on the table -----------------------------------
 __device__ __forceinline__ u32 kg_ld_u32(const void* p) {
@@ -132,47 +140,61 @@ __host__ __device__ inline u32 kg_slot_stride_words(u32 W, bool kaarme) {
 //   Writer: CAS 0->LOCKED, store key words, release-store count=1.  Reader: an ACQUIRE load of meta, then the key words
 //   (W > 1; relaxed loads ordered after the acquire -- PTX does not order loads by control dependency).  W == 1 reads
 //   meta and the key in one aligned 16-byte access.  Key words never change once published.
+// The probe loops below have ONE exit and no side effect other than the claim: lanes of a warp whose probe is over wait at
+// the loop's end for the others, and the count update (RED) and the statistics run once, converged, after it.  (With
+// `break`s inside, the compiler kept the lanes apart and replayed the whole tail once per loop iteration: the probe code
+// was 55 % of the insert kernel's instructions at a third of a warp's width.)
+#define KG_PROBE_SEARCH 0
+#define KG_PROBE_FOUND 1
+#define KG_PROBE_NEW 2
+#define KG_PROBE_FAIL 3
 template <int W>
 __device__ __forceinline__ u64 kg_table_add(const KgTable& t, const u64 (&key)[W], u64 slot, bool& is_new) {
-    is_new = false;
-    const u64 max_probe = t.nslots < KG_MAX_PROBE ? t.nslots : KG_MAX_PROBE;
-    for (u64 probe = 0; probe < max_probe; probe++) {
-        u64* p = t.slots + slot * t.stride;
+    u64* p = t.slots + slot * t.stride;
+    u64* const end = t.slots + t.nslots * t.stride;
+    u32 budget = (u32)(t.nslots < KG_MAX_PROBE ? t.nslots : KG_MAX_PROBE);
+    u32 m = 0;
+    int state = KG_PROBE_SEARCH;
+    do {
         u64 meta, k0 = 0;
         bool k0_valid = false;
         if (W == 1) { kg_ld_v2(p, meta, k0); k0_valid = true; }
         else meta = kg_ld_acquire_u64(p);
-        u32 m = (u32)meta;
+        m = (u32)meta;
         if (m == 0) {
             const u32 old = atomicCAS((u32*)p, 0u, KG_LOCKED);
             if (old == 0) {
 #pragma unroll
                 for (int i = 0; i < W; i++) kg_st_u64(p + 1 + i, key[i]);
                 kg_st_release_u32(p, 1u);
-                is_new = true;
-                return slot;
+                state = KG_PROBE_NEW;
             }
             m = KG_LOCKED;                     // somebody else owns or owned it: observe it again, with acquire
         }
-        if (m == KG_LOCKED) {
-            do { m = kg_ld_acquire_u32(p); } while (m == KG_LOCKED);
-            k0_valid = false;
-        }
-        // slot is published: compare
-        if (!k0_valid) k0 = kg_ld_u64(p + 1);
-        bool same = (k0 == key[0]);
-        if (same) {
+        if (state == KG_PROBE_SEARCH) {
+            if (m == KG_LOCKED) {
+                do { m = kg_ld_acquire_u32(p); } while (m == KG_LOCKED);
+                k0_valid = false;
+            }
+            // slot is published: compare
+            if (!k0_valid) k0 = kg_ld_u64(p + 1);
+            bool same = (k0 == key[0]);
+            if (same) {
 #pragma unroll
-            for (int i = 1; i < W; i++) same = same && (kg_ld_u64(p + 1 + i) == key[i]);
+                for (int i = 1; i < W; i++) same = same && (kg_ld_u64(p + 1 + i) == key[i]);
+            }
+            if (same) {
+                state = KG_PROBE_FOUND;
+            } else {
+                p += t.stride;
+                if (p == end) p = t.slots;
+                if (--budget == 0 || ((budget & 255u) == 0 && t.full_flag && kg_ld_u32(t.full_flag))) state = KG_PROBE_FAIL;
+            }
         }
-        if (same) {
-            if (m < 0xFFFFFFFFu - KG_COUNT_MARGIN) atomicAdd((u32*)p, 1u);      // saturates instead of reaching KG_LOCKED
-            return slot;
-        }
-        slot = slot + 1 == t.nslots ? 0 : slot + 1;
-        if ((probe & 255u) == 255u && t.full_flag && kg_ld_u32(t.full_flag)) break;
-    }
-    return ~0ULL;
+    } while (state == KG_PROBE_SEARCH);
+    is_new = state == KG_PROBE_NEW;
+    if (state == KG_PROBE_FOUND && m < 0xFFFFFFFFu - KG_COUNT_MARGIN) atomicAdd((u32*)p, 1u);   // saturates below KG_LOCKED
+    return state == KG_PROBE_FAIL ? ~0ULL : (u64)(p - t.slots) / t.stride;
 }
 
 // ---- packed 16-byte slots (W == 2, 2k - 64 + count bits <= 64) ---------------------------------------------------
@@ -196,27 +218,33 @@ __device__ __forceinline__ void kg_red_add_u64(u64* p, u64 v) {
 }
 
 __device__ __forceinline__ u64 kg_table_add_packed(const KgTable& t, const u64 (&key)[2], u64 slot, bool& is_new) {
-    is_new = false;
     const u32 tb = t.packed_tb;
     const u64 keymask = (1ULL << tb) - 1, one = 1ULL << tb;
     const u64 sat = ((~0ULL) >> tb) - (u64)KG_COUNT_MARGIN;   // stop counting before the field could wrap into the key
-    const u64 max_probe = t.nslots < KG_MAX_PROBE ? t.nslots : KG_MAX_PROBE;
-    for (u64 probe = 0; probe < max_probe; probe++) {
-        u64* p = t.slots + slot * 2;
-        u64 w0, w1;
+    u64* p = t.slots + slot * 2;
+    u64* const end = t.slots + t.nslots * 2;
+    u32 budget = (u32)(t.nslots < KG_MAX_PROBE ? t.nslots : KG_MAX_PROBE);
+    u64 w0, w1;
+    int state = KG_PROBE_SEARCH;
+    do {
         kg_ld_v2(p, w0, w1);
         if ((w0 | w1) == 0) {
-            kg_cas128(p, 0, 0, one | key[0], key[1], w0, w1);
-            if ((w0 | w1) == 0) { is_new = true; return slot; }
+            kg_cas128(p, 0, 0, one | key[0], key[1], w0, w1);     // w0, w1 = what was there
+            if ((w0 | w1) == 0) state = KG_PROBE_NEW;
         }
-        if ((w0 & keymask) == key[0] && w1 == key[1]) {
-            if ((w0 >> tb) < sat) kg_red_add_u64(p, one);
-            return slot;
+        if (state == KG_PROBE_SEARCH) {
+            if ((w0 & keymask) == key[0] && w1 == key[1]) {
+                state = KG_PROBE_FOUND;
+            } else {
+                p += 2;
+                if (p == end) p = t.slots;
+                if (--budget == 0 || ((budget & 255u) == 0 && t.full_flag && kg_ld_u32(t.full_flag))) state = KG_PROBE_FAIL;
+            }
         }
-        slot = slot + 1 == t.nslots ? 0 : slot + 1;
-        if ((probe & 255u) == 255u && t.full_flag && kg_ld_u32(t.full_flag)) break;
-    }
-    return ~0ULL;
+    } while (state == KG_PROBE_SEARCH);
+    is_new = state == KG_PROBE_NEW;
+    if (state == KG_PROBE_FOUND && (w0 >> tb) < sat) kg_red_add_u64(p, one);
+    return state == KG_PROBE_FAIL ? ~0ULL : (u64)(p - t.slots) >> 1;
 }
 
 // read-only lookup starting at `slot` (compaction / decode); returns slot or ~0

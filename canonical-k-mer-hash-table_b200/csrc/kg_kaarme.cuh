@@ -178,7 +178,7 @@ __global__ void __launch_bounds__(256) kg_kaarme_build(KgTable t, u32 k, const u
                 has_pred = false;                       // predecessor belongs to another shard -> root
             } else {
                 const u64 lo = pm.part_lo[bkt % pm.pl], n_part = pm.part_lo[bkt % pm.pl + 1] - lo;
-                pred_slot = kg_table_find<W>(t, key, lo + __umul64hi(kg_hash_key<W>(key), n_part));
+                pred_slot = kg_table_find<W>(t, key, kg_place(kg_hash_key<W>(key), lo, n_part));
                 if (pred_slot == ~0ULL) has_pred = false;   // predecessor was not admitted (Bloom) -> this k-mer is a root
             }
         }
@@ -304,4 +304,65 @@ __global__ void __launch_bounds__(256) kg_kaarme_chain_stats(KgKaarme ks, u32 k,
     }
     if ((threadIdx.x & 31u) == 0) { atomicMax(&cs->max_chain, mx); atomicAdd(&cs->chain_sum, sum); }
     if (!ok) atomicAdd(&cs->bad, 1ULL);
+}
+
+// ---- order-independent checksum of the counted k-mers (kg_checksum) ---------------------------------------------------
+// out[0] = k-mers with reported count >= min_abundance, out[1] = sum of their counts, out[2] = sum of g(key),
+// out[3] = sum of g(key) * count (mod 2^64), g = a 64-bit mix of the key words that is independent of the table hash.
+// Sharded runs add the four words over the shards; equal words <=> the same multiset of (k-mer, count) as one table.
+template <int W>
+__device__ __forceinline__ u64 kg_checksum_mix(const u64 (&key)[W]) {
+    u64 h = 0x2545F4914F6CDD1DULL;
+#pragma unroll
+    for (int i = 0; i < W; i++) h = kg_fmix64(h ^ key[i]) + 0x9E3779B97F4A7C15ULL * (u64)(i + 1);
+    return kg_fmix64(h);
+}
+__device__ __forceinline__ void kg_checksum_commit(u64 n, u64 c, u64 g, u64 gc, u64* out) {
+    for (int d = 16; d; d >>= 1) {
+        n += __shfl_xor_sync(0xffffffffu, n, d);
+        c += __shfl_xor_sync(0xffffffffu, c, d);
+        g += __shfl_xor_sync(0xffffffffu, g, d);
+        gc += __shfl_xor_sync(0xffffffffu, gc, d);
+    }
+    if ((threadIdx.x & 31u) == 0 && n) { atomicAdd(out, n); atomicAdd(out + 1, c); atomicAdd(out + 2, g); atomicAdd(out + 3, gc); }
+}
+template <int W>
+__global__ void __launch_bounds__(256) kg_checksum_table(KgTable table, u64 min_abundance, int count_mode, int table_mode, u64* out) {
+    u64 n = 0, c = 0, g = 0, gc = 0;
+    for (u64 s = (u64)blockIdx.x * blockDim.x + threadIdx.x; s < table.nslots; s += (u64)gridDim.x * blockDim.x) {
+        const u64* p = table.slots + s * table.stride;
+        u64 key[W];
+        u64 cnt;
+        if (W == 2 && table.packed_tb) {
+            key[0] = p[0] & ((1ULL << table.packed_tb) - 1);
+            key[W - 1] = p[1];
+            cnt = p[0] >> table.packed_tb;
+        } else {
+            cnt = (u32)p[0];
+            if (cnt == KG_LOCKED) cnt = 0;
+#pragma unroll
+            for (int i = 0; i < W; i++) key[i] = p[1 + i];
+        }
+        if (cnt == 0) continue;
+        const u32 c32 = cnt > 0xFFFFFFFFULL ? 0xFFFFFFFFu : (u32)cnt;
+        const u64 rep = count_mode == 0 ? (u64)c32 : (table_mode == 0 ? (u64)(c32 & 0xFFFFu) : (u64)(c32 > 16383u ? 16383u : c32));
+        if (min_abundance == 0 || rep < min_abundance) continue;
+        const u64 h = kg_checksum_mix<W>(key);
+        n++; c += rep; g += h; gc += h * rep;
+    }
+    kg_checksum_commit(n, c, g, gc, out);
+}
+template <int W>
+__global__ void __launch_bounds__(256) kg_checksum_kaarme(KgKaarme ks, u32 k, u64 min_abundance, u64* out, KgCompactStats* cs) {
+    u64 n = 0, c = 0, g = 0, gc = 0;
+    for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < ks.n_kmers; i += (u64)gridDim.x * blockDim.x) {
+        const u64 d = ks.slots[i];
+        const u64 rep = KS_COUNT(d);
+        if (min_abundance == 0 || rep < min_abundance) continue;
+        u64 key[W], hops = 0;
+        if (!kg_kaarme_decode<W>(ks, k, i, key, hops)) { atomicAdd(&cs->bad, 1ULL); continue; }
+        const u64 h = kg_checksum_mix<W>(key);
+        n++; c += rep; g += h; gc += h * rep;
+    }
+    kg_checksum_commit(n, c, g, gc, out);
 }

@@ -26,8 +26,10 @@
 #define KG_SKM_MAXHALO 8                     // words of m-mer hashes needed to the left of a block: ceil((k-m)/32) <= 8
 #define KG_SKM_CHUNKS (KG_SKM_TPB + KG_SKM_MAXHALO)
 #define KG_SKM_MAXRUN 32u
-#define KG_SKM_META 8192                     // bytes at the head of a batch slot: header (64 B) + bucket cursors
-#define KG_SKM_MAXSEG (1024 + 64)             // partition-major segments across senders + one overflow list per sender
+#define KG_SKM_SUB 16u                       // sub-regions per bucket: a scatter block appends to sub-region blockIdx % 16, so the
+                                             // reservations of a bucket spread over 16 counters in 16 different sectors
+#define KG_SKM_META 73728                    // bytes at the head of a batch slot: header (64 B) + dense descriptor counts
+#define KG_SKM_MAXSEG (1024 * 16 + 64)        // (partition, sender, sub-region) segments + one overflow list per sender
 
 // minimizer length: short enough that runs are long (k-m+1 m-mers per window), long enough that buckets balance
 __host__ __device__ inline u32 kg_skm_m(u32 k) {
@@ -68,23 +70,16 @@ __host__ __device__ inline u64 kg_skm_desc(u32 j0, u32 src, u32 n, u32 has_pred,
 // ---- window extraction: the k bases ENDING at position e (inclusive) of a packed stream, right-aligned --------------
 template <int W>
 __host__ __device__ inline void kg_window_at(const u64* __restrict__ words, u32 e, const KgKGeom& g, u64 (&f)[W]) {
-    const u32 q = e + 1u, t = q >> 5, j0 = q & 31u;
-    if (j0 == 0) {
+    // t = word of the last base, j = bases of that word that belong to the window (1..32).  Branch-free: the part taken
+    // from the older word is shifted by 2j in two steps (2j - 1, then 1), so that j = 32 shifts it out entirely.
+    const u32 t = e >> 5, j = (e & 31u) + 1u;
+    u64 lo = words[t];
 #pragma unroll
-        for (int i = 0; i < W; i++) {
-            const int src = (int)t - 1 - i;
-            f[W - 1 - i] = src >= 0 ? words[src] : 0ULL;
-        }
-    } else {
-        const u32 s = 64 - 2 * j0;
-        u64 lo = words[t];
-#pragma unroll
-        for (int i = 0; i < W; i++) {
-            const int src = (int)t - 1 - i;
-            const u64 hi = src >= 0 ? words[src] : 0ULL;
-            f[W - 1 - i] = (hi << (64 - s)) | (lo >> s);
-            lo = hi;
-        }
+    for (int i = 0; i < W; i++) {
+        const int src = (int)t - 1 - i;
+        const u64 hi = src >= 0 ? words[src] : 0ULL;
+        f[W - 1 - i] = ((hi << (2u * j - 1u)) << 1) | (lo >> (64u - 2u * j));
+        lo = hi;
     }
     f[0] &= g.topmask;
 }
@@ -112,11 +107,16 @@ __host__ __device__ inline u64 kg_rev2_hd(u64 x) {
 __host__ __device__ inline u64 kg_revcomp1(u64 f, u32 m) { return (~kg_rev2_hd(f)) >> (64 - 2 * m); }
 
 // ---- scatter, phase 1: m-mer hashes of one packed word (32 end positions) ----------------------------------------------
-// H[i] = hash of the canonical m-mer ENDING at position 32*gc + i; sfx[i] = min(H[i..31]); returns min(H[0..31]).
-// Words before the stream (gc < 0) and m-mers that reach before position 0 give 0xFFFFFFFF (no valid window holds them).
-__host__ __device__ inline u32 kg_skm_hash_word(const u64* __restrict__ words, long long gc, u32 m, u32* H, u32* sfx) {
+// The block's arrays are TRANSPOSED: position i of local word lw lives at [i * KG_SKM_CHUNKS + lw], so that the threads of
+// a warp (consecutive words, same i) touch consecutive shared-memory banks.  (Word-major -- [lw * 32 + i] -- puts all 32
+// lanes on one bank: the first version of this kernel spent its time in 32-way bank conflicts.)
+#define KG_SKM_AT(lw, i) ((i) * KG_SKM_CHUNKS + (lw))
+// H[(lw,i)] = hash of the canonical m-mer ENDING at position 32*gc + i; sfx[(lw,i)] = min(H[(lw,i..31)]); returns
+// min(H[(lw,0..31)]).  Words before the stream (gc < 0) and m-mers that reach before position 0 give 0xFFFFFFFF (no valid
+// window holds them).
+__host__ __device__ inline u32 kg_skm_hash_word(const u64* __restrict__ words, long long gc, u32 m, u32* H, u32* sfx, u32 lw) {
     if (gc < 0) {
-        for (int i = 0; i < 32; i++) { H[i] = 0xFFFFFFFFu; sfx[i] = 0xFFFFFFFFu; }
+        for (u32 i = 0; i < 32; i++) { H[KG_SKM_AT(lw, i)] = 0xFFFFFFFFu; sfx[KG_SKM_AT(lw, i)] = 0xFFFFFFFFu; }
         return 0xFFFFFFFFu;
     }
     const u64 mmask = m == 32 ? ~0ULL : ((1ULL << (2 * m)) - 1ULL);
@@ -128,20 +128,34 @@ __host__ __device__ inline u32 kg_skm_hash_word(const u64* __restrict__ words, l
         const u64 c = (w >> (62 - 2 * i)) & 3ULL;
         f = ((f << 2) | c) & mmask;
         r = (r >> 2) | ((3ULL - c) << (2 * m - 2));
-        H[i] = i >= first_full ? kg_mmer_hash(f < r ? f : r) : 0xFFFFFFFFu;
+        H[KG_SKM_AT(lw, i)] = i >= first_full ? kg_mmer_hash(f < r ? f : r) : 0xFFFFFFFFu;
     }
     u32 run = 0xFFFFFFFFu;
-    for (int i = 31; i >= 0; i--) { run = H[i] < run ? H[i] : run; sfx[i] = run; }
+    for (int i = 31; i >= 0; i--) { const u32 h = H[KG_SKM_AT(lw, i)]; run = h < run ? h : run; sfx[KG_SKM_AT(lw, i)] = run; }
     return run;
 }
 
 // ---- scatter, phase 2: windows of one packed word -> descriptors ------------------------------------------------------
-// H / sfx / cmin are indexed by LOCAL word (local word lw covers positions 32*(gw - lw_of_gw) ...): the caller passes the
-// arrays of its block (halo words first) and the local index of the word being processed.  emit(bucket, j0, n, has_pred).
+// H / sfx (transposed, KG_SKM_AT) / cmin are indexed by LOCAL word: the caller passes the arrays of its block (halo words
+// first) and the local index lw of the word being processed.  emit(bucket, j0, n, has_pred).
+__host__ __device__ inline u32 kg_ctz32(u32 x) {       // x != 0
+#ifdef __CUDA_ARCH__
+    return (u32)__ffs((int)x) - 1u;
+#else
+    u32 n = 0;
+    while (!((x >> n) & 1u)) n++;
+    return n;
+#endif
+}
+
+// The walk over the 32 positions only RECORDS where descriptors start (bit masks; their buckets in a small register
+// queue); the descriptors are emitted afterwards, one loop iteration per descriptor.  (Emitting inside the walk made
+// nearly every one of its 32 iterations pay for the emit path -- an atomic and a store -- on behalf of one or two lanes.)
 template <typename E>
 __host__ __device__ inline u32 kg_skm_segment_word(const u64* __restrict__ words, const u32* __restrict__ brk, u32 T, u32 C,
                                                    u32 k, u32 m, u32 nb, u32 gw, const u32* H, const u32* sfx, const u32* cmin,
                                                    u32 lw, u32 kwords, E&& emit) {
+    (void)words;
     if ((u64)gw * 32u >= T) return 0;
     const u32 wlen = k - m + 1u;                                       // m-mers per window
     const u32 mybrk = brk[gw];
@@ -150,46 +164,62 @@ __host__ __device__ inline u32 kg_skm_segment_word(const u64* __restrict__ words
     for (u32 i = 1; i <= kwords + 1u; i++) {
         if (gw < i) break;                                             // position 0 always carries a break bit
         const u32 b = brk[gw - i];
-        if (b) {
-            u32 low = 0;
-            while (!((b >> low) & 1u)) low++;                          // lowest set bit = most recent run start of that word
-            run += low + 1u;
-            break;
-        }
+        if (b) { run += kg_ctz32(b) + 1u; break; }                     // lowest set bit = most recent run start of that word
         run += 32u;
     }
     const u32 jend = T - gw * 32u < 32u ? T - gw * 32u : 32u;
     const u32 base = lw * 32u;                                         // local position of this word's first base
-    u32 n_windows = 0, cur_n = 0, cur_b = 0, cur_j0 = 0, cur_hp = 0, own = 0xFFFFFFFFu;
+    // bit j of vmask = a counted window ends at position j, of smask = a descriptor starts there, of pmask = that window
+    // has a predecessor window in its read; pend = starts not emitted yet, their buckets queued in bq (10 bits each)
+    u32 vmask = 0, smask = 0, pmask = 0, pend = 0, nq = 0, n_windows = 0;
+    u64 bq = 0;
+    auto flush = [&]() {
+        u32 todo = pend, idx = 0;
+        while (todo) {
+            const u32 j = kg_ctz32(todo);
+            todo &= todo - 1u;
+            const u32 stop = (smask | ~vmask) & ~((2u << j) - 1u);     // next start, or first position without a window, above j
+            const u32 end = stop ? kg_ctz32(stop) : 32u;
+            const u32 b = (u32)(bq >> (10u * (nq - 1u - idx))) & 1023u;
+            idx++;
+            emit(b, gw * 32u + j, end - j, (pmask >> j) & 1u);
+            n_windows += end - j;
+        }
+        pend = 0; nq = 0; bq = 0;
+    };
+    u32 own = 0xFFFFFFFFu, prev_b = 0xFFFFFFFFu;
     for (u32 j = 0; j < jend; j++) {
         run = ((mybrk >> (31u - j)) & 1u) ? 1u : run + 1u;
-        const u32 h = H[base + j];
+        const u32 h = H[KG_SKM_AT(lw, j)];
         own = h < own ? h : own;                                       // min over this word's m-mers up to j
         const u32 pos = gw * 32u + j;
         if (run >= k && pos >= C) {
             u32 mv;
             if (j + 1u >= wlen) {                                      // all m-mers of the window end inside this word
                 mv = 0xFFFFFFFFu;
-                for (u32 i = j + 1u - wlen; i <= j; i++) { const u32 v = H[base + i]; mv = v < mv ? v : mv; }
+                for (u32 i = j + 1u - wlen; i <= j; i++) { const u32 v = H[KG_SKM_AT(lw, i)]; mv = v < mv ? v : mv; }
             } else {                                                   // head in earlier words + own prefix
-                const u32 s = base + j + 1u - wlen;                    // local position of the first m-mer end (base + j >= wlen - 1 by halo)
-                mv = sfx[s] < own ? sfx[s] : own;
+                const u32 s = base + j + 1u - wlen;                    // local position of the first m-mer end (>= 0 by the halo)
+                const u32 sv = sfx[KG_SKM_AT(s >> 5, s & 31u)];
+                mv = sv < own ? sv : own;
                 for (u32 cw = (s >> 5) + 1u; cw < lw; cw++) { const u32 v = cmin[cw]; mv = v < mv ? v : mv; }
             }
             const u32 b = kg_min_to_bucket(mv, nb);
-            n_windows++;
-            if (cur_n && b == cur_b) {
-                cur_n++;
-            } else {
-                if (cur_n) emit(cur_b, cur_j0, cur_n, cur_hp);
-                cur_b = b; cur_j0 = pos; cur_n = 1; cur_hp = run > k ? 1u : 0u;
+            if (b != prev_b) {                                         // a descriptor starts here
+                if (nq == 6u) flush();                                 // (rare) queue full: everything pending ends before j
+                smask |= 1u << j;
+                pend |= 1u << j;
+                bq = (bq << 10) | (u64)b;
+                nq++;
+                if (run > k) pmask |= 1u << j;
             }
-        } else if (cur_n) {
-            emit(cur_b, cur_j0, cur_n, cur_hp);
-            cur_n = 0;
+            vmask |= 1u << j;
+            prev_b = b;
+        } else {
+            prev_b = 0xFFFFFFFFu;
         }
     }
-    if (cur_n) emit(cur_b, cur_j0, cur_n, cur_hp);
+    flush();
     return n_windows;
 }
 
@@ -218,8 +248,9 @@ struct KgSkmScatterArgs {
     const u64* words;
     const u32* brk;
     const KgStream* st;
-    u32* cursors;       // [nb + 1] descriptors reserved per bucket region (may run past cap); [nb] = overflow cursor
-    u64* regions;       // nb regions of cap descriptors
+    u32* cursors;       // [(nb * KG_SKM_SUB + 1) * 8]: one reservation counter per (bucket, sub-region), each in its own
+                        // 32-byte sector; the last one is the overflow list's
+    u64* regions;       // nb * KG_SKM_SUB sub-regions of cap descriptors
     u64* ovf;           // overflow list (descriptors whose region was full), ovf_cap entries
     u64* hdr;           // [0] = global ordinal of position 0 of this batch (KgStream::bases_seen), [1] = T
     KgStats* stats;
@@ -241,8 +272,8 @@ __global__ void __launch_bounds__(KG_SKM_TPB) kg_skm_scatter(KgSkmScatterArgs a)
     for (u32 lw = tid; lw < KG_SKM_TPB + halo; lw += KG_SKM_TPB) {
         const long long gc = first + lw;
         u32 mn = 0xFFFFFFFFu;
-        if (gc < (long long)a.nwords) mn = kg_skm_hash_word(a.words, gc, a.m, sH + lw * 32u, sS + lw * 32u);
-        else for (int i = 0; i < 32; i++) { sH[lw * 32u + i] = 0xFFFFFFFFu; sS[lw * 32u + i] = 0xFFFFFFFFu; }
+        if (gc < (long long)a.nwords) mn = kg_skm_hash_word(a.words, gc, a.m, sH, sS, lw);
+        else for (u32 i = 0; i < 32; i++) { sH[KG_SKM_AT(lw, i)] = 0xFFFFFFFFu; sS[KG_SKM_AT(lw, i)] = 0xFFFFFFFFu; }
         sM[lw] = mn;
     }
     __syncthreads();
@@ -253,10 +284,11 @@ __global__ void __launch_bounds__(KG_SKM_TPB) kg_skm_scatter(KgSkmScatterArgs a)
         n_windows = kg_skm_segment_word(a.words, a.brk, T, C, a.k, a.m, a.nb, gw, sH, sS, sM, tid + halo, kwords,
                                         [&](u32 b, u32 j0, u32 n, u32 hp) {
                                             const u64 d = kg_skm_desc(j0, a.src, n, hp, b % a.pl, b / a.pl);
-                                            const u32 idx = atomicAdd(&a.cursors[b], 1u);
-                                            if (idx < a.cap) a.regions[(u64)b * a.cap + idx] = d;
+                                            const u32 r = b * KG_SKM_SUB + (blockIdx.x & (KG_SKM_SUB - 1u));
+                                            const u32 idx = atomicAdd(&a.cursors[r * 8u], 1u);
+                                            if (idx < a.cap) a.regions[(u64)r * a.cap + idx] = d;
                                             else {
-                                                const u32 o = atomicAdd(&a.cursors[a.nb], 1u);
+                                                const u32 o = atomicAdd(&a.cursors[a.nb * KG_SKM_SUB * 8u], 1u);
                                                 if (o < a.ovf_cap) a.ovf[o] = d;
                                                 else a.stats->table_full = 2;   // cannot happen: ovf_cap = every position of a batch
                                             }
@@ -265,27 +297,40 @@ __global__ void __launch_bounds__(KG_SKM_TPB) kg_skm_scatter(KgSkmScatterArgs a)
     KG_WARP_ADD(a.stats, n_windows, input_kmers)
 }
 
-// Where the receiver finds every sender's bucket cursors (local copy) and descriptors (in place: own slot, or a peer's slot
-// mapped over NVLink).
+// dense descriptor counts of a slot, written next to its header where the peers pull them from:
+// counts[r] = descriptors in sub-region r (r < nb * KG_SKM_SUB), counts[nb * KG_SKM_SUB] = descriptors in the overflow list
+__global__ void __launch_bounds__(256) kg_skm_pack_counts(const u32* __restrict__ cursors, u32 nregions, u32 cap, u32 ovf_cap,
+                                                          u32* __restrict__ counts) {
+    const u32 i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < nregions) counts[i] = min(cursors[i * 8u], cap);
+    else if (i == nregions) counts[i] = min(cursors[i * 8u], ovf_cap);
+}
+
+// Where the receiver finds every sender's descriptor counts (local copy) and descriptors (in place: own slot, or a peer's
+// slot mapped over NVLink).
 struct KgSkmPeers {
-    const u32* cursors[64];
+    const u32* counts[64];
     const u64* desc[64];
 };
 
-// Segment table of one round on owner `me`: the descriptors of my partitions, PARTITION-MAJOR across senders (so one
-// insert launch still walks my table region by region), followed by every sender's overflow list (not owner-sorted:
-// the insert skips what belongs to other owners).  seg id = p * world + s for regions, pl * world + s for overflow.
+// Segment table of one round on owner `me`: the descriptors of my partitions, PARTITION-MAJOR across senders and their
+// sub-regions (so one insert launch still walks my table region by region), followed by every sender's overflow list (not
+// owner-sorted: the insert skips what belongs to other owners).
+// seg id = (p * world + s) * KG_SKM_SUB + sub for regions, pl * world * KG_SKM_SUB + s for the overflow lists.
 __global__ void __launch_bounds__(1024) kg_skm_segments(const KgSkmPeers* __restrict__ peers, u32 world, u32 me, u32 pl, u32 nb,
-                                                        u32 cap, u32 ovf_cap, u64* __restrict__ seg_start,
-                                                        const u64** __restrict__ seg_ptr) {
+                                                        u32 cap, u64* __restrict__ seg_start, const u64** __restrict__ seg_ptr) {
     __shared__ u64 sm[1024];
-    const u32 nseg = pl * world + world, tid = threadIdx.x;
+    const u32 nreg = pl * world * KG_SKM_SUB, nseg = nreg + world, tid = threadIdx.x;
     const u32 per = (nseg + 1023u) / 1024u;
     const u32 i0 = tid * per, i1 = min(i0 + per, nseg);
     u64 mine = 0;
     for (u32 i = i0; i < i1; i++) {
-        if (i < pl * world) { const u32 p = i / world, s = i % world; mine += (u64)min(peers->cursors[s][me * pl + p], cap); }
-        else { const u32 s = i - pl * world; mine += (u64)min(peers->cursors[s][nb], ovf_cap); }
+        if (i < nreg) {
+            const u32 sub = i % KG_SKM_SUB, ps = i / KG_SKM_SUB, p = ps / world, s = ps % world;
+            mine += (u64)peers->counts[s][(me * pl + p) * KG_SKM_SUB + sub];
+        } else {
+            mine += (u64)peers->counts[i - nreg][nb * KG_SKM_SUB];
+        }
     }
     sm[tid] = mine;
     __syncthreads();
@@ -299,14 +344,15 @@ __global__ void __launch_bounds__(1024) kg_skm_segments(const KgSkmPeers* __rest
     for (u32 i = i0; i < i1; i++) {
         u64 n;
         const u64* ptr;
-        if (i < pl * world) {
-            const u32 p = i / world, s = i % world;
-            n = (u64)min(peers->cursors[s][me * pl + p], cap);
-            ptr = peers->desc[s] + (u64)(me * pl + p) * cap;
+        if (i < nreg) {
+            const u32 sub = i % KG_SKM_SUB, ps = i / KG_SKM_SUB, p = ps / world, s = ps % world;
+            const u32 r = (me * pl + p) * KG_SKM_SUB + sub;
+            n = (u64)peers->counts[s][r];
+            ptr = peers->desc[s] + (u64)r * cap;
         } else {
-            const u32 s = i - pl * world;
-            n = (u64)min(peers->cursors[s][nb], ovf_cap);
-            ptr = peers->desc[s] + (u64)nb * cap;
+            const u32 s = i - nreg;
+            n = (u64)peers->counts[s][nb * KG_SKM_SUB];
+            ptr = peers->desc[s] + (u64)nb * KG_SKM_SUB * cap;
         }
         seg_start[i] = cur;
         seg_ptr[i] = ptr;
@@ -335,87 +381,97 @@ struct KgSkmInsertArgs {
     u32 k;
 };
 
-#define KG_SKM_CLAIM 4u                 // groups of 32 descriptors a warp claims with one atomic
-
 template <int W, int SINK>
 __global__ void __launch_bounds__(256) kg_skm_insert(KgSkmInsertArgs a) {
     __shared__ u32 sm[8];
+    __shared__ u64 s_desc[8][32];       // the 32 descriptors of the warp's current group
+    __shared__ u32 s_excl[8][33];       // exclusive prefix of their window counts ([32] = total)
     const u64 n_desc = a.seg_start[a.nseg];
-    const u32 lane = threadIdx.x & 31u;
+    const u32 lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
     const KgKGeom g = kg_geom(a.k);
     KgConsume<W, SINK> sink;
     sink.init(a.table, a.bloom);
     for (;;) {
-        // persistent warps pull groups from one global counter: whatever their relative speed, the warps in flight
-        // work at the FRONT of the (partition-major) descriptor array, so the live table region stays L2-resident
+        // Persistent warps pull groups of 32 descriptors (a few hundred windows) from one global counter: whatever their
+        // relative speed, the warps in flight work at the FRONT of the partition-major descriptor array, so the table
+        // region they hit stays L2-resident.  (Claiming 128 descriptors per warp put ~13 M windows = a dozen partitions
+        // in flight and the table went to DRAM for every second probe.)
         u32 claim = 0;
         if (lane == 0) claim = atomicAdd(a.work, 1u);
         claim = __shfl_sync(0xffffffffu, claim, 0);
-        const u64 first = (u64)claim * (KG_SKM_CLAIM * 32u);
+        const u64 first = (u64)claim * 32u;
         if (first >= n_desc) break;
-        // segment of the first descriptor of the claim (one binary search per claim, done redundantly by every lane)
-        u32 seg;
-        {
-            u32 lo = 0, hi = a.nseg;
-            while (hi - lo > 1) { const u32 mid = (lo + hi) >> 1; if (a.seg_start[mid] <= first) lo = mid; else hi = mid; }
-            seg = lo;
+        const u64 i = first + lane;
+        u64 d = 0;
+        u32 n = 0;
+        u32 seg = 0;
+        {   // segment of the group's first descriptor: the same search in every lane (uniform loads), then each lane walks on
+            u32 hi = a.nseg;
+            while (hi - seg > 1) { const u32 mid = (seg + hi) >> 1; if (a.seg_start[mid] <= first) seg = mid; else hi = mid; }
         }
-#pragma unroll 1
-        for (u32 grp = 0; grp < KG_SKM_CLAIM; grp++) {
-            const u64 i = first + (u64)grp * 32u + lane;
-            u64 d = 0;
-            u32 n = 0;
-            if (i < n_desc) {
-                while (seg + 1 < a.nseg && a.seg_start[seg + 1] <= i) seg++;
-                d = __ldcs(a.seg_ptr[seg] + (i - a.seg_start[seg]));
-                n = KG_SKM_OWNER(d) == a.my_rank ? KG_SKM_N(d) : 0u;
-            }
-            // inclusive prefix of the window counts over the warp; windows are then dealt round-robin to the lanes
-            u32 incl = n;
+        if (i < n_desc) {
+            while (a.seg_start[seg + 1] <= i) seg++;  // (i < n_desc = seg_start[nseg]: stops inside the table)
+            d = __ldcs(a.seg_ptr[seg] + (i - a.seg_start[seg]));
+            n = KG_SKM_OWNER(d) == a.my_rank ? KG_SKM_N(d) : 0u;
+        }
+        u32 incl = n;
 #pragma unroll
-            for (int s = 1; s < 32; s <<= 1) { const u32 o = __shfl_up_sync(0xffffffffu, incl, s); if (lane >= (u32)s) incl += o; }
-            const u32 total = __shfl_sync(0xffffffffu, incl, 31);
-#pragma unroll 1
-            for (u32 w0 = 0; w0 < total; w0 += 32u) {
-                const u32 gi = w0 + lane;
-                // smallest lane q with incl[q] > gi
-                u32 q = 0;
+        for (int s = 1; s < 32; s <<= 1) { const u32 o = __shfl_up_sync(0xffffffffu, incl, s); if (lane >= (u32)s) incl += o; }
+        const u32 total = __shfl_sync(0xffffffffu, incl, 31);
+        s_desc[warp][lane] = d;
+        s_excl[warp][lane] = incl - n;
+        if (lane == 31) s_excl[warp][32] = total;
+        __syncwarp();
+        // every lane takes a CONTIGUOUS share of the group's windows: equal work for all lanes however the windows are
+        // spread over the descriptors, and the walk from one descriptor to the next is incremental (no search per window)
+        const u32 per = (total + 31u) >> 5;
+        u32 gi = lane * per;
+        const u32 gend = min(total, gi + per);
+        if (gi < gend) {
+            u32 q = 0;                                  // descriptor holding window gi: largest q with excl[q] <= gi, n[q] > 0
 #pragma unroll
-                for (u32 s = 16; s; s >>= 1) { const u32 v = __shfl_sync(0xffffffffu, incl, (q + s - 1u) & 31u); if (v <= gi) q += s; }
-                q &= 31u;
-                const u32 before = __shfl_sync(0xffffffffu, incl - n, q);
-                const u64 dq = __shfl_sync(0xffffffffu, d, q);
-                if (gi < total) {
-                    const u32 off = gi - before;
-                    const u32 e = KG_SKM_J0(dq) + off;
-                    const u32 srcr = KG_SKM_SRC(dq), part = KG_SKM_PART(dq);
-                    const u64* __restrict__ words = a.src->words[srcr];
-                    KgKmerWindow<W> win;
-                    kg_window_at<W>(words, e, g, win.f);
-                    kg_revcomp<W>(win.f, win.r, g);
-                    const bool fwd = kg_forward_is_canonical<W>(win);
-                    u64 key[W];
+            for (u32 s = 16; s; s >>= 1) if (s_excl[warp][q + s] <= gi) q += s;
+            u64 dq = s_desc[warp][q];
+            u32 e = KG_SKM_J0(dq) + (gi - s_excl[warp][q]);          // end position of window gi
+            u32 next = s_excl[warp][q + 1];                          // first window of the next descriptor
+            const u64* __restrict__ words = a.src->words[KG_SKM_SRC(dq)];
+            for (;;) {
+                KgKmerWindow<W> win;
+                kg_window_at<W>(words, e, g, win.f);
+                kg_revcomp<W>(win.f, win.r, g);
+                const bool fwd = kg_forward_is_canonical<W>(win);
+                u64 key[W];
 #pragma unroll
-                    for (int x = 0; x < W; x++) key[x] = fwd ? win.f[x] : win.r[x];
-                    if (SINK == KG_SINK_BLOOM1 || SINK == KG_SINK_BLOOM2) {
-                        sink.b_lo = __ldg(a.bpart_lo + part);
-                        sink.b_n = __ldg(a.bpart_lo + part + 1) - sink.b_lo;
-                    }
-                    if (SINK != KG_SINK_BLOOM1) {
-                        sink.t_lo = __ldg(a.part_lo + part);
-                        sink.t_n = __ldg(a.part_lo + part + 1) - sink.t_lo;
-                    }
-                    KgOcc occ; occ.word = ~0ULL;
-                    if (SINK != KG_SINK_BLOOM1 && a.table.kaarme) {
-                        const bool hp = off > 0 || KG_SKM_HP(dq);
-                        const u32 c_out = hp ? kg_base_at(words, e - a.k) : 0u;
-                        const u64 gpos = ((u64)srcr << 48) | (a.src->hdr[srcr][0] + (u64)e);
-                        occ = kg_make_occ(gpos, hp, fwd, c_out);
-                    }
-                    sink(key, kg_hash_key<W>(key), occ);
+                for (int x = 0; x < W; x++) key[x] = fwd ? win.f[x] : win.r[x];
+                const u32 part = KG_SKM_PART(dq);
+                if (SINK == KG_SINK_BLOOM1 || SINK == KG_SINK_BLOOM2) {
+                    sink.b_lo = __ldg(a.bpart_lo + part);
+                    sink.b_n = __ldg(a.bpart_lo + part + 1) - sink.b_lo;
+                }
+                if (SINK != KG_SINK_BLOOM1) {
+                    sink.t_lo = __ldg(a.part_lo + part);
+                    sink.t_n = __ldg(a.part_lo + part + 1) - sink.t_lo;
+                }
+                KgOcc occ; occ.word = ~0ULL;
+                if (SINK != KG_SINK_BLOOM1 && a.table.kaarme) {
+                    const u32 srcr = KG_SKM_SRC(dq);
+                    const bool hp = e > KG_SKM_J0(dq) || KG_SKM_HP(dq);
+                    const u32 c_out = hp ? kg_base_at(words, e - a.k) : 0u;
+                    occ = kg_make_occ(((u64)srcr << 48) | (a.src->hdr[srcr][0] + (u64)e), hp, fwd, c_out);
+                }
+                sink(key, kg_hash_key<W>(key), occ);
+                if (++gi == gend) break;
+                if (gi == next) {                                    // on to the next descriptor that holds windows
+                    do { q++; next = s_excl[warp][q + 1]; } while (next == gi);
+                    dq = s_desc[warp][q];
+                    e = KG_SKM_J0(dq);
+                    words = a.src->words[KG_SKM_SRC(dq)];
+                } else {
+                    e++;
                 }
             }
         }
+        __syncwarp();                                               // the group's shared arrays are reused by the next claim
     }
     if (SINK == KG_SINK_TABLE || SINK == KG_SINK_BLOOM2) {
         kg_block_add(sink.n_ins, &a.stats->inserted, sm);

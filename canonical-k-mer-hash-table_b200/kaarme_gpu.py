@@ -69,7 +69,7 @@ EXPORTS = ["kg_abi_version", "kg_strerror", "kg_last_error", "kg_device_count", 
            "kg_host_alloc", "kg_host_free", "kg_comm_unique_id", "kg_comm_init", "kg_pass_begin",
            "kg_stream_begin", "kg_feed", "kg_feed_device", "kg_pass_end", "kg_compact", "kg_export",
            "kg_table_info", "kg_atomic_ceiling", "kg_launch_count", "kg_kaarme_download", "kg_export_text",
-           "kg_kaarme_upload"]
+           "kg_kaarme_upload", "kg_checksum"]
 
 _lib = None
 
@@ -105,6 +105,7 @@ def lib():
         L.kg_kaarme_download.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
         L.kg_export_text.argtypes = [C.c_void_p, C.c_uint64, C.c_int, TEXT_SINK_FN, C.c_void_p]
         L.kg_kaarme_upload.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64]
+        L.kg_checksum.argtypes = [C.c_void_p, C.c_uint64, C.c_int, C.POINTER(C.c_uint64)]
         _lib = L
     return _lib
 
@@ -210,6 +211,12 @@ class Counter:
         st = PassStats()
         self._check(lib().kg_pass_end(self._h, C.byref(st)), "kg_pass_end")
         return st.as_dict()
+
+    def checksum(self, min_abundance=1, count_mode=COUNT_EXACT):
+        """-> (k-mers, sum of counts, sum of g(k-mer), sum of g(k-mer)*count): order-independent, additive over shards."""
+        out = (C.c_uint64 * 4)()
+        self._check(lib().kg_checksum(self._h, min_abundance, count_mode, out), "kg_checksum")
+        return tuple(int(x) for x in out)
 
     def compact(self) -> dict:
         st = CompactStats()

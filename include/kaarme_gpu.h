@@ -199,6 +199,12 @@ int kg_kaarme_download(kg_ctx* ctx, uint64_t* slots, uint64_t* roots);
  * kmer_hash_table.cpp:3848-4058).  Malformed chains are detected while decoding (KG_ECUDA from the export), never
  * followed out of bounds.  Single GPU (world == 1).                                                            */
 int kg_kaarme_upload(kg_ctx* ctx, const uint64_t* slots, uint64_t n_kmers, const uint64_t* roots, uint64_t n_roots);
+/* Order-independent checksum of what kg_export would deliver (same selection: reported count >= min_abundance):
+ * out[0] = k-mers, out[1] = sum of counts, out[2] = sum of g(k-mer), out[3] = sum of g(k-mer) * count (mod 2^64),
+ * g = a 64-bit mix of the key words.  Computed on the device (plain table, or decoded from the compact structure).
+ * The four words ADD over shards, so a sharded run can be compared with a single table without moving the k-mers --
+ * the role sort + pytools/compare_outputs.py:1-33 plays for two output files.                                   */
+int kg_checksum(kg_ctx* ctx, uint64_t min_abundance, int count_mode, uint64_t out[4]);
 /* Table geometry for reports: bytes per slot and slots. */
 int kg_table_info(const kg_ctx* ctx, uint64_t* slots, uint32_t* slot_bytes, uint32_t* key_words);
 

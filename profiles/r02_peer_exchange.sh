@@ -5,8 +5,8 @@ set -u
 N=${1:-2}; OUT=gpurun_out; mkdir -p $OUT
 TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1"
 # parity first: the seven multi-GPU configurations (plain / uneven slices / k=127 / Bloom / partitions), both exchanges
-timeout 300 $TR --master-port 29511 tests/multigpu_check.py > $OUT/r02_multigpu_nccl.log 2>&1; echo "rc=$?" >> $OUT/r02_multigpu_nccl.log
-KG_PEER=1 timeout 300 $TR --master-port 29512 tests/multigpu_check.py > $OUT/r02_multigpu_peer.log 2>&1; echo "rc=$?" >> $OUT/r02_multigpu_peer.log
+timeout 300 $TR --master-port 29511 tests/multigpu_worker.py > $OUT/r02_multigpu_nccl.log 2>&1; echo "rc=$?" >> $OUT/r02_multigpu_nccl.log
+KG_PEER=1 timeout 300 $TR --master-port 29512 tests/multigpu_worker.py > $OUT/r02_multigpu_peer.log 2>&1; echo "rc=$?" >> $OUT/r02_multigpu_peer.log
 grep -E "multigpu|rc=|Error|error" $OUT/r02_multigpu_nccl.log | tail -9
 grep -E "multigpu|rc=|Error|error" $OUT/r02_multigpu_peer.log | tail -9
 timeout 120 bash tests/multigpu_cli_check.sh > $OUT/r02_multigpu_cli.log 2>&1; tail -8 $OUT/r02_multigpu_cli.log

@@ -323,6 +323,12 @@ int kg_table_info(const kg_ctx* c, uint64_t* slots, uint32_t* slot_bytes, uint32
     return KG_OK;
 }
 int kg_atomic_ceiling(int, uint64_t, uint64_t, int, double*) { return KG_ECUDA; }
+int kg_checksum(kg_ctx* c, uint64_t min_ab, int, uint64_t out[4]) {      // the CLI does not call it; present for the symbol set
+    if (!c || !out) return KG_EBADARG;
+    out[0] = out[1] = out[2] = out[3] = 0;
+    for (auto& kv : owned(c)) if (min_ab && kv.second >= min_ab) { out[0]++; out[1] += kv.second; }
+    return KG_OK;
+}
 int kg_launch_count(const kg_ctx* c, uint64_t* n) { if (!c || !n) return KG_EBADARG; *n = c->launches; return KG_OK; }
 
 }  // extern "C"

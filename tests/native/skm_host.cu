@@ -73,8 +73,8 @@ int main() {
         for (u32 lw = 0; lw < KG_SKM_TPB + halo; lw++) {
             const long long gc = first + lw;
             u32 mn = 0xFFFFFFFFu;
-            if (gc < (long long)nwords) mn = kg_skm_hash_word(words.data(), gc, m, H.data() + lw * 32, S.data() + lw * 32);
-            else for (int i = 0; i < 32; i++) { H[lw * 32 + i] = 0xFFFFFFFFu; S[lw * 32 + i] = 0xFFFFFFFFu; }
+            if (gc < (long long)nwords) mn = kg_skm_hash_word(words.data(), gc, m, H.data(), S.data(), lw);
+            else for (u32 i = 0; i < 32; i++) { H[KG_SKM_AT(lw, i)] = 0xFFFFFFFFu; S[KG_SKM_AT(lw, i)] = 0xFFFFFFFFu; }
             M[lw] = mn;
         }
         for (u32 tid = 0; tid < KG_SKM_TPB; tid++) {

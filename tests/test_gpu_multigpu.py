@@ -1,0 +1,66 @@
+"""Sharded path on real hardware (`-m gpu`, skipped on a box with fewer than two B200s): spawns torchrun over
+tests/multigpu_worker.py -- one process per GPU, NCCL + peer-mapped batch slots -- and over the CLI's own sharding
+(`kaarme --gpus N`, one host thread per GPU).  The reference is a single process on a single table (main.cpp:442-536),
+so the check is its check: the union of the shard outputs equals the single-table count, bit for bit."""
+import importlib
+import json
+import os
+import subprocess
+import sys
+
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+EXE = os.path.join(ROOT, "canonical-k-mer-hash-table_b200", "kaarme")
+
+
+def n_gpus():
+    kg = importlib.import_module("canonical-k-mer-hash-table_b200")
+    return kg.device_count()
+
+
+def worlds():
+    n = n_gpus()
+    return [w for w in (2, 4, 8) if w <= n]
+
+
+def test_sharded_counts_equal_single_table_counts():
+    ws = worlds()
+    if not ws:
+        pytest.skip("needs at least two B200s")
+    for i, w in enumerate(ws):
+        p = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={w}",
+                            "--master-addr", "127.0.0.1", "--master-port", str(29611 + i), os.path.join(ROOT, "tests", "multigpu_worker.py")],
+                           stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=900)
+        lines = [x for x in p.stdout.splitlines() if x.startswith("multigpu ")]
+        print("\n".join(lines))
+        res = [x for x in p.stdout.splitlines() if x.startswith("MULTIGPU_RESULT ")]
+        assert p.returncode == 0 and res, p.stdout[-4000:]
+        r = json.loads(res[-1][len("MULTIGPU_RESULT "):])
+        assert r["world"] == w and r["failures"] == 0 and len(r["cases"]) >= 12 and all(c["ok"] for c in r["cases"])
+
+
+@pytest.mark.parametrize("k,mode,extra", [(21, 0, ["-s", "400000"]), (51, 0, ["-s", "400000"]), (127, 0, ["-s", "400000"]),
+                                          (51, 2, ["-s", "400000"]), (51, 2, ["-b", "-u", "200000"])])
+def test_cli_gpus_n_equals_one_gpu(k, mode, extra, tmp_path):
+    """`kaarme --gpus N` (one host thread per GPU in ONE process: peer access instead of IPC) writes the same lines as
+    one GPU, in -m 0 and in the default -m 2 (per-shard Kaarme structures decoded on export)"""
+    ws = worlds()
+    if not ws:
+        pytest.skip("needs at least two B200s")
+    inp = os.path.join(GOLDEN, "g5_long.fasta")
+    outs = {}
+    for w in [1] + ws:
+        out = tmp_path / f"o{w}.txt"
+        p = subprocess.run([EXE, inp, str(k), "-m", str(mode), "-a", "2", "-t", "8", "--gpus", str(w), "--batch-mb", "1", "-o", str(out)] + extra,
+                           stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=300)
+        assert p.returncode == 0, p.stdout[-2000:] + p.stderr[-2000:]
+        outs[w] = sorted(open(out, "rb").read().splitlines())
+        if mode == 2 and w > 1:
+            assert p.stdout.count("  shard ") == w
+    assert len(outs[1]) > 1000
+    for w in ws:
+        assert outs[w] == outs[1], f"--gpus {w} differs from one GPU"
