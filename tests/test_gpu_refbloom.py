@@ -1,9 +1,9 @@
-"""NOT collected by pytest's default pattern on purpose (run it explicitly: `pytest tests/experimental_refbloom_gpu.py`).
-
-GPU checks of the bit-exact Bloom emulation mode (KG_CFG_REFERENCE_BLOOM, csrc/kg_refbloom.cuh), which was written after
-round 1's GPU budget was spent and has not run on hardware yet.  Expected: the reference's single-worker numbers, bit for
-bit -- new_in_first, new_in_second, table size (golden.json holds them for the Bloom cases, minted from the reference
-binary with one worker) and the exact -a 1 output including its false positives (the oracle's sequential restatement)."""
+"""GPU checks of the bit-exact Bloom emulation mode (KG_CFG_REFERENCE_BLOOM, csrc/kg_refbloom.cuh).
+Expected: the reference's single-worker numbers, bit for bit -- new_in_first, new_in_second, table size (golden.json
+holds them for the Bloom cases, minted from the reference binary with one worker) and the exact -a 1 output including
+its false positives (the oracle's sequential restatement of double_bloomfilter.hpp:371-413 and main.cpp:454,472).
+First run on hardware in round 2 (profiles/r02_call1_gpu_tests.txt): 17 of 18 cases matched; the 18th asks for a table
+the reference itself overflows (see test_admitted_set_equals_sequential_semantics)."""
 import importlib
 import json
 import os
@@ -53,6 +53,14 @@ def test_admitted_set_equals_sequential_semantics(oracle, k, unique, fpr, batch_
     restatement of both passes (count_bloom); small batches put window ordinals across many batches"""
     data = _read("g5_long.fasta")
     want, st = oracle.count_bloom(data, k, unique, fpr)
+    if want.n > st.table_slots:
+        # -u far below the real number of distinct k-mers: the filters saturate, nearly everything is admitted, but the
+        # table is sized 2 x new_in_second (main.cpp:454), which only counts insertions that still set a fresh bit.  The
+        # reference prints "Hash table is full" and writes a partial file (parallel_parser.hpp:742-746); here the pass
+        # reports it.
+        with pytest.raises(kg.TableFull):
+            run(data, k, unique, fpr, batch_bytes=batch_bytes)
+        return
     b, s, keys, counts = run(data, k, unique, fpr, batch_bytes=batch_bytes)
     assert (b["new_in_first"], b["new_in_second"]) == (st.new_in_first, st.new_in_second)
     assert s["table_slots"] == st.table_slots
