@@ -186,8 +186,16 @@ def join_u64(parts):
 
 
 # ---- main ------------------------------------------------------------------------------------------------------
+def trace(msg):
+    if os.environ.get("KAARME_BENCH_TRACE"):
+        print(f"[bench rank {os.environ.get('RANK', '0')}] {msg}", file=sys.stderr, flush=True)
+
+
 def main():
     args = parse_args()
+    if os.environ.get("KAARME_BENCH_TRACE"):
+        import faulthandler
+        faulthandler.dump_traceback_later(int(os.environ["KAARME_BENCH_TRACE"]), exit=False)
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -259,8 +267,10 @@ def main():
         return step(lambda: ctr.feed_device(fasta.data_ptr(), fasta.numel()))
 
     # ---- device-resident metric -------------------------------------------------------------------------------
+    trace("context ready, warm-up")
     for _ in range(args.warmup):
         st = step_device()
+        trace("warm-up step done")
     assert st["input_kmers"] == meta["input_kmers"], (st["input_kmers"], meta["input_kmers"])
     launches0 = ctr.launch_count()
     sampler = ClockSampler(local_rank)
@@ -276,6 +286,7 @@ def main():
         insert_ms += st["insert_ms"]
         insert_launches += st["insert_launches"]
     barrier()
+    trace("timed steps done")
     wall = time.perf_counter() - t0
     clocks = sampler.stop()
     launches = ctr.launch_count() - launches0
@@ -310,6 +321,7 @@ def main():
         if world > 1:
             dist.all_reduce(te, op=dist.ReduceOp.MAX)
         assert st2["input_kmers"] == meta["input_kmers"]
+        trace("e2e done")
         import ctypes
         e2e = {"value": total_kmers * args.steps / te.item(), "unit": UNIT,
                "h2d_bytes_per_step": int(fasta.numel()) * world * (2 if args.bloom else 1),
@@ -349,6 +361,7 @@ def main():
                       "match": sharded == ref and sharded[1] == parts[8],
                       "how": "kg_checksum of every shard, added; against ONE table filled from all ranks' reads by kg_count_kernel on rank 0"}
             assert verify["match"], verify
+    trace("verify done")
     if world > 1:
         dist.barrier()
 

@@ -140,6 +140,7 @@ struct kg_ctx {
     uint64_t round = 0;
     u32* d_work = nullptr;              // work counter of the persistent insert kernel
     u32 insert_grid = 148 * 8;          // resident blocks of the persistent insert kernel (SMs x blocks/SM)
+    int insert_occ = 1;                 // KG_INSERT_OCC: register budget of kg_skm_insert (1 = unconstrained, 6 = six blocks per SM)
     // bit-exact emulation of the reference's double Bloom filter (kg_refbloom.cuh)
     bool ref_bloom = false;
     KgRefBloom rb{nullptr, nullptr, 0, 0, 0};
@@ -156,6 +157,18 @@ struct kg_ctx {
 };
 
 static thread_local std::string g_err;
+
+// KG_TRACE=1: progress of the collective steps on stderr (which call does a hung multi-GPU run sit in?)
+static bool kg_trace_on() { static const bool on = getenv("KG_TRACE") != nullptr; return on; }
+#define KG_TRACE(ctx, ...)                                                                     \
+    do {                                                                                       \
+        if (kg_trace_on()) {                                                                   \
+            fprintf(stderr, "[kg rank %d/%d] ", (ctx)->cfg.rank, (ctx)->cfg.world);            \
+            fprintf(stderr, __VA_ARGS__);                                                      \
+            fprintf(stderr, "\n");                                                             \
+            fflush(stderr);                                                                    \
+        }                                                                                      \
+    } while (0)
 
 // NCCL is resolved with dlopen at first use instead of a link-time dependency: inside a Python process torch
 // has already loaded its own (newer) libnccl.so.2, and a DT_NEEDED on the system copy would either shadow it
@@ -415,6 +428,7 @@ extern "C" int kg_create(const kg_config* cfg, kg_ctx** out) {
     c->cfg = *cfg;
     c->insert_grid = (u32)prop.multiProcessorCount * 8u;
     if (const char* e = getenv("KG_INSERT_GRID")) c->insert_grid = (u32)atoi(e) * (u32)prop.multiProcessorCount;
+    if (const char* e = getenv("KG_INSERT_OCC")) c->insert_occ = atoi(e);
     if (const char* e = getenv("KG_PARSE_TMA")) c->parse_tma = atoi(e) != 0;
     if (const char* e = getenv("KG_FEED_PREFETCH")) c->feed_prefetch = atoi(e) != 0;
     c->W = (int)((cfg->k + 31) / 32);
@@ -481,15 +495,15 @@ extern "C" int kg_create(const kg_config* cfg, kg_ctx** out) {
         bloom_params(cfg->expected_unique, cfg->fpr, &m, &nh);
         if (nh < 1) nh = 1;
         if (nh > 16) nh = 16;
-        // every shard holds m/world bits per filter (rounded up to whole 64-bit words, at least one)
+        // every shard holds m/world bits per filter (rounded up to whole 256-bit blocks, at least one)
         uint64_t m_local = (m + (uint64_t)cfg->world - 1) / (uint64_t)cfg->world;
-        uint64_t nwords = (m_local + 63) / 64;
-        if (nwords == 0) nwords = 1;
+        uint64_t nblocks = (m_local + 255) / 256;
+        if (nblocks == 0) nblocks = 1;
         c->bloom_m = m;
-        c->bloom.nblocks = nwords;
+        c->bloom.nblocks = nblocks;
         c->bloom.nh = nh;
         c->bloom.world = (u32)cfg->world;
-        c->bloom_bytes = nwords * 16;                 // [F1 word][F2 word] pairs: 2m bits, as the reference's interleaved array
+        c->bloom_bytes = nblocks * 64;                // [F1 block][F2 block] pairs: 2m bits, as the reference's interleaved array
         KG_TRY(cudaMalloc(&c->bloom.bits, c->bloom_bytes));
     }
     // partitions: 0 = choose per pass from the table / filter size, 1 = never bucket on one GPU, > 1 = as given
@@ -573,7 +587,9 @@ extern "C" int kg_comm_init(kg_ctx* c, const void* id, int rank, int world) {
     ncclUniqueId uid;
     memcpy(&uid, id, sizeof(uid));
     if (!kg_nccl().ok) { c->err = "libnccl.so.2 could not be loaded"; return KG_ENCCL; }
+    KG_TRACE(c, "comm_init: ncclCommInitRank");
     KG_NCCL(c, kg_nccl().CommInitRank(&c->comm, world, uid, rank));
+    KG_TRACE(c, "comm_init: slots (%zu bytes each)", c->skm_slab_bytes);
     { int rc = alloc_slots(c); if (rc) return rc; }
     KgPeerHandle mine;
     memset(&mine, 0, sizeof(mine));
@@ -592,8 +608,10 @@ extern "C" int kg_comm_init(kg_ctx* c, const void* id, int rank, int world) {
     struct Guard { char** p; ~Guard() { cudaFree(*p); } } guard{&d_all};
     KG_CUDA(c, cudaMemset(d_all, 0, all.size()));
     KG_CUDA(c, cudaMemcpy(d_all + (size_t)rank * KG_PEER_HANDLE_BYTES, &mine, sizeof(mine), cudaMemcpyHostToDevice));
+    KG_TRACE(c, "comm_init: all-gather of the slot handles");
     KG_NCCL(c, kg_nccl().AllGather(d_all + (size_t)rank * KG_PEER_HANDLE_BYTES, d_all, KG_PEER_HANDLE_BYTES, ncclChar, c->comm, c->s_insert));
     KG_CUDA(c, cudaStreamSynchronize(c->s_insert));
+    KG_TRACE(c, "comm_init: mapping the peers' slots");
     KG_CUDA(c, cudaMemcpy(all.data(), d_all, all.size(), cudaMemcpyDeviceToHost));
     for (int r = 0; r < world; r++) {
         if (r == rank) continue;
@@ -622,7 +640,9 @@ extern "C" int kg_comm_init(kg_ctx* c, const void* id, int rank, int world) {
             KG_CUDA(c, cudaMalloc(&s.r_buf[r], KG_SKM_META + c->skm_words_bytes));
         }
     }
-    return publish_slot_tables(c);
+    { int rc = publish_slot_tables(c); if (rc) return rc; }
+    KG_TRACE(c, "comm_init: done");
+    return KG_OK;
 }
 
 // Decide how the coming pass buckets its batches.  region_bytes = what the inserts of this pass hit at random (count
@@ -671,6 +691,7 @@ extern "C" int kg_pass_begin(kg_ctx* c, int pass) {
     if (pass == KG_PASS_COUNT && c->cfg.use_bloom && !c->bloom_done) { c->err = "count pass before Bloom pass"; return KG_EBADARG; }
     if (c->cfg.world > 1 && !c->comm) { c->err = "world > 1 needs kg_comm_init first"; return KG_EBADARG; }
     KG_CUDA(c, cudaSetDevice(c->cfg.device));
+    KG_TRACE(c, "pass_begin %d", pass);
     c->pass = pass;
     c->stream_open = false;
     c->ev_used = 0;
@@ -799,16 +820,23 @@ static int current_sink(const kg_ctx* c) {
     return c->pass == KG_PASS_BLOOM ? KG_SINK_BLOOM1 : (c->cfg.use_bloom ? KG_SINK_BLOOM2 : KG_SINK_TABLE);
 }
 
-template <int W>
-static void launch_skm_insert(kg_ctx* c, const KgSkmInsertArgs& a, int sink) {
+template <int W, int MINB>
+static void launch_skm_insert_b(kg_ctx* c, const KgSkmInsertArgs& a, int sink) {
     const u32 grid = c->insert_grid;     // persistent: SMs x resident blocks
     switch (sink) {
-        case KG_SINK_TABLE: kg_skm_insert<W, KG_SINK_TABLE><<<grid, 256, 0, c->s_insert>>>(a); break;
-        case KG_SINK_BLOOM1: kg_skm_insert<W, KG_SINK_BLOOM1><<<grid, 256, 0, c->s_insert>>>(a); break;
-        case KG_SINK_BLOOM2: kg_skm_insert<W, KG_SINK_BLOOM2><<<grid, 256, 0, c->s_insert>>>(a); break;
+        case KG_SINK_TABLE: kg_skm_insert<W, KG_SINK_TABLE, MINB><<<grid, 256, 0, c->s_insert>>>(a); break;
+        case KG_SINK_BLOOM1: kg_skm_insert<W, KG_SINK_BLOOM1, MINB><<<grid, 256, 0, c->s_insert>>>(a); break;
+        case KG_SINK_BLOOM2: kg_skm_insert<W, KG_SINK_BLOOM2, MINB><<<grid, 256, 0, c->s_insert>>>(a); break;
         default: break;
     }
     c->launches++;
+}
+// two register budgets of the same kernel: as many registers as it wants (MINB = 1), or capped for six resident blocks
+// per SM; KG_INSERT_OCC selects (measured in profiles/)
+template <int W>
+static void launch_skm_insert(kg_ctx* c, const KgSkmInsertArgs& a, int sink) {
+    if (c->insert_occ >= 6) launch_skm_insert_b<W, 6>(c, a, sink);
+    else launch_skm_insert_b<W, 1>(c, a, sink);
 }
 
 // One round of the minimizer-bucketed path (collective when world > 1; every rank issues the same sequence).
@@ -824,6 +852,7 @@ static int skm_round(kg_ctx* c, bool have_batch, bool want_sum) {
     const int b = (int)(c->round & 1);
     SkmSlot& s = c->slot[b];
     const int world = c->cfg.world, me = c->cfg.rank;
+    if (world > 1) KG_TRACE(c, "round %llu: %s", (unsigned long long)c->round, have_batch ? "batch" : "no batch");
     if (!have_batch) {
         KG_CUDA(c, cudaStreamWaitEvent(c->s_compute, s.ev_free, 0));
         KG_CUDA(c, cudaMemsetAsync(s.counts, 0, sizeof(u32) * (c->nb * KG_SKM_SUB + 1), c->s_compute));
@@ -1099,6 +1128,7 @@ extern "C" int kg_pass_end(kg_ctx* c, kg_pass_stats* out) {
             int rc = skm_round(c, false, true);
             if (rc) return rc;
             KG_CUDA(c, cudaStreamSynchronize(c->s_insert));
+            KG_TRACE(c, "pass_end: round %llu had %u ranks with a batch", (unsigned long long)c->round - 1, c->h_round_sum[0]);
             if (c->h_round_sum[0] == 0) break;
         }
     }

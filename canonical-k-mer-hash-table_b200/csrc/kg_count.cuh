@@ -19,59 +19,87 @@ enum KgSink : int {
     KG_SINK_BLOOM2 = 2   // Bloom pass 2: insert only if F2 admits
 };
 
-// Word-blocked double Bloom filter.  Filter bit h of the reference (double_bloomfilter.hpp:303-368: bit 2h = filter
-// 1, bit 2h+1 = filter 2 of one interleaved array) becomes: all nh bit positions of a k-mer fall into ONE 64-bit word
-// per filter, the two words sit side by side [F1 word][F2 word] (16 B, one sector).  m = bits per filter
-// (main.cpp:404-410), nwords = m / 64.
-// Why one word: a single atomicOr then is an exact, atomic test-and-set of the whole k-mer.  Of any number of
-// concurrent occurrences of a k-mer exactly one sees "not all bits were set" -- no false negative is possible and
-// new_in_first / new_in_second are exact without the reference's race heuristic ("a bit was set by someone else
-// meanwhile => also put it into filter 2", :401-411), which with ~300k threads working on one L2-resident filter
-// region fired for unrelated k-mers and inflated the false-positive rate to 2.6 % (a 256-bit-block version of this
-// filter; profiles/r01_fullsize_reference_parity.txt shows the admitted singletons).
+// Blocked double Bloom filter.  Filter bit h of the reference (double_bloomfilter.hpp:303-368: bit 2h = filter 1, bit
+// 2h+1 = filter 2 of one interleaved array) becomes: all nh bit positions of a k-mer fall into ONE 256-bit block per filter,
+// and the two blocks sit side by side [F1: 4 words][F2: 4 words] (64 B, two sectors).  m = bits per filter
+// (main.cpp:404-410), nblocks = m / 256, total 2m bits as in the reference.
+// Why 256 bits: the false-positive rate of a blocked filter grows as the blocks shrink (a block holding more k-mers than
+// average is fuller than average).  Measured against the reference's 2 028 admitted singletons on C3 (-u 8e7, 56 M distinct
+// 31-mers): 64-bit blocks admitted 27 461 (13.5x), the model gives 5.0x for 128-bit and 2.6x for 256-bit blocks.
+// Exactness: pass 1 must decide "first / second / later occurrence" atomically per k-mer, or two concurrent first
+// occurrences both believe they are first and the k-mer never reaches filter 2 (a false NEGATIVE; the reference papers over
+// this with "a bit was set by someone else meanwhile => also put it into filter 2", double_bloomfilter.hpp:401-411, which on
+// a GPU fires for unrelated k-mers all the time).  No atomic spans 256 bits, so bit 255 of the F1 block is a LOCK: the
+// test-and-set of both filters runs under it.  Occurrences of k-mers already in filter 2 (most of them at coverage >= 3)
+// never take the lock: an unlocked look at F2 can at worst see a half-written block and take the slow path.
 struct KgBloom {
-    u64* bits;     // nwords * 2 words: [F1][F2] pairs
-    u64 nblocks;   // nwords
+    u64* bits;     // nblocks * 8 words: [F1 x4][F2 x4]
+    u64 nblocks;   // 256-bit blocks per filter
     u32 nh;        // ceil(h) (main.cpp:417)
-    u32 world;     // shards (the word index uses the in-shard part of the hash)
+    u32 world;     // (unused since placement went by partition; kept for the struct layout)
 };
+#define KG_BLOOM_LOCK 0x8000000000000000ULL   // bit 63 of F1 word 3 = bit 255 of the block; never a k-mer's position
 
-// the nh bit positions of a k-mer inside its 64-bit word (6 hash bits each)
-__device__ __forceinline__ u64 kg_bloom_mask(u64 h, u32 nh) {
+// the nh bit positions of a k-mer inside its 256-bit block (positions 0..254), as four word masks
+__device__ __forceinline__ void kg_bloom_mask(u64 h, u32 nh, u64 (&m)[4]) {
     u64 g = kg_fmix64(h ^ 0xA24BAED4963EE407ULL);
-    u64 mask = 0;
+    m[0] = m[1] = m[2] = m[3] = 0;
     for (u32 i = 0; i < nh; i++) {
-        if (i == 10) g = kg_fmix64(g + 0x9FB21C651E98DF25ULL);   // 10 probes per 64-bit draw
-        mask |= 1ULL << ((g >> (6 * (i % 10))) & 63ULL);
+        if (i == 8) g = kg_fmix64(g + 0x9FB21C651E98DF25ULL);    // 8 positions per 64-bit draw
+        const u32 pos = (u32)((((g >> (8 * (i & 7u))) & 255ULL) * 255ULL) >> 8);   // 0..254
+        const u64 bit = 1ULL << (pos & 63u);
+        const u32 w = pos >> 6;
+        m[0] |= w == 0 ? bit : 0ULL; m[1] |= w == 1 ? bit : 0ULL; m[2] |= w == 2 ? bit : 0ULL; m[3] |= w == 3 ? bit : 0ULL;
     }
-    return mask;
 }
-// word index = range partition of the in-shard hash (like the table slot), so a bucket of the partitioned path
-// touches one contiguous region of the filter; the bit positions inside the word come from an independent mix
-__device__ __forceinline__ u64 kg_bloom_block(u64 h, u64 nwords, u32 world) {
-    return __umul64hi(kg_local_hash(h, world), nwords);
+__device__ __forceinline__ u64 kg_atom_or_acquire(u64* p, u64 v) {
+    u64 old;
+    asm volatile("atom.acquire.gpu.global.or.b64 %0, [%1], %2;" : "=l"(old) : "l"(p), "l"(v) : "memory");
+    return old;
+}
+__device__ __forceinline__ void kg_red_and_release(u64* p, u64 v) {
+    asm volatile("red.release.gpu.global.and.b64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ bool kg_bloom_has(const u64* blk, const u64 (&m)[4]) {
+    u64 a, b, c, d;
+    kg_ld_v2(blk, a, b);
+    kg_ld_v2(blk + 2, c, d);
+    return ((a & m[0]) == m[0]) & ((b & m[1]) == m[1]) & ((c & m[2]) == m[2]) & ((d & m[3]) == m[3]);
 }
 
 // pass 1 (insertion_process, double_bloomfilter.hpp:371-413): in F2 -> done; in F1 -> into F2; else into F1
 __device__ __forceinline__ void kg_bloom_insert(const KgBloom& bf, u64 h, u64 block, u32& new1, u32& new2) {
-    const u64 mask = kg_bloom_mask(h, bf.nh);
-    u64* w = bf.bits + block * 2;
-    u64 f1, f2;
-    kg_ld_v2(w, f1, f2);
-    if ((f2 & mask) == mask) return;                              // already in the second filter
-    if ((f1 & mask) != mask) {
-        const u64 old1 = atomicOr(w, mask);                       // exact test-and-set of the whole k-mer
-        if ((old1 & mask) != mask) { new1++; return; }            // I am its first occurrence
+    u64 m[4];
+    kg_bloom_mask(h, bf.nh, m);
+    u64* blk = bf.bits + block * 8;
+    if (kg_bloom_has(blk + 4, m)) return;                             // already in the second filter (no lock needed)
+    bool done = false;
+    while (!done) {                                                  // (the lock holder finishes inside its own iteration)
+        if ((kg_atom_or_acquire(blk + 3, KG_BLOOM_LOCK) & KG_BLOOM_LOCK) == 0) {
+            u64* dst = blk;                                          // where the k-mer goes: F1, else F2, else nowhere
+            u32* counter = &new1;
+            if (kg_bloom_has(blk, m)) {
+                dst = blk + 4; counter = &new2;
+                if (kg_bloom_has(blk + 4, m)) dst = nullptr;
+            }
+            if (dst) {
+                (*counter)++;
+#pragma unroll
+                for (int i = 0; i < 4; i++) if (m[i]) atomicOr(dst + i, m[i]);   // (RED: F1 word 3 also carries the lock bit)
+            }
+            kg_red_and_release(blk + 3, ~KG_BLOOM_LOCK);
+            done = true;
+        }
     }
-    const u64 old2 = atomicOr(w + 1, mask);
-    if ((old2 & mask) != mask) new2++;                            // first to complete it in filter 2
 }
 
 // pass 2 admission (second_contains, double_bloomfilter.hpp:319-337; parallel_parser.hpp:2021-2026)
 __device__ __forceinline__ bool kg_bloom_admits(const KgBloom& bf, u64 h, u64 block) {
-    const u64 mask = kg_bloom_mask(h, bf.nh);
-    const u64 f2 = __ldg(bf.bits + block * 2 + 1);
-    return (f2 & mask) == mask;
+    u64 m[4];
+    kg_bloom_mask(h, bf.nh, m);
+    const ulonglong2* f2 = reinterpret_cast<const ulonglong2*>(bf.bits + block * 8 + 4);
+    const ulonglong2 lo = __ldg(f2), hi = __ldg(f2 + 1);
+    return ((lo.x & m[0]) == m[0]) & ((lo.y & m[1]) == m[1]) & ((hi.x & m[2]) == m[2]) & ((hi.y & m[3]) == m[3]);
 }
 
 struct KgCountArgs {

@@ -247,6 +247,60 @@ __device__ __forceinline__ u64 kg_table_add_packed(const KgTable& t, const u64 (
     return state == KG_PROBE_FAIL ? ~0ULL : (u64)(p - t.slots) >> 1;
 }
 
+// ---- one probe at a time (the bucketed insert, kg_skm.cuh) --------------------------------------------------------------
+// kg_probe_step looks at ONE slot.  FOUND / NEW: the occurrence is counted, p is the k-mer's slot.  SEARCH: not decided
+// yet -- p has moved on to the next slot, or stays where it is when the slot is being written by somebody else right now
+// (no spinning: the caller parks the key in its warp's queue and comes back with a full warp of such keys).
+template <int W>
+__device__ __forceinline__ int kg_probe_step(const KgTable& t, const u64 (&key)[W], u64*& p) {
+    if constexpr (W == 2) {
+        if (t.packed_tb) {
+            const u32 tb = t.packed_tb;
+            const u64 keymask = (1ULL << tb) - 1, one = 1ULL << tb;
+            u64 w0, w1;
+            kg_ld_v2(p, w0, w1);
+            if ((w0 | w1) == 0) {
+                kg_cas128(p, 0, 0, one | key[0], key[1], w0, w1);     // w0, w1 = what was there
+                if ((w0 | w1) == 0) return KG_PROBE_NEW;
+            }
+            if ((w0 & keymask) == key[0] && w1 == key[1]) {
+                if ((w0 >> tb) < ((~0ULL) >> tb) - (u64)KG_COUNT_MARGIN) kg_red_add_u64(p, one);
+                return KG_PROBE_FOUND;
+            }
+            p += 2;
+            if (p == t.slots + t.nslots * 2) p = t.slots;
+            return KG_PROBE_SEARCH;
+        }
+    }
+    u64 meta, k0 = 0;
+    if (W == 1) kg_ld_v2(p, meta, k0);                 // one aligned 16-byte access: key word 0 comes with a published meta
+    else meta = kg_ld_acquire_u64(p);
+    const u32 m = (u32)meta;
+    if (m == 0) {
+        if (atomicCAS((u32*)p, 0u, KG_LOCKED) == 0u) {
+#pragma unroll
+            for (int i = 0; i < W; i++) kg_st_u64(p + 1 + i, key[i]);
+            kg_st_release_u32(p, 1u);
+            return KG_PROBE_NEW;
+        }
+        return KG_PROBE_SEARCH;                        // claimed by somebody else this instant: look again later
+    }
+    if (m == KG_LOCKED) return KG_PROBE_SEARCH;        // being written: look again later
+    if (W != 1) k0 = kg_ld_u64(p + 1);
+    bool same = (k0 == key[0]);
+    if (same) {
+#pragma unroll
+        for (int i = 1; i < W; i++) same = same && (kg_ld_u64(p + 1 + i) == key[i]);
+    }
+    if (same) {
+        if (m < 0xFFFFFFFFu - KG_COUNT_MARGIN) atomicAdd((u32*)p, 1u);
+        return KG_PROBE_FOUND;
+    }
+    p += t.stride;
+    if (p == t.slots + t.nslots * t.stride) p = t.slots;
+    return KG_PROBE_SEARCH;
+}
+
 // read-only lookup starting at `slot` (compaction / decode); returns slot or ~0
 template <int W>
 __device__ __forceinline__ u64 kg_table_find(const KgTable& t, const u64 (&key)[W], u64 slot) {

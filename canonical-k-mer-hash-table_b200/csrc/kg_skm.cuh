@@ -381,16 +381,79 @@ struct KgSkmInsertArgs {
     u32 k;
 };
 
-template <int W, int SINK>
-__global__ void __launch_bounds__(256) kg_skm_insert(KgSkmInsertArgs a) {
+// Probe queue: unresolved probes of a warp wait in shared memory until 32 of them are together.  A probe sequence of a
+// k-mer takes 1.4 steps on average but 4+ for the unluckiest of 32 lanes; looping per window until every lane is done ran
+// the probe code at a third of a warp's width (45 % of this kernel's instructions).  Instead every window gets ONE probe
+// with the whole warp; what is not decided is parked -- key, next slot, probes so far, occurrence record -- and the queue is
+// drained 32 entries at a time, again one probe each at full width.
+#define KG_SKM_QCAP 64u
+
+template <int W, int SINK, int MINB>
+__global__ void __launch_bounds__(256, MINB) kg_skm_insert(KgSkmInsertArgs a) {
     __shared__ u32 sm[8];
     __shared__ u64 s_desc[8][32];       // the 32 descriptors of the warp's current group
     __shared__ u32 s_excl[8][33];       // exclusive prefix of their window counts ([32] = total)
+    __shared__ u64 s_qkey[SINK == KG_SINK_BLOOM1 ? 1 : 8][SINK == KG_SINK_BLOOM1 ? 1 : KG_SKM_QCAP][W];
+    __shared__ u64 s_qptr[SINK == KG_SINK_BLOOM1 ? 1 : 8][SINK == KG_SINK_BLOOM1 ? 1 : KG_SKM_QCAP];
+    __shared__ u64 s_qocc[SINK == KG_SINK_BLOOM1 ? 1 : 8][SINK == KG_SINK_BLOOM1 ? 1 : KG_SKM_QCAP];
+    __shared__ u32 s_qcnt[SINK == KG_SINK_BLOOM1 ? 1 : 8][SINK == KG_SINK_BLOOM1 ? 1 : KG_SKM_QCAP];
     const u64 n_desc = a.seg_start[a.nseg];
     const u32 lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    const u32 lt = (1u << lane) - 1u;
     const KgKGeom g = kg_geom(a.k);
+    const u32 max_probe = (u32)(a.table.nslots < KG_MAX_PROBE ? a.table.nslots : KG_MAX_PROBE);
     KgConsume<W, SINK> sink;
     sink.init(a.table, a.bloom);
+    u32 qn = 0;                         // entries in this warp's queue (the same value in every lane)
+
+    // one probe for the lanes with `live`; counts what is decided, parks what is not
+    auto probe_round = [&](bool live, u64 (&key)[W], u64* p, u32 cnt, u64 occw) {
+        int st = -1;
+        if (live) {
+            st = kg_probe_step<W>(a.table, key, p);
+            if (st != KG_PROBE_SEARCH) {
+                sink.n_ins++;
+                sink.n_new += st == KG_PROBE_NEW ? 1u : 0u;
+                if (a.table.kaarme) atomicMax(p + 1 + W, ~occw);     // earliest occurrence (table starts zeroed)
+            } else if (++cnt >= max_probe || ((cnt & 255u) == 0 && kg_ld_u32(a.table.full_flag))) {
+                sink.full = true;                                    // probe budget exhausted: the table is full
+                st = KG_PROBE_FAIL;
+            }
+        }
+        const u32 park = __ballot_sync(0xffffffffu, st == KG_PROBE_SEARCH);
+        if (st == KG_PROBE_SEARCH) {
+            const u32 at = qn + __popc(park & lt);
+#pragma unroll
+            for (int x = 0; x < W; x++) s_qkey[warp][at][x] = key[x];
+            s_qptr[warp][at] = (u64)(uintptr_t)p;
+            s_qocc[warp][at] = occw;
+            s_qcnt[warp][at] = cnt;
+        }
+        qn += __popc(park);
+        __syncwarp();
+    };
+    auto drain = [&](u32 keep) {        // one probe for the youngest 32 entries, until at most `keep` are left
+        while (qn > keep) {
+            const u32 take = qn < 32u ? qn : 32u;
+            const u32 at = qn - take + lane;
+            const bool live = lane < take;
+            u64 key[W];
+            u64* p = nullptr;
+            u32 cnt = 0;
+            u64 occw = 0;
+            if (live) {
+#pragma unroll
+                for (int x = 0; x < W; x++) key[x] = s_qkey[warp][at][x];
+                p = (u64*)(uintptr_t)s_qptr[warp][at];
+                occw = s_qocc[warp][at];
+                cnt = s_qcnt[warp][at];
+            }
+            __syncwarp();
+            qn -= take;
+            probe_round(live, key, p, cnt, occw);
+        }
+    };
+
     for (;;) {
         // Persistent warps pull groups of 32 descriptors (a few hundred windows) from one global counter: whatever their
         // relative speed, the warps in flight work at the FRONT of the partition-major descriptor array, so the table
@@ -427,50 +490,71 @@ __global__ void __launch_bounds__(256) kg_skm_insert(KgSkmInsertArgs a) {
         const u32 per = (total + 31u) >> 5;
         u32 gi = lane * per;
         const u32 gend = min(total, gi + per);
+        u32 q = 0, e = 0, next = 0;
+        u64 dq = 0;
+        const u64* __restrict__ words = nullptr;
         if (gi < gend) {
-            u32 q = 0;                                  // descriptor holding window gi: largest q with excl[q] <= gi, n[q] > 0
+            // descriptor holding window gi: largest q with excl[q] <= gi (it has windows: excl[q + 1] > gi)
 #pragma unroll
             for (u32 s = 16; s; s >>= 1) if (s_excl[warp][q + s] <= gi) q += s;
-            u64 dq = s_desc[warp][q];
-            u32 e = KG_SKM_J0(dq) + (gi - s_excl[warp][q]);          // end position of window gi
-            u32 next = s_excl[warp][q + 1];                          // first window of the next descriptor
-            const u64* __restrict__ words = a.src->words[KG_SKM_SRC(dq)];
-            for (;;) {
+            dq = s_desc[warp][q];
+            e = KG_SKM_J0(dq) + (gi - s_excl[warp][q]);              // end position of window gi
+            next = s_excl[warp][q + 1];                              // first window of the next descriptor
+            words = a.src->words[KG_SKM_SRC(dq)];
+        }
+#pragma unroll 1
+        for (u32 it = 0; it < per; it++) {                           // the same trip count in every lane (collectives inside)
+            bool live = gi < gend;
+            u64 key[W];
+            u64* p = nullptr;
+            KgOcc occ; occ.word = ~0ULL;
+            if (live) {
                 KgKmerWindow<W> win;
                 kg_window_at<W>(words, e, g, win.f);
                 kg_revcomp<W>(win.f, win.r, g);
                 const bool fwd = kg_forward_is_canonical<W>(win);
-                u64 key[W];
 #pragma unroll
                 for (int x = 0; x < W; x++) key[x] = fwd ? win.f[x] : win.r[x];
+                const u64 h = kg_hash_key<W>(key);
                 const u32 part = KG_SKM_PART(dq);
                 if (SINK == KG_SINK_BLOOM1 || SINK == KG_SINK_BLOOM2) {
-                    sink.b_lo = __ldg(a.bpart_lo + part);
-                    sink.b_n = __ldg(a.bpart_lo + part + 1) - sink.b_lo;
+                    const u64 b_lo = __ldg(a.bpart_lo + part), b_n = __ldg(a.bpart_lo + part + 1) - b_lo;
+                    if (SINK == KG_SINK_BLOOM1) {
+                        kg_bloom_insert(a.bloom, h, kg_place(h, b_lo, b_n), sink.n_b1, sink.n_b2);
+                        live = false;
+                    } else if (!kg_bloom_admits(a.bloom, h, kg_place(h, b_lo, b_n))) {
+                        sink.n_rej++;
+                        live = false;
+                    }
                 }
-                if (SINK != KG_SINK_BLOOM1) {
-                    sink.t_lo = __ldg(a.part_lo + part);
-                    sink.t_n = __ldg(a.part_lo + part + 1) - sink.t_lo;
+                if (SINK != KG_SINK_BLOOM1 && live) {
+                    const u64 t_lo = __ldg(a.part_lo + part), t_n = __ldg(a.part_lo + part + 1) - t_lo;
+                    p = a.table.slots + kg_place(h, t_lo, t_n) * a.table.stride;
+                    if (a.table.kaarme) {
+                        const u32 srcr = KG_SKM_SRC(dq);
+                        const bool hp = e > KG_SKM_J0(dq) || KG_SKM_HP(dq);
+                        const u32 c_out = hp ? kg_base_at(words, e - a.k) : 0u;
+                        occ = kg_make_occ(((u64)srcr << 48) | (a.src->hdr[srcr][0] + (u64)e), hp, fwd, c_out);
+                    }
                 }
-                KgOcc occ; occ.word = ~0ULL;
-                if (SINK != KG_SINK_BLOOM1 && a.table.kaarme) {
-                    const u32 srcr = KG_SKM_SRC(dq);
-                    const bool hp = e > KG_SKM_J0(dq) || KG_SKM_HP(dq);
-                    const u32 c_out = hp ? kg_base_at(words, e - a.k) : 0u;
-                    occ = kg_make_occ(((u64)srcr << 48) | (a.src->hdr[srcr][0] + (u64)e), hp, fwd, c_out);
-                }
-                sink(key, kg_hash_key<W>(key), occ);
-                if (++gi == gend) break;
-                if (gi == next) {                                    // on to the next descriptor that holds windows
-                    do { q++; next = s_excl[warp][q + 1]; } while (next == gi);
-                    dq = s_desc[warp][q];
-                    e = KG_SKM_J0(dq);
-                    words = a.src->words[KG_SKM_SRC(dq)];
-                } else {
-                    e++;
+                // on to my next window
+                if (++gi < gend) {
+                    if (gi == next) {                                // next descriptor that holds windows
+                        do { q++; next = s_excl[warp][q + 1]; } while (next == gi);
+                        dq = s_desc[warp][q];
+                        e = KG_SKM_J0(dq);
+                        words = a.src->words[KG_SKM_SRC(dq)];
+                    } else {
+                        e++;
+                    }
                 }
             }
+            if (SINK != KG_SINK_BLOOM1) {
+                probe_round(live, key, p, 0u, occ.word);
+                if (qn > KG_SKM_QCAP - 32u) drain(KG_SKM_QCAP - 64u + 31u);    // keep room for the next round's 32
+            }
         }
+        if (SINK != KG_SINK_BLOOM1) drain(0u);
         __syncwarp();                                               // the group's shared arrays are reused by the next claim
     }
     if (SINK == KG_SINK_TABLE || SINK == KG_SINK_BLOOM2) {

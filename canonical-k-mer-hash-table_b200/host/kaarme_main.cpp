@@ -445,6 +445,18 @@ void json_pass(std::ostream& o, const char* name, const kg_pass_stats& s) {
 }
 
 // the product path needs `need` usable sm_100 devices; say so before any file is created
+// KAARME_TIMING=1: wall clock of the start-up stages on stderr (where does a small input spend its second?)
+static void stage_time(const char* what) {
+    static const bool on = getenv("KAARME_TIMING") != nullptr;
+    static const auto t0 = std::chrono::steady_clock::now();
+    static auto last = t0;
+    if (!on) return;
+    const auto now = std::chrono::steady_clock::now();
+    fprintf(stderr, "[timing] %-28s +%8.1f ms  (%8.1f ms)\n", what, std::chrono::duration<double, std::milli>(now - last).count(),
+            std::chrono::duration<double, std::milli>(now - t0).count());
+    last = now;
+}
+
 void require_devices(int need) {
     int have = 0;
     const int rc = kg_device_count(&have);
@@ -573,7 +585,9 @@ int main(int argc, char** argv) {
     std::vector<kg_compact_stats> compact_stats(world);
     std::vector<uint64_t> table_slots(world, 0);
     for (int r = 0; r < world; r++) { memset(&bloom_stats[r], 0, sizeof(kg_pass_stats)); memset(&count_stats[r], 0, sizeof(kg_pass_stats)); memset(&compact_stats[r], 0, sizeof(kg_compact_stats)); }
+    stage_time("arguments parsed");
     require_devices(args.device + world);   // before anything is created on disk
+    stage_time("device count");
     if (!args.dump_kaarme.empty() && (args.mode != KG_TABLE_KAARME || world != 1)) {
         std::cerr << "kaarme: --dump-kaarme needs -m 2 on one GPU\n";
         return 1;
@@ -617,9 +631,12 @@ int main(int argc, char** argv) {
                 std::exit(2);
             }
         }
+        if (rank == 0) stage_time("kg_create");
         if (world > 1) KG_CHECK(kg_comm_init(ctx, nccl_id, rank, world));
+        if (rank == 0) stage_time("kg_comm_init");
         uint8_t* bufs[nbufs] = {nullptr, nullptr, nullptr};
         for (int i = 0; i < nbufs; i++) KG_CHECK(kg_host_alloc(buf_bytes, (void**)&bufs[i]));
+        if (rank == 0) stage_time("pinned ring buffers");
         int fd = open(args.input.c_str(), O_RDONLY);
         const Slice sl = fmt.gz ? Slice{0, 0, 0, false} : make_slice(fd, fst.st_size, rank, world, (uint32_t)args.k, input_mode == KG_INPUT_FASTA);
         close(fd);
@@ -641,6 +658,7 @@ int main(int argc, char** argv) {
         barrier.wait();
         if (rank == 0) t_build0 = std::chrono::high_resolution_clock::now();
         KG_CHECK(kg_pass_begin(ctx, KG_PASS_COUNT));
+        if (rank == 0) stage_time("count pass begin (table)");
         kg_table_info(ctx, &table_slots[rank], nullptr, nullptr);
         if (rank == 0) {
             std::cout << (args.mode == 0 ? "Starting atomic flag basic hash table\n" : "Starting atomic variable pointer hash table\n");
@@ -648,6 +666,7 @@ int main(int argc, char** argv) {
         }
         feed_file(ctx, args.input, fmt.gz, bufs, nbufs, buf_bytes, sl, io_threads);
         KG_CHECK(kg_pass_end(ctx, &count_stats[rank]));
+        if (rank == 0) stage_time("count pass fed + ended");
         barrier.wait();                            // every shard's table is complete
         if (args.mode == KG_TABLE_KAARME) {        // every shard builds its own self-contained structure
             KG_CHECK(kg_compact(ctx, &compact_stats[rank]));
@@ -684,9 +703,10 @@ int main(int argc, char** argv) {
             }
         }
         barrier.wait();
-        if (rank == 0) t_write1 = std::chrono::high_resolution_clock::now();
+        if (rank == 0) { t_write1 = std::chrono::high_resolution_clock::now(); stage_time("export + write"); }
         for (int i = 0; i < nbufs; i++) kg_host_free(bufs[i]);
         kg_destroy(ctx);
+        if (rank == 0) stage_time("destroy");
     };
     if (world == 1) rank_main(0);
     else {
