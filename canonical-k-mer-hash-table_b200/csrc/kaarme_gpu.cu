@@ -160,6 +160,16 @@ static thread_local std::string g_err;
 
 // KG_TRACE=1: progress of the collective steps on stderr (which call does a hung multi-GPU run sit in?)
 static bool kg_trace_on() { static const bool on = getenv("KG_TRACE") != nullptr; return on; }
+static bool kg_trace_sync() { static const bool on = getenv("KG_TRACE") && atoi(getenv("KG_TRACE")) >= 2; return on; }
+// KG_TRACE=2: additionally wait for the stream after every step of a round (serialises everything; debugging only)
+#define KG_TRACE_SYNC(ctx, stream, what)                                                       \
+    do {                                                                                       \
+        if (kg_trace_sync()) {                                                                 \
+            KG_TRACE(ctx, "  ... %s queued", what);                                            \
+            cudaError_t e_ = cudaStreamSynchronize(stream);                                    \
+            KG_TRACE(ctx, "  ... %s done (%s)", what, cudaGetErrorString(e_));                 \
+        }                                                                                      \
+    } while (0)
 #define KG_TRACE(ctx, ...)                                                                     \
     do {                                                                                       \
         if (kg_trace_on()) {                                                                   \
@@ -564,6 +574,38 @@ extern "C" int kg_comm_unique_id(void* id_out) {
     return KG_OK;
 }
 
+// Load every kernel a round launches NOW (cudaFuncGetAttributes forces the load).  CUDA loads kernels lazily, at their
+// first launch, and loading may have to synchronise the whole process; with several GPUs driven by threads of ONE process
+// that first launch can come while another GPU's NCCL kernel spins waiting for this thread -- a deadlock (seen on
+// 2 B200s: `kaarme --gpus 2` hung in round 0 unless CUDA_MODULE_LOADING=EAGER).  After this, and one warm-up all-reduce,
+// nothing is loaded inside a round any more.
+template <int W>
+static void preload_insert(int occ) {
+    cudaFuncAttributes at;
+    if (occ >= 6) {
+        cudaFuncGetAttributes(&at, kg_skm_insert<W, KG_SINK_TABLE, 6>);
+        cudaFuncGetAttributes(&at, kg_skm_insert<W, KG_SINK_BLOOM1, 6>);
+        cudaFuncGetAttributes(&at, kg_skm_insert<W, KG_SINK_BLOOM2, 6>);
+    } else {
+        cudaFuncGetAttributes(&at, kg_skm_insert<W, KG_SINK_TABLE, 1>);
+        cudaFuncGetAttributes(&at, kg_skm_insert<W, KG_SINK_BLOOM1, 1>);
+        cudaFuncGetAttributes(&at, kg_skm_insert<W, KG_SINK_BLOOM2, 1>);
+    }
+}
+static void preload_round_kernels(kg_ctx* c) {
+    cudaFuncAttributes at;
+    cudaFuncGetAttributes(&at, kg_hdr_summary<true>); cudaFuncGetAttributes(&at, kg_hdr_summary<false>);
+    cudaFuncGetAttributes(&at, kg_tile_count<true, true>); cudaFuncGetAttributes(&at, kg_tile_count<true, false>);
+    cudaFuncGetAttributes(&at, kg_tile_count<false, true>); cudaFuncGetAttributes(&at, kg_tile_count<false, false>);
+    cudaFuncGetAttributes(&at, kg_tile_pack<true, true>); cudaFuncGetAttributes(&at, kg_tile_pack<true, false>);
+    cudaFuncGetAttributes(&at, kg_tile_pack<false, true>); cudaFuncGetAttributes(&at, kg_tile_pack<false, false>);
+    cudaFuncGetAttributes(&at, kg_lww_scan); cudaFuncGetAttributes(&at, kg_tile_scan);
+    cudaFuncGetAttributes(&at, kg_carry_save); cudaFuncGetAttributes(&at, kg_carry_restore);
+    cudaFuncGetAttributes(&at, kg_skm_scatter); cudaFuncGetAttributes(&at, kg_skm_pack_counts); cudaFuncGetAttributes(&at, kg_skm_segments);
+    KG_DISPATCH_W(c->W, preload_insert, c->insert_occ);
+    cudaGetLastError();
+}
+
 // What one rank tells the others about its two batch slots (all-gathered through NCCL inside kg_comm_init).
 struct KgPeerHandle {
     uint64_t magic, pid;
@@ -641,6 +683,10 @@ extern "C" int kg_comm_init(kg_ctx* c, const void* id, int rank, int world) {
         }
     }
     { int rc = publish_slot_tables(c); if (rc) return rc; }
+    preload_round_kernels(c);
+    // warm-up all-reduce: NCCL loads that kernel and sets up its channels here, where every rank is at the same point
+    KG_NCCL(c, kg_nccl().AllReduce(c->d_round, c->d_round + 6, 1, ncclUint32, ncclSum, c->comm, c->s_insert));
+    KG_CUDA(c, cudaStreamSynchronize(c->s_insert));
     KG_TRACE(c, "comm_init: done");
     return KG_OK;
 }
@@ -858,13 +904,16 @@ static int skm_round(kg_ctx* c, bool have_batch, bool want_sum) {
         KG_CUDA(c, cudaMemsetAsync(s.counts, 0, sizeof(u32) * (c->nb * KG_SKM_SUB + 1), c->s_compute));
     }
     KG_CUDA(c, cudaEventRecord(s.ev_ready, c->s_compute));
+    KG_TRACE_SYNC(c, c->s_compute, "parse + scatter");
     KG_CUDA(c, cudaStreamWaitEvent(c->s_insert, s.ev_ready, 0));
     if (world > 1) {
         KG_NCCL(c, kg_nccl().AllReduce(c->d_round + (have_batch ? 1 : 0), c->d_round + 4 + b, 1, ncclUint32, ncclSum, c->comm, c->s_insert));
+        KG_TRACE_SYNC(c, c->s_insert, "all-reduce");
         KG_CUDA(c, cudaEventRecord(c->slot[b ^ 1].ev_free, c->s_insert));
         if (want_sum) KG_CUDA(c, cudaMemcpyAsync(c->h_round_sum, c->d_round + 4 + b, sizeof(u32), cudaMemcpyDeviceToHost, c->s_insert));
         for (int r = 0; r < world; r++)
             if (r != me) KG_CUDA(c, cudaMemcpyAsync(s.r_buf[r], s.peer_slab[r], KG_SKM_META + c->skm_words_bytes, cudaMemcpyDefault, c->s_insert));
+        KG_TRACE_SYNC(c, c->s_insert, "pulls");
     }
     const u32 nseg = (u32)world * c->pl * KG_SKM_SUB + (u32)world;
     kg_skm_segments<<<1, 1024, 0, c->s_insert>>>(s.d_peers, (u32)world, (u32)me, c->pl, c->nb, c->skm_cap, s.d_seg_start, s.d_seg_ptr);
@@ -879,6 +928,7 @@ static int skm_round(kg_ctx* c, bool have_batch, bool want_sum) {
     c->ins_launches++;
     KG_DISPATCH_W(c->W, launch_skm_insert, c, a, current_sink(c));
     if (ib) cudaEventRecord(ib, c->s_insert);
+    KG_TRACE_SYNC(c, c->s_insert, "insert");
     if (world == 1) KG_CUDA(c, cudaEventRecord(s.ev_free, c->s_insert));
     c->round++;
     return KG_OK;

@@ -508,8 +508,23 @@ int decode_kaarme_file(const Args& args) {
 
 }  // namespace
 
+// CUDA initialises every visible device at the first runtime call (about a second on an 8-GPU box, most of a small
+// run's wall clock).  Unless the user has narrowed the set already, make only the GPUs this run uses visible; they are
+// then devices 0 .. gpus-1.
+static void narrow_visible_devices(Args& args) {
+    // several GPUs driven by threads of this one process: no lazy kernel loading while NCCL kernels may be spinning
+    // (the library also preloads what a round launches, kg_comm_init; this covers everything else)
+    if (args.gpus > 1) setenv("CUDA_MODULE_LOADING", "EAGER", 0);
+    if (getenv("CUDA_VISIBLE_DEVICES")) return;
+    std::string v;
+    for (int i = 0; i < std::max(1, args.gpus); i++) v += (i ? "," : "") + std::to_string(args.device + i);
+    setenv("CUDA_VISIBLE_DEVICES", v.c_str(), 1);
+    args.device = 0;
+}
+
 int main(int argc, char** argv) {
     Args args = parse_args(argc, argv);
+    narrow_visible_devices(args);
     if (args.from_kaarme) return decode_kaarme_file(args);
     Format fmt = file_format(args.input);
     if (fmt.ill_formed) {
