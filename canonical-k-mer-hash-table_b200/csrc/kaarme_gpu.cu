@@ -586,6 +586,10 @@ static void preload_insert(int occ) {
         cudaFuncGetAttributes(&at, kg_skm_insert<W, KG_SINK_TABLE, 6>);
         cudaFuncGetAttributes(&at, kg_skm_insert<W, KG_SINK_BLOOM1, 6>);
         cudaFuncGetAttributes(&at, kg_skm_insert<W, KG_SINK_BLOOM2, 6>);
+    } else if (occ == 5) {
+        cudaFuncGetAttributes(&at, kg_skm_insert<W, KG_SINK_TABLE, 5>);
+        cudaFuncGetAttributes(&at, kg_skm_insert<W, KG_SINK_BLOOM1, 5>);
+        cudaFuncGetAttributes(&at, kg_skm_insert<W, KG_SINK_BLOOM2, 5>);
     } else {
         cudaFuncGetAttributes(&at, kg_skm_insert<W, KG_SINK_TABLE, 1>);
         cudaFuncGetAttributes(&at, kg_skm_insert<W, KG_SINK_BLOOM1, 1>);
@@ -882,6 +886,7 @@ static void launch_skm_insert_b(kg_ctx* c, const KgSkmInsertArgs& a, int sink) {
 template <int W>
 static void launch_skm_insert(kg_ctx* c, const KgSkmInsertArgs& a, int sink) {
     if (c->insert_occ >= 6) launch_skm_insert_b<W, 6>(c, a, sink);
+    else if (c->insert_occ == 5) launch_skm_insert_b<W, 5>(c, a, sink);
     else launch_skm_insert_b<W, 1>(c, a, sink);
 }
 
@@ -921,6 +926,7 @@ static int skm_round(kg_ctx* c, bool have_batch, bool want_sum) {
     KG_CUDA(c, cudaMemsetAsync(c->d_work, 0, sizeof(u32), c->s_insert));
     KgSkmInsertArgs a;
     a.seg_start = s.d_seg_start; a.seg_ptr = s.d_seg_ptr; a.nseg = nseg; a.my_rank = (u32)me; a.src = s.d_src;
+    a.nparts = c->pl; a.segs_per_part = getenv("KG_NO_PREFETCH") ? 0u : (u32)world * KG_SKM_SUB;
     a.part_lo = c->d_part_lo; a.bpart_lo = c->d_bpart_lo; a.table = c->table; a.bloom = c->bloom; a.stats = c->d_stats;
     a.work = c->d_work; a.k = c->cfg.k;
     cudaEvent_t ia = next_ins_event(c), ib = next_ins_event(c);

@@ -83,6 +83,21 @@ __host__ __device__ inline void kg_window_at(const u64* __restrict__ words, u32 
     }
     f[0] &= g.topmask;
 }
+// the same from W + 1 packed words held in registers: wreg[i] = word (e >> 5) - i (a descriptor never crosses a packed
+// word, so all its windows use the same W + 1 words)
+template <int W>
+__host__ __device__ inline void kg_window_regs(const u64 (&wreg)[W + 1], u32 e, const KgKGeom& g, u64 (&f)[W]) {
+    const u32 j = (e & 31u) + 1u;
+#pragma unroll
+    for (int i = 0; i < W; i++) f[W - 1 - i] = ((wreg[i + 1] << (2u * j - 1u)) << 1) | (wreg[i] >> (64u - 2u * j));
+    f[0] &= g.topmask;
+}
+template <int W>
+__host__ __device__ inline void kg_load_window_words(const u64* __restrict__ words, u32 e, u64 (&wreg)[W + 1]) {
+    const u32 t = e >> 5;
+#pragma unroll
+    for (int i = 0; i <= W; i++) wreg[i] = (int)t - i >= 0 ? words[t - i] : 0ULL;
+}
 __host__ __device__ inline u32 kg_base_at(const u64* __restrict__ words, u32 pos) {
     return (u32)(words[pos >> 5] >> (62 - 2 * (pos & 31u))) & 3u;
 }
@@ -370,6 +385,7 @@ struct KgSkmInsertArgs {
     const u64* seg_start;               // [nseg + 1] logical index of the first descriptor of each segment
     const u64* const* seg_ptr;          // [nseg] where the segment's descriptors are (local, or a peer's slot over NVLink)
     u32 nseg;
+    u32 nparts, segs_per_part;          // the first nparts * segs_per_part segments are the partitions' regions, in table order
     u32 my_rank;                        // descriptors of another owner are skipped (overflow lists are not owner-sorted)
     const KgSkmSources* src;
     const u64* part_lo;                 // [pl + 1] first table slot of each partition
@@ -385,7 +401,8 @@ struct KgSkmInsertArgs {
 // k-mer takes 1.4 steps on average but 4+ for the unluckiest of 32 lanes; looping per window until every lane is done ran
 // the probe code at a third of a warp's width (45 % of this kernel's instructions).  Instead every window gets ONE probe
 // with the whole warp; what is not decided is parked -- key, next slot, probes so far, occurrence record -- and the queue is
-// drained 32 entries at a time, again one probe each at full width.
+// drained 32 entries at a time, again one probe each at full width.  The queue lives across the warp's groups (entries
+// hold absolute slot pointers); only the end of the kernel drains it to the last entry.
 #define KG_SKM_QCAP 64u
 
 template <int W, int SINK, int MINB>
@@ -472,6 +489,23 @@ __global__ void __launch_bounds__(256, MINB) kg_skm_insert(KgSkmInsertArgs a) {
             u32 hi = a.nseg;
             while (hi - seg > 1) { const u32 mid = (seg + hi) >> 1; if (a.seg_start[mid] <= first) seg = mid; else hi = mid; }
         }
+        // Prefetch into L2 the slice of the NEXT partition's table region that corresponds to this group's place in its
+        // own partition.  A batch touches every sector of a region about twice, so half of the probes would be first
+        // touches served from DRAM; by the time the walk reaches the next partition its region is L2-resident already.
+        if (SINK != KG_SINK_BLOOM1 && a.segs_per_part && seg < a.nparts * a.segs_per_part) {
+            const u32 part = seg / a.segs_per_part;
+            if (part + 1 < a.nparts) {
+                const u64 p0 = a.seg_start[part * a.segs_per_part], p1 = a.seg_start[(part + 1) * a.segs_per_part];
+                const u32 ngrp = (u32)((p1 - p0 + 31u) >> 5), j = (u32)((first - p0) >> 5);
+                const u64 s0 = __ldg(a.part_lo + part + 1), s1 = __ldg(a.part_lo + part + 2);
+                const u32 lines = (u32)(((s1 - s0) * a.table.stride * 8u + 127u) >> 7);      // 128-byte lines of the region
+                const u32 per_grp = lines / ngrp + 1u;
+                const char* base = (const char*)(a.table.slots + s0 * a.table.stride);
+                const u32 l1 = min(lines, (j + 1u) * per_grp);
+                for (u32 l = j * per_grp + lane; l < l1; l += 32u)
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(base + (u64)l * 128u));
+            }
+        }
         if (i < n_desc) {
             while (a.seg_start[seg + 1] <= i) seg++;  // (i < n_desc = seg_start[nseg]: stops inside the table)
             d = __ldcs(a.seg_ptr[seg] + (i - a.seg_start[seg]));
@@ -493,6 +527,17 @@ __global__ void __launch_bounds__(256, MINB) kg_skm_insert(KgSkmInsertArgs a) {
         u32 q = 0, e = 0, next = 0;
         u64 dq = 0;
         const u64* __restrict__ words = nullptr;
+        u64 wreg[W + 1];                                             // the packed words the current descriptor's windows use
+        u64 t_lo = 0, t_n = 0, b_lo = 0, b_n = 0;                    // its partition's slot range / Bloom block range
+        auto enter = [&]() {                                         // per-descriptor state (not per window)
+            words = a.src->words[KG_SKM_SRC(dq)];
+            kg_load_window_words<W>(words, e, wreg);
+            const u32 part = KG_SKM_PART(dq);
+            if (SINK != KG_SINK_BLOOM1) { t_lo = __ldg(a.part_lo + part); t_n = __ldg(a.part_lo + part + 1) - t_lo; }
+            if (SINK != KG_SINK_TABLE) { b_lo = __ldg(a.bpart_lo + part); b_n = __ldg(a.bpart_lo + part + 1) - b_lo; }
+        };
+#pragma unroll
+        for (int x = 0; x <= W; x++) wreg[x] = 0;
         if (gi < gend) {
             // descriptor holding window gi: largest q with excl[q] <= gi (it has windows: excl[q + 1] > gi)
 #pragma unroll
@@ -500,7 +545,7 @@ __global__ void __launch_bounds__(256, MINB) kg_skm_insert(KgSkmInsertArgs a) {
             dq = s_desc[warp][q];
             e = KG_SKM_J0(dq) + (gi - s_excl[warp][q]);              // end position of window gi
             next = s_excl[warp][q + 1];                              // first window of the next descriptor
-            words = a.src->words[KG_SKM_SRC(dq)];
+            enter();
         }
 #pragma unroll 1
         for (u32 it = 0; it < per; it++) {                           // the same trip count in every lane (collectives inside)
@@ -510,15 +555,13 @@ __global__ void __launch_bounds__(256, MINB) kg_skm_insert(KgSkmInsertArgs a) {
             KgOcc occ; occ.word = ~0ULL;
             if (live) {
                 KgKmerWindow<W> win;
-                kg_window_at<W>(words, e, g, win.f);
+                kg_window_regs<W>(wreg, e, g, win.f);
                 kg_revcomp<W>(win.f, win.r, g);
                 const bool fwd = kg_forward_is_canonical<W>(win);
 #pragma unroll
                 for (int x = 0; x < W; x++) key[x] = fwd ? win.f[x] : win.r[x];
                 const u64 h = kg_hash_key<W>(key);
-                const u32 part = KG_SKM_PART(dq);
                 if (SINK == KG_SINK_BLOOM1 || SINK == KG_SINK_BLOOM2) {
-                    const u64 b_lo = __ldg(a.bpart_lo + part), b_n = __ldg(a.bpart_lo + part + 1) - b_lo;
                     if (SINK == KG_SINK_BLOOM1) {
                         kg_bloom_insert(a.bloom, h, kg_place(h, b_lo, b_n), sink.n_b1, sink.n_b2);
                         live = false;
@@ -528,7 +571,6 @@ __global__ void __launch_bounds__(256, MINB) kg_skm_insert(KgSkmInsertArgs a) {
                     }
                 }
                 if (SINK != KG_SINK_BLOOM1 && live) {
-                    const u64 t_lo = __ldg(a.part_lo + part), t_n = __ldg(a.part_lo + part + 1) - t_lo;
                     p = a.table.slots + kg_place(h, t_lo, t_n) * a.table.stride;
                     if (a.table.kaarme) {
                         const u32 srcr = KG_SKM_SRC(dq);
@@ -543,7 +585,7 @@ __global__ void __launch_bounds__(256, MINB) kg_skm_insert(KgSkmInsertArgs a) {
                         do { q++; next = s_excl[warp][q + 1]; } while (next == gi);
                         dq = s_desc[warp][q];
                         e = KG_SKM_J0(dq);
-                        words = a.src->words[KG_SKM_SRC(dq)];
+                        enter();
                     } else {
                         e++;
                     }
@@ -554,9 +596,9 @@ __global__ void __launch_bounds__(256, MINB) kg_skm_insert(KgSkmInsertArgs a) {
                 if (qn > KG_SKM_QCAP - 32u) drain(KG_SKM_QCAP - 64u + 31u);    // keep room for the next round's 32
             }
         }
-        if (SINK != KG_SINK_BLOOM1) drain(0u);
         __syncwarp();                                               // the group's shared arrays are reused by the next claim
     }
+    if (SINK != KG_SINK_BLOOM1) drain(0u);                           // what is still parked when the work runs out
     if (SINK == KG_SINK_TABLE || SINK == KG_SINK_BLOOM2) {
         kg_block_add(sink.n_ins, &a.stats->inserted, sm);
         kg_block_add(sink.n_new, &a.stats->distinct, sm);

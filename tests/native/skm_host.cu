@@ -27,6 +27,10 @@ static bool check_windows(const std::vector<u64>& words, const std::vector<unsig
                 rc[W - 1 - pos / 32] |= (u64)(3u - bases[e - j]) << (2 * (pos % 32));
             }
             if (memcmp(f, want, sizeof f) != 0) { printf("FAIL: kg_window_at differs at end position %u\n", e); return false; }
+            u64 wreg[W + 1], f2[W];
+            kg_load_window_words<W>(words.data(), d.j0, wreg);       // loaded once per descriptor, as the insert kernel does
+            kg_window_regs<W>(wreg, e, g, f2);
+            if (memcmp(f2, want, sizeof f2) != 0) { printf("FAIL: kg_window_regs differs at end position %u\n", e); return false; }
             if (kg_key_bucket<W>(want, k, m, nb) != d.b || kg_key_bucket<W>(rc, k, m, nb) != d.b) {
                 printf("FAIL: kg_key_bucket differs from the scatter's bucket at end position %u\n", e);
                 return false;
