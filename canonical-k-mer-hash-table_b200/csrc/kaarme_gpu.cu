@@ -139,7 +139,9 @@ struct kg_ctx {
     cudaEvent_t ev_pass_ready = nullptr, ev_tail = nullptr;
     uint64_t round = 0;
     u32* d_work = nullptr;              // work counter of the persistent insert kernel
-    u32 insert_grid = 148 * 8;          // resident blocks of the persistent insert kernel (SMs x blocks/SM)
+    u32 sm_count = 148;
+    u32 insert_grid_auto = 0;           // resident blocks per SM of the insert kernel in use (occupancy API, first launch)
+    u32 insert_grid_env = 0;            // KG_INSERT_GRID: fewer blocks per SM than that (leaves room for the other stream)
     int insert_occ = 1;                 // KG_INSERT_OCC: register budget of kg_skm_insert (1 = unconstrained, 6 = six blocks per SM)
     // bit-exact emulation of the reference's double Bloom filter (kg_refbloom.cuh)
     bool ref_bloom = false;
@@ -436,8 +438,14 @@ extern "C" int kg_create(const kg_config* cfg, kg_ctx** out) {
     }
     kg_ctx* c = new kg_ctx();
     c->cfg = *cfg;
-    c->insert_grid = (u32)prop.multiProcessorCount * 8u;
-    if (const char* e = getenv("KG_INSERT_GRID")) c->insert_grid = (u32)atoi(e) * (u32)prop.multiProcessorCount;
+    c->sm_count = (u32)prop.multiProcessorCount;
+    if (const char* e = getenv("KG_INSERT_GRID")) c->insert_grid_env = (u32)atoi(e);
+    // register budget and resident blocks of the persistent insert kernel (profiles/r02_overlap_sweep.txt): two-word keys
+    // run best capped at 48 registers with 4 of the 5 possible blocks per SM -- the rest of the SM then takes blocks of
+    // the next batch's parse + bucketing kernels; wider keys would spill under that cap
+    c->W = (int)((cfg->k + 31) / 32);
+    c->insert_occ = c->W <= 2 ? 5 : 1;
+    c->insert_grid_env = c->W <= 2 ? 4 : 0;
     if (const char* e = getenv("KG_INSERT_OCC")) c->insert_occ = atoi(e);
     if (const char* e = getenv("KG_PARSE_TMA")) c->parse_tma = atoi(e) != 0;
     if (const char* e = getenv("KG_FEED_PREFETCH")) c->feed_prefetch = atoi(e) != 0;
@@ -457,7 +465,11 @@ extern "C" int kg_create(const kg_config* cfg, kg_ctx** out) {
     } while (0)
 
     KG_TRY(cudaSetDevice(cfg->device));
-    KG_TRY(cudaStreamCreateWithFlags(&c->s_compute, cudaStreamNonBlocking));
+    {   // parse + bucketing of the NEXT batch get the SM slots the persistent insert leaves free: higher priority
+        int lo = 0, hi = 0;
+        cudaDeviceGetStreamPriorityRange(&lo, &hi);
+        KG_TRY(cudaStreamCreateWithPriority(&c->s_compute, cudaStreamNonBlocking, hi));
+    }
     KG_TRY(cudaStreamCreateWithFlags(&c->s_copy, cudaStreamNonBlocking));
     for (int i = 0; i < 2; i++) {
         KG_TRY(cudaMalloc(&c->d_raw[i], c->batch_bytes));
@@ -872,7 +884,18 @@ static int current_sink(const kg_ctx* c) {
 
 template <int W, int MINB>
 static void launch_skm_insert_b(kg_ctx* c, const KgSkmInsertArgs& a, int sink) {
-    const u32 grid = c->insert_grid;     // persistent: SMs x resident blocks
+    // Persistent kernel: exactly as many blocks as can be resident (SMs x occupancy), or fewer per SM when KG_INSERT_GRID
+    // says so.  Never more: blocks of this grid that wait for a slot are served before the blocks of the NEXT batch's
+    // parse / bucketing kernels on the other stream, which would then never run beside the insert.
+    if (!c->insert_grid_auto) {
+        int per_sm = 0;
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kg_skm_insert<W, KG_SINK_TABLE, MINB>, 256, 0);
+        if (per_sm < 1) per_sm = 1;
+        c->insert_grid_auto = (u32)per_sm;
+    }
+    u32 per_sm = c->insert_grid_auto;
+    if (c->insert_grid_env && c->insert_grid_env < per_sm) per_sm = c->insert_grid_env;
+    const u32 grid = c->sm_count * per_sm;
     switch (sink) {
         case KG_SINK_TABLE: kg_skm_insert<W, KG_SINK_TABLE, MINB><<<grid, 256, 0, c->s_insert>>>(a); break;
         case KG_SINK_BLOOM1: kg_skm_insert<W, KG_SINK_BLOOM1, MINB><<<grid, 256, 0, c->s_insert>>>(a); break;

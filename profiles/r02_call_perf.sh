@@ -19,8 +19,8 @@ PY
 EXTRA=""
 run occ1 KG_INSERT_OCC=1
 run occ5 KG_INSERT_OCC=5
-run occ5_noprefetch KG_INSERT_OCC=5 KG_NO_PREFETCH=1
-run occ6 KG_INSERT_OCC=6
+run occ1_noprefetch KG_INSERT_OCC=1 KG_NO_PREFETCH=1
+run occ5_noprefetch2 KG_INSERT_OCC=5 KG_NO_PREFETCH=1
 EXTRA="--batch-mb 1024"
 run occ5_batch1024 KG_INSERT_OCC=5
 run occ1_batch1024 KG_INSERT_OCC=1

@@ -37,10 +37,15 @@ def main():
     torch.cuda.set_device(local)
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     failures, results = 0, []
-    for k, use_bloom, uneven, npart, mode in CASES:
+    cases = CASES
+    if os.environ.get("KAARME_MULTIGPU_CASES"):                       # e.g. "0,3,8": a subset (box time on 8 GPUs is dear)
+        cases = [CASES[int(i)] for i in os.environ["KAARME_MULTIGPU_CASES"].split(",")]
+    for k, use_bloom, uneven, npart, mode in cases:
         rng = np.random.default_rng(1234 + k)
         data = make_fasta(rng, 200000, 600, 2000, wrap=80, err=0.01, n_rate=0.0003)
-        truth = oracle.count(data, k)
+        truth = oracle.count(data, k) if rank == 0 else None          # the checker runs on rank 0 only
+        n_distinct = [truth.n if rank == 0 else None]
+        dist.broadcast_object_list(n_distinct, src=0)
         # uneven: rank 0 gets 3/4 of the file, so ranks feed different numbers of batches
         if uneven:
             cuts = [0] + [len(data) * 3 // 4 + (len(data) // 4) * i // (world - 1) for i in range(world)]
@@ -49,7 +54,7 @@ def main():
         cuts[-1] = len(data)
         lo, hi = cuts[rank], cuts[rank + 1]
         ctx_lo, in_hdr = K.slice_context(data, lo, k)
-        c = kg.Counter(k=k, table_mode=mode, min_slots=2_000_000, use_bloom=use_bloom, expected_unique=truth.n, fpr=0.01,
+        c = kg.Counter(k=k, table_mode=mode, min_slots=2_000_000, use_bloom=use_bloom, expected_unique=n_distinct[0], fpr=0.01,
                        device=local, rank=rank, world=world, batch_bytes=1 << 20, partitions=npart)
         uid = [kg.comm_unique_id() if rank == 0 else None]
         dist.broadcast_object_list(uid, src=0)

@@ -24,7 +24,10 @@ def n_gpus():
 
 def worlds():
     n = n_gpus()
-    return [w for w in (2, 4, 8) if w <= n]
+    ws = [w for w in (2, 4, 8) if w <= n]
+    if os.environ.get("KAARME_MULTIGPU_WORLDS"):                       # e.g. "8": only that many ranks (box time on 8 GPUs is dear)
+        ws = [w for w in ws if str(w) in os.environ["KAARME_MULTIGPU_WORLDS"].split(",")]
+    return ws
 
 
 def test_sharded_counts_equal_single_table_counts():
@@ -34,13 +37,14 @@ def test_sharded_counts_equal_single_table_counts():
     for i, w in enumerate(ws):
         p = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={w}",
                             "--master-addr", "127.0.0.1", "--master-port", str(29611 + i), os.path.join(ROOT, "tests", "multigpu_worker.py")],
-                           stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=900)
+                           stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=600)
         lines = [x for x in p.stdout.splitlines() if x.startswith("multigpu ")]
         print("\n".join(lines))
         res = [x for x in p.stdout.splitlines() if x.startswith("MULTIGPU_RESULT ")]
         assert p.returncode == 0 and res, p.stdout[-4000:]
         r = json.loads(res[-1][len("MULTIGPU_RESULT "):])
-        assert r["world"] == w and r["failures"] == 0 and len(r["cases"]) >= 12 and all(c["ok"] for c in r["cases"])
+        want = len(os.environ["KAARME_MULTIGPU_CASES"].split(",")) if os.environ.get("KAARME_MULTIGPU_CASES") else 12
+        assert r["world"] == w and r["failures"] == 0 and len(r["cases"]) >= want and all(c["ok"] for c in r["cases"])
 
 
 @pytest.mark.parametrize("k,mode,extra", [(21, 0, ["-s", "400000"]), (51, 0, ["-s", "400000"]), (127, 0, ["-s", "400000"]),
@@ -56,7 +60,7 @@ def test_cli_gpus_n_equals_one_gpu(k, mode, extra, tmp_path):
     for w in [1] + ws:
         out = tmp_path / f"o{w}.txt"
         p = subprocess.run([EXE, inp, str(k), "-m", str(mode), "-a", "2", "-t", "8", "--gpus", str(w), "--batch-mb", "1", "-o", str(out)] + extra,
-                           stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=300)
+                           stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=90)
         assert p.returncode == 0, p.stdout[-2000:] + p.stderr[-2000:]
         outs[w] = sorted(open(out, "rb").read().splitlines())
         if mode == 2 and w > 1:
