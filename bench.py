@@ -135,9 +135,23 @@ def cpu_port_run(sample_bytes, k):
     return time.perf_counter() - t0, c.total_windows
 
 
-def reference_sample(workload, k, scale, torch, bench_data, dev):
-    """the sample every reference step counts: REF_FRACTION of the workload, same coverage -> (path, meta)"""
-    fasta, meta = bench_data.make_config(workload, dev, scale=scale * REF_FRACTION)
+def reference_fraction(workload, scale, bench_data, threads):
+    """about REF_FRACTION of the workload, rounded so that the sample is a whole number of 10 MiB chunks per worker: the
+    reference's parallelism is one chunk per worker at a time (parallel_parser.hpp:834-843), and a sample that leaves
+    workers idle in its last wave would understate it"""
+    c = bench_data.CONFIGS[workload]
+    full_bytes = c["G"] * scale * c["cov"] * (1.0 + 1.0 / c["wrap"] if c["wrap"] else 1.0 + 12.0 / c["L"])
+    workers = max(1, threads - 2)
+    waves = max(1, round(REF_FRACTION * full_bytes / (10 << 20) / workers))
+    return min(1.0, waves * workers * (10 << 20) * 0.999 / full_bytes)
+
+
+def reference_sample(workload, k, scale, torch, bench_data, dev, threads=None):
+    """the sample every reference step counts: ~REF_FRACTION of the workload, same coverage -> (path, meta)"""
+    threads = threads or max(3, min(64, os.cpu_count() or 3))
+    frac = reference_fraction(workload, scale, bench_data, threads)
+    fasta, meta = bench_data.make_config(workload, dev, scale=scale * frac)
+    meta["fraction"] = frac
     path = f"/dev/shm/kaarme_bench_ref_{os.getpid()}.fasta"
     with open(path, "wb") as f:
         f.write(fasta.cpu().numpy().tobytes())
@@ -148,7 +162,7 @@ def reference_sample(workload, k, scale, torch, bench_data, dev):
 
 
 def sample_string(meta, k):
-    return (f"{REF_FRACTION:g} of the workload at the same coverage: {meta['G']} bp genome, {meta['cov']}x of {meta['L']} bp reads "
+    return (f"{meta['fraction']:.3f} of the workload at the same coverage (whole 10 MiB chunks per worker): {meta['G']} bp genome, {meta['cov']}x of {meta['L']} bp reads "
             f"({meta['n_reads']} reads, {meta['path_bytes']} bytes, {meta['input_kmers']} input k-mers), -m 0 -s {meta['slots']}")
 
 

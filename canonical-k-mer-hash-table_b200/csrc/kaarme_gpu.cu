@@ -949,7 +949,9 @@ static int skm_round(kg_ctx* c, bool have_batch, bool want_sum) {
     KG_CUDA(c, cudaMemsetAsync(c->d_work, 0, sizeof(u32), c->s_insert));
     KgSkmInsertArgs a;
     a.seg_start = s.d_seg_start; a.seg_ptr = s.d_seg_ptr; a.nseg = nseg; a.my_rank = (u32)me; a.src = s.d_src;
-    a.nparts = c->pl; a.segs_per_part = getenv("KG_NO_PREFETCH") ? 0u : (u32)world * KG_SKM_SUB;
+    // L2 prefetch of the next partition's table region: measured without effect (profiles/r02_insert_variants.txt: the
+    // hit rate does not move, DRAM reads grow by what was prefetched), so it is off unless KG_PREFETCH=1
+    a.nparts = c->pl; a.segs_per_part = getenv("KG_PREFETCH") ? (u32)world * KG_SKM_SUB : 0u;
     a.part_lo = c->d_part_lo; a.bpart_lo = c->d_bpart_lo; a.table = c->table; a.bloom = c->bloom; a.stats = c->d_stats;
     a.work = c->d_work; a.k = c->cfg.k;
     cudaEvent_t ia = next_ins_event(c), ib = next_ins_event(c);

@@ -51,7 +51,9 @@ def test_sharded_counts_equal_single_table_counts():
                                           (51, 2, ["-s", "400000"]), (51, 2, ["-b", "-u", "200000"])])
 def test_cli_gpus_n_equals_one_gpu(k, mode, extra, tmp_path):
     """`kaarme --gpus N` (one host thread per GPU in ONE process: peer access instead of IPC) writes the same lines as
-    one GPU, in -m 0 and in the default -m 2 (per-shard Kaarme structures decoded on export)"""
+    one GPU, in -m 0 and in the default -m 2 (per-shard Kaarme structures decoded on export).  Green on 2 B200s; on the
+    8-GPU box the in-process start-up (eager kernel loading in eight contexts) did not finish within 90 s, hence the
+    long limit above two GPUs -- the one-process-per-GPU path (the worker above, bench.py) is the measured one"""
     ws = worlds()
     if not ws:
         pytest.skip("needs at least two B200s")
@@ -60,7 +62,7 @@ def test_cli_gpus_n_equals_one_gpu(k, mode, extra, tmp_path):
     for w in [1] + ws:
         out = tmp_path / f"o{w}.txt"
         p = subprocess.run([EXE, inp, str(k), "-m", str(mode), "-a", "2", "-t", "8", "--gpus", str(w), "--batch-mb", "1", "-o", str(out)] + extra,
-                           stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=90)
+                           stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=90 if w <= 2 else 600)
         assert p.returncode == 0, p.stdout[-2000:] + p.stderr[-2000:]
         outs[w] = sorted(open(out, "rb").read().splitlines())
         if mode == 2 and w > 1:
