@@ -402,6 +402,22 @@ def test_partition_overflow_falls_back_to_direct_insert(oracle):
 
 
 # ---- file-level mirrors of the reference functors (parallel_parser.hpp:229,1181,1577,2255) ---------------------------
+@pytest.mark.parametrize("k,mode", [(127, K.TABLE_PLAIN), (200, K.TABLE_PLAIN), (51, K.TABLE_KAARME), (97, K.TABLE_KAARME)])
+@pytest.mark.parametrize("partitions", [1, 8])
+def test_contended_generic_slots(oracle, k, mode, partitions):
+    """a handful of distinct multi-word k-mers hammered by every block at once (the same short read, 60 000 times): the
+    generic slot protocol (CAS-claim, key words, release-publish; acquire on the reader's side; parked probes on the
+    bucketed path) must neither split a k-mer over two slots nor lose an occurrence -- distinct and counts == oracle"""
+    rng = np.random.default_rng(k)
+    read = "".join("ACGT"[x] for x in rng.integers(0, 4, k + 40))
+    data = b"".join(f">r{i}\n{read}\n".encode() for i in range(4)) * 15000
+    want = oracle.count(data, k)
+    assert want.n <= 41 and want.counts.max() == 60000
+    keys, counts, st = gpu_count(data, k, table_mode=mode, slots=5000, partitions=partitions, batch_bytes=1 << 20)
+    assert st["distinct"] == want.n
+    assert_same(keys, counts, want)
+
+
 @pytest.mark.parametrize("fn,mode,bloom", [("parse_input_atomic_flag", 0, False), ("parse_input_pointer_atomic_variable", 2, False),
                                            ("parse_input_atomic_flag_BF", 0, True), ("parse_input_pointer_atomic_variable_BF", 2, True)])
 def test_functor_mirrors(tmp_path, fn, mode, bloom):
