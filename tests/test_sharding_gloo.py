@@ -1,6 +1,7 @@
 """N > 1 host logic on CPU: two gloo ranks each take a byte range of one FASTA, repair the cut with
 slice_context (k-1 bases of context + header state), count their range with the oracle, and the merged result
-must equal the whole-file count.  (The device exchange itself needs >= 2 GPUs: tests/multigpu_check.py.)"""
+must equal the whole-file count; and the round protocol of the device exchange (csrc/kaarme_gpu.cu skm_round /
+kg_pass_end) modelled with gloo all-reduces.  (The device exchange itself needs >= 2 GPUs: tests/test_gpu_multigpu.py.)"""
 import importlib
 import os
 import subprocess
@@ -95,3 +96,47 @@ def test_slice_context_cuts(oracle, cut_in):
     a = oracle.count(data[ctx_lo:], k, oracle.FASTA, hdr)
     b = oracle.count(data[ctx_lo:pos], k, oracle.FASTA, hdr)
     assert a.total_windows - b.total_windows == whole.total_windows - left.total_windows
+
+
+ROUNDS = textwrap.dedent("""
+    # Model of the round protocol of the sharded path (csrc/kaarme_gpu.cu: skm_round, kg_pass_end): every round is one
+    # all-reduce of "I have a batch"; a rank that has fed its last batch keeps taking part (contributing 0) until a round
+    # whose sum is 0.  Slot b = round & 1 of a rank may be rewritten for round j + 2 only after the all-reduce of round
+    # j + 1, which every rank enters after its insert of round j (the peers read the slot in place during that insert).
+    import sys
+    import torch, torch.distributed as dist
+    dist.init_process_group("gloo")
+    rank, world = dist.get_rank(), dist.get_world_size()
+    batches = {batches}[rank]
+    rounds, inserted_upto, log = 0, -1, []
+    while True:
+        have = 1 if rounds < batches else 0
+        # (scatter of round `rounds` into slot rounds & 1 happens here: the slot's previous user was round - 2)
+        t = torch.tensor([have, inserted_upto], dtype=torch.int64)
+        s = t.clone(); dist.all_reduce(s, op=dist.ReduceOp.SUM)
+        m = t.clone(); dist.all_reduce(m, op=dist.ReduceOp.MIN)
+        # entering this all-reduce, every rank had finished the insert of round - 1: so slot (rounds - 1) & 1 is free
+        assert int(m[1]) == rounds - 1, (rounds, int(m[1]))
+        inserted_upto = rounds                      # insert of this round (reads the peers' slot `rounds & 1`)
+        log.append(int(s[0]))
+        rounds += 1
+        if int(s[0]) == 0:
+            break
+    want = max({batches}) + 1
+    assert rounds == want, (rank, rounds, want)
+    assert log[:-1] == [sum(1 for b in {batches} if r < b) for r in range(want - 1)]
+    print("ROUNDS_OK", rank, rounds)
+    dist.destroy_process_group()
+""")
+
+
+@pytest.mark.parametrize("batches", [[3, 3], [5, 2], [0, 4], [0, 0], [1, 7]])
+def test_round_protocol_terminates_together(tmp_path, batches):
+    """ranks that feed different numbers of batches leave the pass after the same number of rounds (the first round in
+    which nobody had a batch), and a slot is never rewritten before every rank has finished reading it"""
+    script = tmp_path / "rounds.py"
+    script.write_text(ROUNDS.format(batches=batches))
+    p = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+                        "--master-addr", "127.0.0.1", "--master-port", str(29650 + sum(batches)), str(script)],
+                       stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=300)
+    assert p.returncode == 0 and p.stdout.count("ROUNDS_OK") == 2, p.stdout[-3000:]
