@@ -660,6 +660,7 @@ int main(int argc, char** argv) {
             barrier.wait();
             if (rank == 0) { std::cout << "Starting parallel bloom filtering\n"; t_bloom0 = std::chrono::high_resolution_clock::now(); }  // parallel_parser.hpp:2689
             KG_CHECK(kg_pass_begin(ctx, KG_PASS_BLOOM));
+            barrier.wait();   // (see the count pass below)
             feed_file(ctx, args.input, fmt.gz, bufs, nbufs, buf_bytes, sl, io_threads);
             KG_CHECK(kg_pass_end(ctx, &bloom_stats[rank]));
             barrier.wait();
@@ -673,6 +674,10 @@ int main(int argc, char** argv) {
         barrier.wait();
         if (rank == 0) t_build0 = std::chrono::high_resolution_clock::now();
         KG_CHECK(kg_pass_begin(ctx, KG_PASS_COUNT));
+        // All contexts of this process allocate (the table!) before any of them feeds: with peer access enabled between
+        // the GPUs a cudaMalloc has to update the peers' mappings, and would wait for ever on a peer whose NCCL kernel
+        // is already spinning for this thread's batch.
+        barrier.wait();
         if (rank == 0) stage_time("count pass begin (table)");
         kg_table_info(ctx, &table_slots[rank], nullptr, nullptr);
         if (rank == 0) {

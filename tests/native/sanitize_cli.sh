@@ -19,7 +19,7 @@ for san in address,undefined thread; do
 $G/g5_long.fasta 51 -m 0 -a 2 -t 8 -o $d/o.txt --gpus 4 -b -u 100000 -f 0.01
 $G/g2_reads.fa 21 -a 2 -t 6 -s 200000 -o $d/o.txt --dump-kaarme $d/d.kaarme
 $d/d.kaarme 21 --from-kaarme -a 2 -o $d/o2.txt
-$G/g1_multiline.fasta 127 -m 0 -a 1 -s 200000 -o $d/o.txt --host-format --gpus 3 --peer-exchange
+$G/g1_multiline.fasta 127 -m 0 -a 1 -s 200000 -o $d/o.txt --host-format --gpus 3
 $G/g3_plain.txt 21 -m 0 -a 1 -s 200000 -o $d/o.txt --gpus 8
 ARGS
 done
