@@ -302,7 +302,8 @@ __global__ void __launch_bounds__(256) kg_export_kernel(KgTable table, u64 slot_
         if (W == 2 && table.packed_tb) {
             pk0 = p[0] & ((1ULL << table.packed_tb) - 1);
             pk1 = p[1];
-            n = (u32)(p[0] >> table.packed_tb);
+            const u64 n64 = p[0] >> table.packed_tb;             // up to 62 bits wide: clamp, do not truncate
+            n = n64 > 0xFFFFFFFEULL ? 0xFFFFFFFEu : (u32)n64;
         } else {
             n = (u32)p[0];
         }
