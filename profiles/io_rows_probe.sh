@@ -21,10 +21,10 @@ run() { # label, exe, args...
 }
 # reader-bound: 610 MB of FASTA, nothing written (-a 1000)
 run "new  read+count 610MB" $PKG/kaarme /dev/shm/g30.fasta 51 -m 0 -s 50000000 -a 1000 -t 16 -o /dev/shm/o.txt
-run "prev read+count 610MB" $PKG/kaarme_prev /dev/shm/g30.fasta 51 -m 0 -s 50000000 -a 1000 -t 16 -o /dev/shm/o.txt
+[ -x $PKG/kaarme_prev ] && run "prev read+count 610MB" $PKG/kaarme_prev /dev/shm/g30.fasta 51 -m 0 -s 50000000 -a 1000 -t 16 -o /dev/shm/o.txt
 run "new  read+count 610MB (2nd)" $PKG/kaarme /dev/shm/g30.fasta 51 -m 0 -s 50000000 -a 1000 -t 16 -o /dev/shm/o.txt
 # writer-bound: 20 M lines (1.1 GB of text)
 run "new  gpu-format 20M lines" $PKG/kaarme /dev/shm/g.fasta 51 -m 0 -s 50000000 -a 1 -t 16 -o /dev/shm/o.txt
 run "new  host-format 20M lines" $PKG/kaarme /dev/shm/g.fasta 51 -m 0 -s 50000000 -a 1 -t 16 -o /dev/shm/o.txt --host-format
-run "prev host-format 20M lines" $PKG/kaarme_prev /dev/shm/g.fasta 51 -m 0 -s 50000000 -a 1 -t 16 -o /dev/shm/o.txt
+[ -x $PKG/kaarme_prev ] && run "prev host-format 20M lines" $PKG/kaarme_prev /dev/shm/g.fasta 51 -m 0 -s 50000000 -a 1 -t 16 -o /dev/shm/o.txt
 rm -f /dev/shm/g.fasta /dev/shm/g30.fasta /dev/shm/fx.txt
