@@ -152,9 +152,21 @@ def reference_sample(workload, k, scale, torch, bench_data, dev, threads=None):
     frac = reference_fraction(workload, scale, bench_data, threads)
     fasta, meta = bench_data.make_config(workload, dev, scale=scale * frac)
     meta["fraction"] = frac
-    path = f"/dev/shm/kaarme_bench_ref_{os.getpid()}.fasta"
-    with open(path, "wb") as f:
-        f.write(fasta.cpu().numpy().tobytes())
+    data = fasta.cpu().numpy().tobytes()
+    path = None
+    for d in ("/dev/shm", "/tmp"):                     # RAM-backed if there is room, else local disk
+        try:
+            path = os.path.join(d, f"kaarme_bench_ref_{os.getpid()}.fasta")
+            with open(path, "wb") as f:
+                f.write(data)
+            break
+        except OSError:
+            if path and os.path.exists(path):
+                os.remove(path)
+            path = None
+    if path is None:
+        raise RuntimeError("no room for the reference sample in /dev/shm or /tmp")
+    del data
     meta["input_kmers"] = meta["n_reads"] * (meta["L"] - k + 1)
     meta["path_bytes"] = int(fasta.numel())
     del fasta
