@@ -41,6 +41,12 @@
 #define KG_DEFAULT_BATCH (128ull << 20)
 #define KG_MAX_BATCH (1ull << 30)
 
+// the slot header must hold the dense descriptor counts of the largest bucket set, and the segment table one entry per
+// (partition, sender, sub-region) plus one overflow list per sender
+static_assert(64 + 4 * ((size_t)KG_MAX_BUCKETS * KG_SKM_SUB + 1) <= KG_SKM_META, "KG_SKM_META too small for the descriptor counts");
+static_assert((size_t)KG_MAX_BUCKETS * KG_SKM_SUB + KG_MAX_WORLD <= KG_SKM_MAXSEG, "KG_SKM_MAXSEG too small");
+static_assert(KG_MAX_BUCKETS <= 1024 && KG_MAX_WORLD <= 64, "descriptor fields: 10 bits of partition, 6 bits of owner / sender");
+
 // One of the two batch slots of the minimizer-bucketed path.  A slot is ONE device allocation
 //   [ header 64 B | descriptor counts | pad to KG_SKM_META | packed 2-bit words of the batch | descriptor regions + overflow list ]
 // so that a peer can map it with one IPC handle and pull header + counts + words with one copy.
