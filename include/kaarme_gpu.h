@@ -164,7 +164,10 @@ int kg_comm_init(kg_ctx* ctx, const void* id, int rank, int world);    /* collec
 
 /* ---- passes ------------------------------------------------------------------------------------ */
 /* KG_PASS_BLOOM: clears the filters.  KG_PASS_COUNT: allocates and clears the table with
- * next_prime3mod4(min_slots) slots, or next_prime3mod4(2*new_in_second) after a Bloom pass.         */
+ * next_prime3mod4(min_slots) slots, or next_prime3mod4(2*new_in_second) after a Bloom pass.
+ * Several contexts in ONE process (a host thread per GPU): let every context return from kg_pass_begin
+ * before any of them feeds -- it allocates, and an allocation must not wait on a peer whose collective
+ * is already in flight.                                                        */
 int kg_pass_begin(kg_ctx* ctx, int pass);
 /* Start an independent byte stream (a file, or one rank's slice of it). starts_in_header mirrors
  * text_chunk::broken_header (text_reader.h:22).                                                    */
